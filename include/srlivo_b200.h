@@ -1,0 +1,202 @@
+/*
+ * srlivo_b200.h — C ABI of the B200-native LIO scan-matching hot path of SR-LIVO.
+ *
+ * The reference (ZikangYuan/sr_livo) has no plugin/FFI layer: the path is a set of member
+ * functions of `class lioOptimization` (include/lioOptimization.h:334-353) operating on
+ * `voxelHashMap` (include/cloudMap.h:171).  This header is the seam a maintainer binds to
+ * (see INTEGRATION.md): each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no Eigen, no exceptions, no torch types.
+ *   - quaternions are (x, y, z, w) = Eigen::Quaterniond::coeffs() order; 3x3 matrices row-major.
+ *   - the library owns all device memory behind opaque handles; the caller owns every host
+ *     pointer it passes; nothing is retained past a call except inside srl_map / srl_sweep.
+ *   - one srl_ctx per host thread / GPU; calls on a ctx are serialised by the caller
+ *     (the reference hot path is single-threaded: src/lioOptimization.cpp:1596-1604).
+ *   - every function returns an srl_status; srl_last_error(ctx) gives the text.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     SRL_CUDA_ERROR.
+ */
+#ifndef SRLIVO_B200_H
+#define SRLIVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRL_ABI_VERSION 1
+
+typedef enum srl_status {
+    SRL_OK = 0,
+    SRL_TOO_FEW_RESIDUALS = 1, /* optimizeSummary.success=false (src/optimize.cpp:110-123); num_residuals still filled */
+    SRL_NAN_PLANARITY = 2,     /* the reference throws std::runtime_error("error") (src/optimize.cpp:348-350) */
+    SRL_CUDA_ERROR = 3,
+    SRL_BAD_ARG = 4,
+    SRL_MAP_FULL = 5,          /* more voxels than srl_map_create's max_voxels */
+    SRL_SINGULAR = 6,          /* a 17x17 inverse failed (src/optimize.cpp:234,237) */
+    SRL_COMM_ERROR = 7
+} srl_status;
+
+typedef struct srl_ctx srl_ctx;     /* device + stream + scratch */
+typedef struct srl_map srl_map;     /* HBM-resident voxelHashMap (include/cloudMap.h:171) */
+typedef struct srl_sweep srl_sweep; /* device-resident keypoints of one reconstructed sweep */
+
+/* icpOptions fields read by the path (include/parameters.h:8-56, config/r3live.yaml:57-69),
+ * plus lioOptimization::laser_point_cov (src/lioOptimization.cpp:364) and the frame id that
+ * selects init-mode behaviour (src/optimize.cpp:21-23,135). */
+typedef struct srl_icp_params {
+    double size_voxel_map;
+    double power_planarity;
+    double max_dist_to_plane_icp;
+    double weight_alpha;
+    double weight_neighborhood;
+    double threshold_orientation_norm; /* degrees */
+    double threshold_translation_norm; /* metres */
+    double laser_point_cov;
+    int32_t voxel_neighborhood;        /* 1 or 2 */
+    int32_t min_number_neighbors;      /* <= max_number_neighbors */
+    int32_t max_number_neighbors;      /* <= 32 */
+    int32_t threshold_voxel_occupancy;
+    int32_t max_num_residuals;         /* cap, keypoint order (src/optimize.cpp:107) */
+    int32_t num_iters_icp;
+    int32_t init_num_frames;
+    int32_t frame_id;
+} srl_icp_params;
+
+void srl_icp_params_r3live(srl_icp_params* p); /* config/r3live.yaml values, frame_id = 100 */
+
+/* eskfEstimator state (src/eskfEstimator.cpp:3-21) */
+typedef struct srl_eskf_state {
+    double p[3];
+    double q[4];
+    double v[3];
+    double ba[3];
+    double bg[3];
+    double g[3];
+    double cov[17 * 17];
+} srl_eskf_state;
+
+/* the per-pass pose inputs of buildPlaneResiduals (src/optimize.cpp:25-28,38,49,83) */
+typedef struct srl_frame {
+    double q_cur[4];  /* p_frame->p_state->rotation */
+    double t_cur[3];  /* p_frame->p_state->translation */
+    double t_last[3]; /* all_cloud_frame[id-1]->p_state->translation */
+    double R_il[9];   /* R_imu_lidar */
+    double t_il[3];   /* t_imu_lidar */
+} srl_frame;
+
+/* What one pass reduces to (src/optimize.cpp:160-170,235,239) */
+typedef struct srl_normal_eq {
+    double HTH[36]; /* H_x^T H_x, row-major 6x6 */
+    double HTh[6];  /* H_x^T h, h = distance*weight */
+    double loss_sum;
+    int64_t num_residuals;
+    int64_t num_full_neighborhoods; /* keypoints that passed src/optimize.cpp:78 */
+    int64_t num_candidates_scanned; /* map points whose distance the GPU evaluated (<= reference's sum C_k) */
+    int64_t num_keypoints;          /* keypoints processed by this rank in this pass */
+    int32_t nan_planarity;
+    int32_t reserved;
+} srl_normal_eq;
+
+/* optional per-keypoint outputs (host pointers, any may be NULL); layouts match oracle/srl_oracle.h */
+typedef struct srl_debug_out {
+    double* world_xyz;  /* n*3 */
+    int32_t* status;    /* n : -1 not visited (cap), 0 <K neighbours, 1 gated out, 2 accepted */
+    int16_t* nbr;       /* n*K*4 : voxel key x,y,z + index in block, ascending distance */
+    double* nbr_dist;   /* n*K */
+    double* plane;      /* n*16 : raw_point3 norm_vector3 jacobians6 norm_offset distance weight a2D */
+} srl_debug_out;
+
+typedef struct srl_iekf_summary {
+    int32_t success;            /* optimizeSummary.success */
+    int32_t passes_run;
+    int32_t num_residuals_used; /* optimizeSummary.num_residuals_used */
+    int32_t converged;
+    double trace[32][24];       /* per pass: d_x[17], frame_t[3], frame_q[4] */
+} srl_iekf_summary;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int srl_abi_version(void);
+const char* srl_build_info(void);
+/* stream == NULL: the library creates its own non-blocking stream; otherwise a cudaStream_t to run on */
+int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out);
+void srl_ctx_destroy(srl_ctx* ctx);
+const char* srl_last_error(const srl_ctx* ctx);
+int srl_ctx_synchronize(srl_ctx* ctx);
+/* number of this library's kernels launched on the ctx since creation (bench.py "gpu_launches") */
+int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
+
+/* ---- map: voxelHashMap + addPointsToMap (include/cloudMap.h:124-184, src/lioOptimization.cpp:400-446,520-554) */
+int srl_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_voxel, size_t max_voxels,
+                   srl_map** out);
+void srl_map_destroy(srl_map* map);
+int srl_map_clear(srl_map* map);
+int srl_map_stats(srl_map* map, int64_t* n_voxels, int64_t* n_points); /* mapSize (src/lioOptimization.cpp:574-581) */
+/* mirror of a host voxelHashMap: keys n*3, counts n, xyz n*cap*3 (block order = voxelBlock::points order) */
+int srl_map_upload(srl_map* map, const int16_t* keys, const int32_t* counts, const float* xyz, size_t n_voxels);
+int srl_map_download(srl_map* map, int16_t* keys, int32_t* counts, float* xyz, size_t max_voxels, int64_t* n_voxels);
+/* addPointsToMap, sweep order preserved per voxel. xyz_world: host (or device if *_device) n*3 doubles */
+int srl_map_insert(srl_map* map, const double* xyz_world, size_t n, double min_distance_points,
+                   int32_t min_num_points, int64_t* n_added);
+int srl_map_insert_device(srl_map* map, const double* d_xyz_world, size_t n, double min_distance_points,
+                          int32_t min_num_points, int64_t* n_added);
+
+/* ---- sweep: the keypoints vector of optimize() (src/optimize.cpp:430) ------------------------ */
+int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out);
+void srl_sweep_destroy(srl_sweep* sweep);
+int srl_sweep_upload(srl_sweep* sweep, const double* raw_xyz, size_t n);        /* host -> HBM (pinned staging) */
+int srl_sweep_set_device(srl_sweep* sweep, const double* d_raw_xyz, size_t n);  /* device -> device copy */
+/* keypoints [begin, end) are this rank's shard (point-index sharding); default whole sweep */
+int srl_sweep_set_shard(srl_sweep* sweep, size_t begin, size_t end);
+
+/* ---- one ESIKF pass: buildPlaneResiduals + H_x/h + HTH/HTh (src/optimize.cpp:18-131,160-170,235,239) */
+int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, const srl_frame* frame,
+                              const srl_icp_params* prm, srl_normal_eq* out, srl_debug_out* dbg);
+/* asynchronous form: enqueue the pass on the ctx stream; the 32-double result block
+ * [HTH upper triangle 21 | HTh 6 | loss | num_residuals | num_full | candidates | flags] lands in d_out32
+ * (device memory owned by the caller, e.g. the buffer handed to an all-reduce). No cap support. */
+int srl_build_plane_residuals_async(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, const srl_frame* frame,
+                                    const srl_icp_params* prm, double* d_out32);
+/* unpack an (all-reduced) 32-double block */
+int srl_normal_eq_unpack(const double* h_out32, srl_normal_eq* out);
+
+/* ---- the iterated update: updateIEKF (src/optimize.cpp:133-314) incl. eskfEstimator::observe -- */
+/* one pass of the host algebra (src/optimize.cpp:172-310) given the reduced normal equations;
+ * *done = 1 when the loop would `break` (:309); `diverged` mirrors the `continue` at :248-251 */
+typedef struct srl_iekf_iter {
+    srl_eskf_state predict; /* snapshot at src/optimize.cpp:138-143 */
+    int32_t pass_index;     /* i in [-1, max_num_iter) */
+    int32_t max_num_iter;
+} srl_iekf_iter;
+int srl_iekf_begin(const srl_eskf_state* eskf, const srl_icp_params* prm, srl_iekf_iter* it);
+int srl_iekf_step(srl_iekf_iter* it, const srl_normal_eq* ne, const srl_icp_params* prm, srl_eskf_state* eskf,
+                  double frame_q[4], double frame_t[3], double d_x_out[17], int32_t* done, int32_t* diverged);
+/* full loop on one GPU (sweep already resident) */
+int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],
+                    double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
+                    const srl_icp_params* prm, srl_iekf_summary* summary);
+/* optimize() minus gridSampling (src/optimize.cpp:428-448): host keypoints in, updateIEKF, then the
+ * final re-transform of the frame (:441-445) written to world_xyz_out (host, n*3, may be NULL).
+ * This is the end-to-end entry point with HOST buffers (H2D + D2H inside). */
+int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, const double* raw_xyz, size_t n,
+                      srl_eskf_state* eskf, double frame_q[4], double frame_t[3], const double t_last[3],
+                      const double R_il[9], const double t_il[3], const srl_icp_params* prm,
+                      srl_iekf_summary* summary, double* world_xyz_out);
+/* transformPoint over the sweep (src/utility.cpp:314-318) into a device buffer (e.g. for srl_map_insert_device) */
+int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sweep, const double q[4], const double t[3],
+                               const double R_il[9], const double t_il[3], double* d_world_xyz);
+
+/* eskfEstimator::observe (src/eskfEstimator.cpp:219-230) — host math, exported for parity tests */
+int srl_eskf_observe(srl_eskf_state* eskf, const double d_x[17]);
+
+/* host-side unit hooks for the per-keypoint math of the kernel (same source compiled for the host);
+ * used by CPU tests only — they do not run the path. */
+int srl_host_plane_fit(const double* nbr_xyz /*K*3*/, int32_t K, double normal[3], double* a2D, double evals[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRLIVO_B200_H */

@@ -1,0 +1,431 @@
+// srl_api.cu — C-ABI glue: context, sweep residency, one ESIKF pass, the iterated update.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "srl_internal.h"
+
+namespace srl {
+
+int set_err(srl_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int cuda_fail(srl_ctx* ctx, cudaError_t e, const char* where) {
+    if (ctx) ctx->err = std::string(where) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();   // clear sticky-less errors
+    return SRL_CUDA_ERROR;
+}
+int ensure_scratch(srl_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return SRL_OK;
+    if (ctx->d_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&ctx->d_scratch, want);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "ensure_scratch/cudaMalloc");
+    ctx->scratch_bytes = want;
+    return SRL_OK;
+}
+int ensure_pinned(srl_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return SRL_OK;
+    if (ctx->h_pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->pinned_bytes = 0; }
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMallocHost(&ctx->h_pinned, want);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "ensure_pinned/cudaMallocHost");
+    ctx->pinned_bytes = want;
+    return SRL_OK;
+}
+
+// the per-pass constants of buildPlaneResiduals (src/optimize.cpp:21-28,35,55-61,95)
+void make_pass_const(const srl_frame& f, const srl_icp_params& p, PassConst& c) {
+    const double* q = f.q_cur;
+    // Eigen normalized() on the 4 coefficients (SSE2 pairing (x^2+z^2)+(y^2+w^2))
+    double n2 = (q[0] * q[0] + q[2] * q[2]) + (q[1] * q[1] + q[3] * q[3]);
+    double qn[4] = {q[0], q[1], q[2], q[3]};
+    if (n2 > 0.0) { const double n = std::sqrt(n2); for (int i = 0; i < 4; ++i) qn[i] = q[i] / n; }
+    quat_to_rot(qn, c.Rn);
+    quat_to_rot(q, c.Rq);
+    for (int i = 0; i < 3; ++i) { c.t[i] = f.t_cur[i]; c.t_last[i] = f.t_last[i]; c.t_il[i] = f.t_il[i]; }
+    for (int i = 0; i < 9; ++i) c.R_il[i] = f.R_il[i];
+    c.size = p.size_voxel_map;
+    double lw = std::fabs(p.weight_alpha), ln = std::fabs(p.weight_neighborhood);
+    const double sum = lw + ln;
+    c.lambda_w = lw / sum; c.lambda_n = ln / sum;
+    c.power = p.power_planarity;
+    c.dmax = p.max_dist_to_plane_icp;
+    c.exp_den = p.max_dist_to_plane_icp * p.min_number_neighbors;
+    c.K = p.max_number_neighbors;
+    c.Kmin = p.min_number_neighbors;
+    const bool init = p.frame_id < p.init_num_frames;
+    c.nb = init ? 2 : p.voxel_neighborhood;
+    c.thr_occ = init ? 1 : p.threshold_voxel_occupancy;
+}
+
+static int check_params(srl_ctx* ctx, const srl_icp_params* p) {
+    if (!p) return set_err(ctx, SRL_BAD_ARG, "null srl_icp_params");
+    if (!(p->size_voxel_map > 0)) return set_err(ctx, SRL_BAD_ARG, "size_voxel_map must be > 0");
+    if (p->max_number_neighbors < 1 || p->max_number_neighbors > 32) return set_err(ctx, SRL_BAD_ARG, "max_number_neighbors must be in [1,32]");
+    if (p->min_number_neighbors < 1) return set_err(ctx, SRL_BAD_ARG, "min_number_neighbors must be >= 1");
+    const int nb = p->frame_id < p->init_num_frames ? 2 : p->voxel_neighborhood;
+    if (nb < 0 || nb > 2) return set_err(ctx, SRL_BAD_ARG, "voxel_neighborhood must be 0, 1 or 2");
+    return SRL_OK;
+}
+
+static void unpack32(const double* o, srl_normal_eq* out, long long n_keypoints) {
+    int idx = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) { out->HTH[a * 6 + b] = o[idx]; out->HTH[b * 6 + a] = o[idx]; ++idx; }
+    for (int a = 0; a < 6; ++a) out->HTh[a] = o[21 + a];
+    out->loss_sum = o[27];
+    out->num_residuals = (int64_t)llround(o[28]);
+    out->num_full_neighborhoods = (int64_t)llround(o[29]);
+    out->num_candidates_scanned = (int64_t)llround(o[30]);
+    out->nan_planarity = o[31] > 0.0 ? 1 : 0;
+    out->num_keypoints = n_keypoints;
+    out->reserved = 0;
+}
+
+static int pass_grid(srl_ctx* ctx, long long n, int K, int nb) {
+    const long long n_groups = (n + 31) / 32;
+    long long want = (n_groups + kK1Warps - 1) / kK1Warps;
+    const long long resident = (long long)ctx->sm_count * k1_max_blocks_per_sm(K, nb);
+    if (want > resident) want = resident;
+    if (want < 1) want = 1;
+    if (want > ctx->max_grid) want = ctx->max_grid;
+    return (int)want;
+}
+
+}  // namespace srl
+
+using namespace srl;
+
+template <typename T>
+static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
+    if (*p) return SRL_OK;
+    cudaError_t e = cudaMalloc(p, count * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(debug/rows)");
+    return SRL_OK;
+}
+
+extern "C" {
+
+int srl_abi_version(void) { return SRL_ABI_VERSION; }
+const char* srl_build_info(void) { return "srlivo_b200 sm_100a, CUDA " __DATE__; }
+
+int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
+    if (!out) return SRL_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) { cudaGetLastError(); return SRL_CUDA_ERROR; }   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return SRL_CUDA_ERROR;
+    srl_ctx* ctx = new srl_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) { ctx->stream = static_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SRL_CUDA_ERROR; }
+        ctx->own_stream = true;
+    }
+    ctx->max_grid = ctx->sm_count * 8;
+    bool ok = cudaMalloc(&ctx->d_partials, (size_t)ctx->max_grid * 32 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_out32, 64 * sizeof(double)) == cudaSuccess &&
+              cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
+    if (!ok) { srl_ctx_destroy(ctx); cudaGetLastError(); return SRL_CUDA_ERROR; }
+    *out = ctx;
+    return SRL_OK;
+}
+
+void srl_ctx_destroy(srl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state);
+    cudaFree(ctx->d_scratch);
+    if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* srl_last_error(const srl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+int srl_ctx_synchronize(srl_ctx* ctx) {
+    if (!ctx) return SRL_BAD_ARG;
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SRL_OK;
+}
+int64_t srl_ctx_kernel_launches(const srl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- sweep -------------------------------------------------------------------------------------------------
+int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out) {
+    if (!ctx || !out || capacity == 0) return SRL_BAD_ARG;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    srl_sweep* s = new srl_sweep();
+    s->ctx = ctx; s->capacity = capacity;
+    cudaError_t e = cudaMalloc(&s->d_raw, capacity * 3 * sizeof(double));
+    if (e != cudaSuccess) { delete s; return cuda_fail(ctx, e, "srl_sweep_create/cudaMalloc"); }
+    *out = s;
+    return SRL_OK;
+}
+void srl_sweep_destroy(srl_sweep* s) {
+    if (!s) return;
+    cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status);
+    cudaFree(s->d_dbg_world); cudaFree(s->d_dbg_nbr); cudaFree(s->d_dbg_nbr_dist); cudaFree(s->d_dbg_plane);
+    delete s;
+}
+int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
+    if (!s || (n && !raw_xyz)) return SRL_BAD_ARG;
+    srl_ctx* ctx = s->ctx;
+    if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_upload: n exceeds capacity");
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // stage through pinned memory so the H2D copy runs at link speed and asynchronously
+    int rc = ensure_pinned(ctx, n * 3 * sizeof(double));
+    if (rc != SRL_OK) return rc;
+    std::memcpy(ctx->h_pinned, raw_xyz, n * 3 * sizeof(double));
+    SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, ctx->h_pinned, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    s->n = n; s->shard_begin = 0; s->shard_end = n;
+    return SRL_OK;
+}
+int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
+    if (!s || (n && !d_raw_xyz)) return SRL_BAD_ARG;
+    srl_ctx* ctx = s->ctx;
+    if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
+    SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    s->n = n; s->shard_begin = 0; s->shard_end = n;
+    return SRL_OK;
+}
+int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
+    if (!s || begin > end || end > s->n) return SRL_BAD_ARG;
+    s->shard_begin = begin; s->shard_end = end;
+    return SRL_OK;
+}
+
+// ---- one pass ----------------------------------------------------------------------------------------------
+static int fill_k1_args(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const srl_frame* frame, const srl_icp_params* prm, K1Args& a) {
+    int rc = check_params(ctx, prm);
+    if (rc != SRL_OK) return rc;
+    if (!map || !sw || !frame) return set_err(ctx, SRL_BAD_ARG, "null map/sweep/frame");
+    if (map->ctx != ctx || sw->ctx != ctx) return set_err(ctx, SRL_BAD_ARG, "map/sweep belong to another ctx");
+    if (std::fabs(prm->size_voxel_map - map->voxel_size) > 0) return set_err(ctx, SRL_BAD_ARG, "icp size_voxel_map differs from the map's voxel size");
+    std::memset(&a, 0, sizeof(a));
+    make_pass_const(*frame, *prm, a.c);
+    a.slots = map->d_slots; a.mask = (unsigned)(map->capacity - 1); a.blocks = map->d_blocks;
+    a.raw = sw->d_raw; a.k_begin = (long long)sw->shard_begin; a.k_end = (long long)sw->shard_end;
+    a.partials = ctx->d_partials; a.ticket = ctx->d_ticket; a.out32 = ctx->d_out32;
+    return SRL_OK;
+}
+
+int srl_build_plane_residuals_async(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const srl_frame* frame, const srl_icp_params* prm,
+                                    double* d_out32) {
+    if (!ctx || !d_out32) return SRL_BAD_ARG;
+    K1Args a;
+    int rc = fill_k1_args(ctx, map, sw, frame, prm, a);
+    if (rc != SRL_OK) return rc;
+    const long long n = a.k_end - a.k_begin;
+    if ((long long)prm->max_num_residuals < n) return set_err(ctx, SRL_BAD_ARG, "async pass does not implement the max_num_residuals cap");
+    a.out32 = d_out32;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n <= 0) { SRL_CUDA(ctx, cudaMemsetAsync(d_out32, 0, 32 * sizeof(double), ctx->stream)); return SRL_OK; }
+    SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), false, ctx->device, ctx->stream));
+    ctx->launches += 1;
+    return SRL_OK;
+}
+
+int srl_normal_eq_unpack(const double* h_out32, srl_normal_eq* out) {
+    if (!h_out32 || !out) return SRL_BAD_ARG;
+    unpack32(h_out32, out, 0);
+    return SRL_OK;
+}
+
+int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const srl_frame* frame, const srl_icp_params* prm,
+                              srl_normal_eq* out, srl_debug_out* dbg) {
+    if (!ctx || !out) return SRL_BAD_ARG;
+    K1Args a;
+    int rc = fill_k1_args(ctx, map, sw, frame, prm, a);
+    if (rc != SRL_OK) return rc;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::memset(out, 0, sizeof(*out));
+    const long long n = a.k_end - a.k_begin;
+    const int K = a.c.K;
+    const bool cap_mode = (long long)prm->max_num_residuals < n;
+    if (cap_mode && (sw->shard_begin != 0 || sw->shard_end != sw->n))
+        return set_err(ctx, SRL_BAD_ARG, "max_num_residuals < shard size is only supported on an unsharded sweep");
+    const bool debug = dbg != nullptr;
+    if (debug) {
+        if (sw->dbg_K != K) {   // neighbour arrays depend on K
+            cudaFree(sw->d_dbg_nbr); cudaFree(sw->d_dbg_nbr_dist); sw->d_dbg_nbr = nullptr; sw->d_dbg_nbr_dist = nullptr; sw->dbg_K = K;
+        }
+        if ((rc = ensure_buf(ctx, &sw->d_dbg_world, sw->capacity * 3)) != SRL_OK) return rc;
+        if ((rc = ensure_buf(ctx, &sw->d_dbg_nbr, sw->capacity * K * 4)) != SRL_OK) return rc;
+        if ((rc = ensure_buf(ctx, &sw->d_dbg_nbr_dist, sw->capacity * K)) != SRL_OK) return rc;
+        if ((rc = ensure_buf(ctx, &sw->d_dbg_plane, sw->capacity * 16)) != SRL_OK) return rc;
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_dbg_world, 0, sw->capacity * 3 * sizeof(double), ctx->stream));
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_dbg_nbr, 0xff, sw->capacity * K * 4 * sizeof(short), ctx->stream));
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_dbg_nbr_dist, 0, sw->capacity * K * sizeof(double), ctx->stream));
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_dbg_plane, 0, sw->capacity * 16 * sizeof(double), ctx->stream));
+        a.dbg_world = sw->d_dbg_world; a.dbg_nbr = sw->d_dbg_nbr; a.dbg_nbr_dist = sw->d_dbg_nbr_dist; a.dbg_plane = sw->d_dbg_plane;
+    }
+    if (debug || cap_mode) {
+        if ((rc = ensure_buf(ctx, &sw->d_status, sw->capacity)) != SRL_OK) return rc;
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_status, 0, sw->capacity * sizeof(int), ctx->stream));
+        a.status = sw->d_status;
+    }
+    double* h = ctx->h_out32;
+    if (n <= 0) {
+        std::memset(h, 0, 32 * sizeof(double));
+    } else if (!cap_mode) {
+        SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, K, a.c.nb), debug, ctx->device, ctx->stream));
+        ctx->launches += 1;
+        SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        // ordered cap (src/optimize.cpp:107): process keypoints in order, chunk by chunk, until k* is found
+        if ((rc = ensure_buf(ctx, &sw->d_rows, sw->capacity * 8)) != SRL_OK) return rc;
+        a.rows = sw->d_rows;
+        double* d_cap_out = ctx->d_out32 + 32;
+        SRL_CUDA(ctx, cudaMemsetAsync(d_cap_out, 0, 32 * sizeof(double), ctx->stream));
+        SRL_CUDA(ctx, cudaMemsetAsync(ctx->d_k2_state, 0, 4 * sizeof(long long), ctx->stream));
+        const long long cap = prm->max_num_residuals;
+        long long chunk = std::max<long long>(4096, 2 * std::max<long long>(cap, 1));
+        double scanned = 0, nanf = 0;
+        long long begin = 0;
+        long long st[4] = {0, 0, 0, 0};
+        while (begin < n) {
+            const long long end = std::min(n, begin + chunk);
+            K1Args c = a;
+            c.k_begin = begin; c.k_end = end;
+            SRL_CUDA(ctx, launch_k1(c, pass_grid(ctx, end - begin, K, a.c.nb), debug, ctx->device, ctx->stream));
+            SRL_CUDA(ctx, launch_k2(sw->d_rows, sw->d_status, begin, end, (int)cap, ctx->d_k2_state, d_cap_out, 0, ctx->stream));
+            ctx->launches += 2;
+            SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            SRL_CUDA(ctx, cudaMemcpyAsync(st, ctx->d_k2_state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+            SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            scanned += h[30]; nanf += h[31];
+            begin = end;
+            if (st[1]) break;   // k* found: the reference loop has hit its `break`
+            chunk *= 2;
+        }
+        // keypoints after k* were never visited
+        if (st[1] && st[2] + 1 < n) {
+            const long long first = st[2] + 1;
+            std::vector<int> neg((size_t)(n - first), -1);
+            SRL_CUDA(ctx, cudaMemcpyAsync(sw->d_status + first, neg.data(), neg.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        SRL_CUDA(ctx, cudaMemcpyAsync(h, d_cap_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h[30] = scanned; h[31] = nanf;
+    }
+    unpack32(h, out, n);
+    if (debug) {
+        const size_t N = sw->n;
+        if (dbg->world_xyz) SRL_CUDA(ctx, cudaMemcpyAsync(dbg->world_xyz, sw->d_dbg_world, N * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dbg->status) SRL_CUDA(ctx, cudaMemcpyAsync(dbg->status, sw->d_status, N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dbg->nbr) SRL_CUDA(ctx, cudaMemcpyAsync(dbg->nbr, sw->d_dbg_nbr, N * K * 4 * sizeof(short), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dbg->nbr_dist) SRL_CUDA(ctx, cudaMemcpyAsync(dbg->nbr_dist, sw->d_dbg_nbr_dist, N * K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dbg->plane) SRL_CUDA(ctx, cudaMemcpyAsync(dbg->plane, sw->d_dbg_plane, N * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (out->nan_planarity) return set_err(ctx, SRL_NAN_PLANARITY, "NaN planarity (the reference throws at src/optimize.cpp:348)");
+    if (out->num_residuals < prm->min_number_neighbors)
+        return set_err(ctx, SRL_TOO_FEW_RESIDUALS, "[Optimization] Error : not enough keypoints selected in ct-icp !");
+    return SRL_OK;
+}
+
+// ---- iterated update ---------------------------------------------------------------------------------------
+int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sw, srl_eskf_state* eskf, double frame_q[4], double frame_t[3],
+                    const double t_last[3], const double R_il[9], const double t_il[3], const srl_icp_params* prm,
+                    srl_iekf_summary* summary) {
+    if (!ctx || !eskf || !frame_q || !frame_t || !t_last || !R_il || !t_il || !prm) return SRL_BAD_ARG;
+    srl_iekf_iter it;
+    int rc = srl_iekf_begin(eskf, prm, &it);
+    if (rc != SRL_OK) return rc;
+    if (summary) { std::memset(summary, 0, sizeof(*summary)); summary->success = 1; }
+    srl_frame fr;
+    std::memcpy(fr.t_last, t_last, sizeof(fr.t_last));
+    std::memcpy(fr.R_il, R_il, sizeof(fr.R_il));
+    std::memcpy(fr.t_il, t_il, sizeof(fr.t_il));
+    int passes = 0;
+    for (;;) {
+        std::memcpy(fr.q_cur, frame_q, sizeof(fr.q_cur));
+        std::memcpy(fr.t_cur, frame_t, sizeof(fr.t_cur));
+        srl_normal_eq ne;
+        rc = srl_build_plane_residuals(ctx, map, sw, &fr, prm, &ne, nullptr);       // src/optimize.cpp:153
+        ++passes;
+        if (summary) { summary->passes_run = passes; summary->num_residuals_used = (int32_t)ne.num_residuals; }
+        if (rc == SRL_TOO_FEW_RESIDUALS) { if (summary) summary->success = 0; return rc; }   // :155
+        if (rc != SRL_OK) return rc;
+        double d_x[17];
+        int32_t done = 0, diverged = 0;
+        rc = srl_iekf_step(&it, &ne, prm, eskf, frame_q, frame_t, d_x, &done, &diverged);
+        if (rc != SRL_OK) return set_err(ctx, rc, "srl_iekf_step failed (singular 17x17)");
+        if (summary && passes <= 32) {
+            double* tr = summary->trace[passes - 1];
+            std::memcpy(tr, d_x, 17 * sizeof(double));
+            std::memcpy(tr + 17, frame_t, 3 * sizeof(double));
+            std::memcpy(tr + 20, frame_q, 4 * sizeof(double));
+        }
+        if (done) { if (summary) summary->converged = (done == 2); break; }
+    }
+    return SRL_OK;
+}
+
+int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sw, const double q[4], const double t[3], const double R_il[9],
+                               const double t_il[3], double* d_world_xyz) {
+    if (!ctx || !sw || !q || !t || !R_il || !t_il || !d_world_xyz) return SRL_BAD_ARG;
+    PassConst c;
+    std::memset(&c, 0, sizeof(c));
+    quat_to_rot(q, c.Rq);   // transformPoint uses q_end.toRotationMatrix() un-normalised (src/utility.cpp:317)
+    for (int i = 0; i < 3; ++i) { c.t[i] = t[i]; c.t_il[i] = t_il[i]; }
+    for (int i = 0; i < 9; ++i) c.R_il[i] = R_il[i];
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    SRL_CUDA(ctx, launch_transform(sw->d_raw, (long long)sw->n, c, d_world_xyz, ctx->stream));
+    ctx->launches += 1;
+    return SRL_OK;
+}
+
+int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const double* raw_xyz, size_t n, srl_eskf_state* eskf,
+                      double frame_q[4], double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
+                      const srl_icp_params* prm, srl_iekf_summary* summary, double* world_xyz_out) {
+    if (!ctx || !sw) return SRL_BAD_ARG;
+    int rc = srl_sweep_upload(sw, raw_xyz, n);                                   // H2D of the keypoints
+    if (rc != SRL_OK) return rc;
+    rc = srl_update_iekf(ctx, map, sw, eskf, frame_q, frame_t, t_last, R_il, t_il, prm, summary);   // src/optimize.cpp:435
+    if (rc != SRL_OK) return rc;                                                 // :437-439
+    if (world_xyz_out && n) {                                                    // :441-445
+        int r2 = ensure_scratch(ctx, n * 3 * sizeof(double));
+        if (r2 != SRL_OK) return r2;
+        r2 = srl_sweep_transform_device(ctx, sw, frame_q, frame_t, R_il, t_il, static_cast<double*>(ctx->d_scratch));
+        if (r2 != SRL_OK) return r2;
+        SRL_CUDA(ctx, cudaMemcpyAsync(world_xyz_out, ctx->d_scratch, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SRL_OK;
+}
+
+// ---- host unit hook for the per-keypoint math (same source as the kernel's phase 2) -------------------------
+struct HostNb {
+    const double* p;
+    float x(int j) const { return (float)p[3 * j]; }
+    float y(int j) const { return (float)p[3 * j + 1]; }
+    float z(int j) const { return (float)p[3 * j + 2]; }
+};
+int srl_host_plane_fit(const double* nbr_xyz, int32_t K, double normal[3], double* a2D, double evals[3]) {
+    if (!nbr_xyz || K < 1 || !normal || !a2D || !evals) return SRL_BAD_ARG;
+    double mx = 0, my = 0, mz = 0;
+    HostNb nb{nbr_xyz};
+    for (int j = 0; j < K; ++j) { mx += (double)nb.x(j); my += (double)nb.y(j); mz += (double)nb.z(j); }
+    mx /= K; my /= K; mz /= K;
+    double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
+    for (int j = 0; j < K; ++j) {
+        double dx = (double)nb.x(j) - mx, dy = (double)nb.y(j) - my, dz = (double)nb.z(j) - mz;
+        c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
+    }
+    eig3_sym(c00, c01, c11, c02, c12, c22, evals, normal[0], normal[1], normal[2]);
+    *a2D = (std::sqrt(std::fabs(evals[1])) - std::sqrt(std::fabs(evals[0]))) / std::sqrt(std::fabs(evals[2]));
+    return SRL_OK;
+}
+
+}  // extern "C"

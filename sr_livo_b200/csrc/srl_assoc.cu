@@ -1,0 +1,512 @@
+// srl_assoc.cu — K1: the fused scan-matching pass for sm_100a.
+//
+// One launch = one ESIKF pass over this rank's keypoint shard, replacing the body of
+// lioOptimization::buildPlaneResiduals (src/optimize.cpp:18-131) plus the H_x/h assembly and the
+// HTH / H^T h products (src/optimize.cpp:160-170,235,239):
+//
+//   prologue (thread per keypoint)  raw -> body -> world (FP64, same operation order as the reference,
+//                                    no FMA contraction) -> voxel key by truncation (:38,:372-374)
+//   phase 1 (warp per keypoint)     27/125 hash probes by 27/125 lanes (16 B slot loads), voxels ordered by
+//                                    a conservative point-to-cell lower bound, candidate distances in FP64
+//                                    from the FP32 map points, K-best list kept sorted across lanes with
+//                                    warp shuffles; a voxel whose lower bound exceeds the current K-th
+//                                    distance ends the scan (the reference visits all of them: :379-405).
+//                                    Order = (distance^2, reference visit index): equal to the reference's
+//                                    heap walk whenever no exact tie exists.
+//   phase 2 (thread per keypoint)   plane fit, weight, signed distance, gate, 1x6 Jacobian (srl_math.cuh)
+//   reduction                       32-component register transpose-reduce per group of 32 keypoints ->
+//                                    per-warp -> per-block -> last block sums block partials in fixed order
+//                                    (no FP64 atomics on the result: run-to-run deterministic).
+//
+// The 32-double result block: [0..20] HTH upper triangle (row-major a<=b), [21..26] H^T h, [27] sum d^2,
+// [28] residuals, [29] keypoints with a full neighbourhood, [30] map points scanned, [31] NaN-planarity count.
+#include "srl_internal.h"
+
+namespace srl {
+
+__constant__ signed char c_off[125 * 4];   // voxel offsets ordered by |offset|^2; first 27 = the nb=1 cube
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NBS = 33;   // padded stride of the per-warp neighbour tile (bank-conflict free both ways)
+
+__device__ __forceinline__ bool lex_less(double da, unsigned ia, double db, unsigned ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+struct SmemNb {
+    const float* x_; const float* y_; const float* z_; int lane;
+    __device__ __forceinline__ float x(int j) const { return x_[j * NBS + lane]; }
+    __device__ __forceinline__ float y(int j) const { return y_[j * NBS + lane]; }
+    __device__ __forceinline__ float z(int j) const { return z_[j * NBS + lane]; }
+};
+
+// 32x32 transpose-reduce: on return lane l holds sum over lanes of v[l] (31 shuffles instead of 160).
+__device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const double send = upper ? v[i] : v[i + s];
+            const double keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <int NCH, bool DEBUG>
+__global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const PassConst& c = A.c;
+    const int K = c.K;
+    const int nb = c.nb;
+    const int W = 2 * nb + 1;
+    const int V = W * W * W;
+
+    // per-warp shared memory: neighbour tile 3 x K x 33 floats, then block index per visited voxel (128 ints)
+    const size_t warp_bytes = (size_t)(3 * K * NBS) * sizeof(float) + 128 * sizeof(int);
+    float* nbx = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);
+    float* nby = nbx + K * NBS;
+    float* nbz = nby + K * NBS;
+    int* sblk = reinterpret_cast<int*>(nbz + K * NBS);
+
+    const float size_f = (float)c.size;
+    const float lb_margin = 1e-5f * size_f;
+
+    double acc = 0.0;                 // lane i accumulates component i of the 32-double result
+    long long scanned = 0;            // warp-uniform: map points whose distance was evaluated
+
+    const long long n = A.k_end - A.k_begin;
+    const long long n_groups = (n + 31) / 32;
+    const long long gwarp = (long long)blockIdx.x * kK1Warps + warp;
+    const long long total_warps = (long long)gridDim.x * kK1Warps;
+
+    for (long long g = gwarp; g < n_groups; g += total_warps) {
+        // ------------------------------------------------------------------ prologue: thread per keypoint
+        const long long k = A.k_begin + g * 32 + lane;
+        const bool valid = k < A.k_end;
+        double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        float relx = 0, rely = 0, relz = 0;
+        bool in_range = false;
+        if (valid) {
+            const double rx = A.raw[3 * k], ry = A.raw[3 * k + 1], rz = A.raw[3 * k + 2];
+            double tx, ty, tz;
+            matvec3_exact(c.R_il, rx, ry, rz, tx, ty, tz);                 // R_il * raw
+            bx = SRL_ADD(tx, c.t_il[0]); by = SRL_ADD(ty, c.t_il[1]); bz = SRL_ADD(tz, c.t_il[2]);   // + t_il  (:83)
+            matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);                   // R * (...)
+            pwx = SRL_ADD(tx, c.t[0]); pwy = SRL_ADD(ty, c.t[1]); pwz = SRL_ADD(tz, c.t[2]);         // + t     (:38)
+            const double qx = SRL_DIV(pwx, c.size), qy = SRL_DIV(pwy, c.size), qz = SRL_DIV(pwz, c.size);   // :372-374
+            in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;   // (short) cast is UB beyond
+            if (in_range) {
+                kx = (int)qx; ky = (int)qy; kz = (int)qz;   // truncation toward zero, like static_cast<short>
+                relx = (float)(pwx - (double)kx * c.size);
+                rely = (float)(pwy - (double)ky * c.size);
+                relz = (float)(pwz - (double)kz * c.size);
+            }
+            if (DEBUG && A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
+        }
+        int my_count = 0;   // neighbours found for this lane's keypoint (0 = not a full neighbourhood)
+
+        // ------------------------------------------------------------------ phase 1: warp per keypoint
+        const int n_in_group = (int)min((long long)32, n - g * 32);
+        for (int kp = 0; kp < n_in_group; ++kp) {
+            if (!__shfl_sync(FULL, (int)in_range, kp)) continue;
+            const double px = __shfl_sync(FULL, pwx, kp), py = __shfl_sync(FULL, pwy, kp), pz = __shfl_sync(FULL, pwz, kp);
+            const int ckx = __shfl_sync(FULL, kx, kp), cky = __shfl_sync(FULL, ky, kp), ckz = __shfl_sync(FULL, kz, kp);
+            const float rlx = __shfl_sync(FULL, relx, kp), rly = __shfl_sync(FULL, rely, kp), rlz = __shfl_sync(FULL, relz, kp);
+
+            // ---- probes: lane o handles voxel offset o of the chunk
+            unsigned cnt[NCH], blk[NCH];
+            float lb[NCH];
+            int vis[NCH];
+            int total = 0;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                cnt[ch] = 0; blk[ch] = 0; vis[ch] = 0; lb[ch] = 0.f;
+                const int o = ch * 32 + lane;
+                if (o < V) {
+                    const int ox = c_off[4 * o], oy = c_off[4 * o + 1], oz = c_off[4 * o + 2];
+                    const int vx = ckx + ox, vy = cky + oy, vz = ckz + oz;
+                    vis[ch] = ((ox + nb) * W + (oy + nb)) * W + (oz + nb);   // reference scan order (:379-381)
+                    unsigned b, cn;
+                    if (map_find(A.slots, A.mask, vx, vy, vz, b, cn) && (int)cn >= c.thr_occ) {   // :386-390
+                        cnt[ch] = cn; blk[ch] = b;
+                        sblk[vis[ch]] = (int)b;
+                        // conservative lower bound of the distance to any point stored under key (vx,vy,vz):
+                        // cell k>0 spans [k,k+1), k<0 spans (k-1,k], k=0 spans (-1,1) (truncation toward zero)
+                        const float lox = (float)((vx > 0 ? vx : vx - 1) - ckx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - ckx) * size_f;
+                        const float loy = (float)((vy > 0 ? vy : vy - 1) - cky) * size_f, hiy = (float)((vy < 0 ? vy : vy + 1) - cky) * size_f;
+                        const float loz = (float)((vz > 0 ? vz : vz - 1) - ckz) * size_f, hiz = (float)((vz < 0 ? vz : vz + 1) - ckz) * size_f;
+                        const float gx = fmaxf(fmaxf(lox - rlx, rlx - hix) - lb_margin, 0.f);
+                        const float gy = fmaxf(fmaxf(loy - rly, rly - hiy) - lb_margin, 0.f);
+                        const float gz = fmaxf(fmaxf(loz - rlz, rlz - hiz) - lb_margin, 0.f);
+                        lb[ch] = (gx * gx + gy * gy + gz * gz) * 0.999999f;
+                    }
+                }
+                total += (int)cnt[ch];
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) total += __shfl_xor_sync(FULL, total, s);
+            if (total < c.Kmin) continue;   // fewer candidates than min_number_neighbors: :78 will skip it
+            __syncwarp();                   // sblk[] visible to the whole warp
+
+            // ---- K-best list: lane j holds the j-th smallest (d2, id); lanes >= K hold +inf
+            double best_d2 = CUDART_INF, kth_d2 = CUDART_INF;
+            unsigned best_id = 0xffffffffu, kth_id = 0xffffffffu;
+            bool list_empty = true;
+
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                // sort this chunk's voxels by lower bound (ascending); absent voxels last
+                unsigned key = cnt[ch] ? ((__float_as_uint(lb[ch]) & ~31u) | (unsigned)lane) : 0xffffffffu;
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const unsigned other = __shfl_xor_sync(FULL, key, j);
+                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                        key = (lower == up) ? min(key, other) : max(key, other);
+                    }
+                }
+                const int src = (int)(key & 31u);
+                const unsigned s_cnt = __shfl_sync(FULL, cnt[ch], src);
+                const unsigned s_blk = __shfl_sync(FULL, blk[ch], src);
+                const int s_vis = __shfl_sync(FULL, vis[ch], src);
+                const float s_lb = __uint_as_float(key & ~31u);   // mantissa truncated downward: still a lower bound
+                const int n_present = __popc(__ballot_sync(FULL, key != 0xffffffffu));
+
+                for (int r = 0; r < n_present; ++r) {
+                    const float lb_r = __shfl_sync(FULL, s_lb, r);
+                    if ((double)lb_r > kth_d2) break;   // every remaining voxel of this chunk is farther
+                    const unsigned b = __shfl_sync(FULL, s_blk, r);
+                    const int cn = (int)__shfl_sync(FULL, s_cnt, r);
+                    const int v = __shfl_sync(FULL, s_vis, r);
+                    scanned += cn;
+                    double d2 = CUDART_INF;
+                    unsigned id = 0xffffffffu;
+                    if (lane < cn) {
+                        const float* bp = A.blocks + (size_t)b * kBlockFloats;
+                        const double mx = (double)__ldg(bp + lane), my = (double)__ldg(bp + kOffY + lane), mz = (double)__ldg(bp + kOffZ + lane);
+                        const double dx = SRL_SUB(mx, px), dy = SRL_SUB(my, py), dz = SRL_SUB(mz, pz);   // :394-395
+                        d2 = SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz)));
+                        id = ((unsigned)v << 5) | (unsigned)lane;
+                    }
+                    if (list_empty) {
+                        // first voxel: bitonic sort of the 32 lanes by (d2, id) initialises the list
+#pragma unroll
+                        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                            for (int j = kk >> 1; j > 0; j >>= 1) {
+                                const double od = __shfl_xor_sync(FULL, d2, j);
+                                const unsigned oi = __shfl_xor_sync(FULL, id, j);
+                                const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                                const bool take = (lower == up) ? lex_less(od, oi, d2, id) : lex_less(d2, id, od, oi);
+                                if (take) { d2 = od; id = oi; }
+                            }
+                        }
+                        if (lane < K) { best_d2 = d2; best_id = id; }
+                        list_empty = false;
+                    } else {
+                        unsigned m = __ballot_sync(FULL, lex_less(d2, id, kth_d2, kth_id));
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            const double nd = __shfl_sync(FULL, d2, j);
+                            const unsigned ni = __shfl_sync(FULL, id, j);
+                            if (!lex_less(nd, ni, kth_d2, kth_id)) continue;   // threshold tightened meanwhile
+                            const int pos = __popc(__ballot_sync(FULL, lex_less(best_d2, best_id, nd, ni)));
+                            const double ud = __shfl_up_sync(FULL, best_d2, 1);
+                            const unsigned ui = __shfl_up_sync(FULL, best_id, 1);
+                            if (lane < K) {
+                                if (lane > pos) { best_d2 = ud; best_id = ui; }
+                                else if (lane == pos) { best_d2 = nd; best_id = ni; }
+                            }
+                            kth_d2 = __shfl_sync(FULL, best_d2, K - 1);
+                            kth_id = __shfl_sync(FULL, best_id, K - 1);
+                        }
+                        continue;
+                    }
+                    kth_d2 = __shfl_sync(FULL, best_d2, K - 1);
+                    kth_id = __shfl_sync(FULL, best_id, K - 1);
+                }
+            }
+
+            const int nfound = __popc(__ballot_sync(FULL, lane < K && best_d2 < CUDART_INF));
+            if (nfound >= c.Kmin) {
+                if (lane < nfound) {
+                    const int v = (int)(best_id >> 5), i = (int)(best_id & 31u);
+                    const float* bp = A.blocks + (size_t)sblk[v] * kBlockFloats;
+                    nbx[lane * NBS + kp] = __ldg(bp + i);
+                    nby[lane * NBS + kp] = __ldg(bp + kOffY + i);
+                    nbz[lane * NBS + kp] = __ldg(bp + kOffZ + i);
+                    if (DEBUG) {
+                        const long long kk = A.k_begin + g * 32 + kp;
+                        if (A.dbg_nbr) {
+                            short* d = A.dbg_nbr + (kk * K + lane) * 4;
+                            d[0] = (short)(ckx + v / (W * W) - nb);
+                            d[1] = (short)(cky + (v / W) % W - nb);
+                            d[2] = (short)(ckz + v % W - nb);
+                            d[3] = (short)i;
+                        }
+                        if (A.dbg_nbr_dist) A.dbg_nbr_dist[kk * K + lane] = sqrt(best_d2);
+                    }
+                }
+                if (lane == kp) my_count = nfound;
+            }
+            __syncwarp();   // sblk[] is rewritten by the next keypoint's probes
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------------ phase 2: thread per keypoint
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+        int status = 0;
+        if (valid && my_count > 0) {
+            PlaneRow row;
+            SmemNb acc_nb{nbx, nby, nbz, lane};
+            plane_residual(acc_nb, my_count, c, pwx, pwy, pwz, bx, by, bz, row);
+            status = row.accepted ? 2 : 1;
+            v[29] = 1.0;
+            v[31] = (double)row.nan_planarity;
+            const double h = row.distance * row.weight;   // :169
+            if (row.accepted) {
+                v[0] = row.J[0] * row.J[0]; v[1] = row.J[0] * row.J[1]; v[2] = row.J[0] * row.J[2];
+                v[3] = row.J[0] * row.J[3]; v[4] = row.J[0] * row.J[4]; v[5] = row.J[0] * row.J[5];
+                v[6] = row.J[1] * row.J[1]; v[7] = row.J[1] * row.J[2]; v[8] = row.J[1] * row.J[3];
+                v[9] = row.J[1] * row.J[4]; v[10] = row.J[1] * row.J[5];
+                v[11] = row.J[2] * row.J[2]; v[12] = row.J[2] * row.J[3]; v[13] = row.J[2] * row.J[4];
+                v[14] = row.J[2] * row.J[5];
+                v[15] = row.J[3] * row.J[3]; v[16] = row.J[3] * row.J[4]; v[17] = row.J[3] * row.J[5];
+                v[18] = row.J[4] * row.J[4]; v[19] = row.J[4] * row.J[5];
+                v[20] = row.J[5] * row.J[5];
+                v[21] = row.J[0] * h; v[22] = row.J[1] * h; v[23] = row.J[2] * h;
+                v[24] = row.J[3] * h; v[25] = row.J[4] * h; v[26] = row.J[5] * h;
+                v[27] = row.distance * row.distance;   // :104
+                v[28] = 1.0;
+            }
+            if (A.rows) {   // per-keypoint rows for the ordered max_num_residuals cap (:107)
+                double* rr = A.rows + 8 * k;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) rr[i] = row.J[i];
+                rr[6] = h; rr[7] = row.distance * row.distance;
+            }
+            if (DEBUG && A.dbg_plane) {
+                double* d = A.dbg_plane + 16 * k;
+                d[0] = bx; d[1] = by; d[2] = bz; d[3] = row.nx; d[4] = row.ny; d[5] = row.nz;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) d[6 + i] = row.accepted ? row.J[i] : 0.0;
+                d[12] = row.offset; d[13] = row.distance; d[14] = row.weight; d[15] = row.a2D;
+            }
+        }
+        if (valid && A.status) A.status[k] = status;
+        acc += transpose_reduce32(v, lane);
+        __syncwarp();   // the neighbour tile is rewritten by the next group
+    }
+    if (lane == 30) acc += (double)scanned;
+
+    // ---------------------------------------------------------------------- block + grid reduction
+    __shared__ double s_acc[kK1Warps][32];
+    __shared__ bool s_last;
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kK1Warps; ++w) s += s_acc[w][lane];
+        A.partials[(size_t)blockIdx.x * 32 + lane] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(A.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = warp; b < (int)gridDim.x; b += kK1Warps) s += __ldcg(A.partials + (size_t)b * 32 + lane);
+        s_acc[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kK1Warps; ++w) tot += s_acc[w][lane];
+            A.out32[lane] = tot;
+            if (lane == 0) *A.ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: ordered residual cap (src/optimize.cpp:99,107).  Single block.  The reference loop stops after
+// the first full-neighbourhood keypoint k* at which the running count of accepted residuals is >= cap,
+// so the rows that count are the accepted ones with k <= k*.  cap >= 1: k* = the cap-th accepted
+// keypoint; cap <= 0 (the compiled default -1): k* = the first keypoint with a full neighbourhood.
+// state[0] = running accepted count, state[1] = k* found flag, state[2] = k*
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) k2_cap_reduce(const double* __restrict__ rows, int* __restrict__ status,
+                                                          long long k_begin, long long k_end, int cap,
+                                                          long long* __restrict__ state, double* __restrict__ out32,
+                                                          int mark_unvisited) {
+    __shared__ int s_scan[1024];
+    __shared__ double s_red[32][33];
+    __shared__ long long s_kstar;
+    __shared__ int s_found;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long run_acc = state[0];
+    if (tid == 0) { s_found = (int)state[1]; s_kstar = state[2]; }
+    __syncthreads();
+    double acc[29];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) acc[i] = 0.0;
+    double n_full = 0.0;
+    for (long long base = k_begin; base < k_end && !s_found; base += 1024) {
+        const long long k = base + tid;
+        const int st = (k < k_end) ? status[k] : 0;
+        const int a = (st == 2) ? 1 : 0;
+        // inclusive block scan of accepted flags
+        s_scan[tid] = a;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            int t = (tid >= off) ? s_scan[tid - off] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        const long long incl = run_acc + s_scan[tid];
+        // k* candidate: full neighbourhood and running count >= cap
+        const bool is_kstar_cand = (st >= 1) && (incl >= (long long)cap);
+        // first such k in this chunk
+        unsigned long long cand = is_kstar_cand ? (unsigned long long)k : ~0ull;
+        // block min via shared
+        __shared__ unsigned long long s_min[32];
+        for (int s = 16; s >= 1; s >>= 1) { unsigned long long o = __shfl_xor_sync(0xffffffffu, cand, s); cand = o < cand ? o : cand; }
+        if (lane == 0) s_min[warp] = cand;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long m = s_min[lane];
+            for (int s = 16; s >= 1; s >>= 1) { unsigned long long o = __shfl_xor_sync(0xffffffffu, m, s); m = o < m ? o : m; }
+            if (lane == 0 && m != ~0ull) { s_found = 1; s_kstar = (long long)m; }
+        }
+        __syncthreads();
+        const long long kstar = s_found ? s_kstar : (long long)0x7fffffffffffffffLL;
+        if (k < k_end && k <= kstar) {
+            if (st >= 1) n_full += 1.0;
+            if (a) {
+                const double* r = rows + 8 * k;
+                int idx = 0;
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+#pragma unroll
+                    for (int q = p; q < 6; ++q) acc[idx++] += r[p] * r[q];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) acc[21 + p] += r[p] * r[6];
+                acc[27] += r[7];
+                acc[28] += 1.0;
+            }
+        }
+        run_acc += s_scan[1023];
+        __syncthreads();
+    }
+    // keypoints after k* were never visited by the reference loop
+    if (mark_unvisited && s_found)
+        for (long long k = s_kstar + 1 + tid; k < k_end; k += 1024) status[k] = -1;
+    // fixed-order block reduction of the 30 components
+    double comps[30];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) comps[i] = acc[i];
+    comps[29] = n_full;
+    for (int i = 0; i < 30; ++i) {
+        double x = comps[i];
+        for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+        if (lane == 0) s_red[warp][i] = x;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 30) {
+        double tot = 0.0;
+        for (int w = 0; w < 32; ++w) tot += s_red[w][lane];
+        out32[lane] += tot;   // chunks append
+    }
+    if (tid == 0) { state[0] = run_acc; state[1] = s_found; state[2] = s_kstar; }
+}
+
+// transformPoint over a sweep (src/utility.cpp:314-318): world = R(q) * (R_il * raw + t_il) + t
+__global__ void k_transform(const double* __restrict__ raw, long long n, PassConst c, double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double tx, ty, tz;
+    matvec3_exact(c.R_il, raw[3 * k], raw[3 * k + 1], raw[3 * k + 2], tx, ty, tz);
+    const double bx = SRL_ADD(tx, c.t_il[0]), by = SRL_ADD(ty, c.t_il[1]), bz = SRL_ADD(tz, c.t_il[2]);
+    matvec3_exact(c.Rq, bx, by, bz, tx, ty, tz);
+    out[3 * k] = SRL_ADD(tx, c.t[0]); out[3 * k + 1] = SRL_ADD(ty, c.t[1]); out[3 * k + 2] = SRL_ADD(tz, c.t[2]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static bool g_off_uploaded[64] = {false};
+
+static void upload_offsets(int device) {
+    if (device >= 0 && device < 64 && g_off_uploaded[device]) return;
+    // all 125 offsets of the 5x5x5 cube ordered by squared norm; the 27 with |.|inf <= 1 come first
+    signed char tab[125 * 4];
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int d2 = 0; d2 <= 12; ++d2)
+            for (int x = -2; x <= 2; ++x)
+                for (int y = -2; y <= 2; ++y)
+                    for (int z = -2; z <= 2; ++z) {
+                        const bool inner = x >= -1 && x <= 1 && y >= -1 && y <= 1 && z >= -1 && z <= 1;
+                        if ((pass == 0) != inner) continue;
+                        if (x * x + y * y + z * z != d2) continue;
+                        tab[4 * n] = (signed char)x; tab[4 * n + 1] = (signed char)y; tab[4 * n + 2] = (signed char)z; tab[4 * n + 3] = 0;
+                        ++n;
+                    }
+    cudaMemcpyToSymbol(c_off, tab, sizeof(tab));
+    if (device >= 0 && device < 64) g_off_uploaded[device] = true;
+}
+
+size_t k1_smem_bytes(int K) { return (size_t)kK1Warps * ((size_t)(3 * K * NBS) * sizeof(float) + 128 * sizeof(int)); }
+
+cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream) {
+    upload_offsets(device);
+    const size_t smem = k1_smem_bytes(a.c.K);
+    void (*fn)(const K1Args) = nullptr;
+    if (a.c.nb == 1) fn = debug ? k1_assoc<1, true> : k1_assoc<1, false>;
+    else fn = debug ? k1_assoc<4, true> : k1_assoc<4, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fn<<<grid, kK1Threads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+int k1_max_blocks_per_sm(int K, int nb) {
+    int nblk = 0;
+    void (*fn)(const K1Args) = (nb == 1) ? k1_assoc<1, false> : k1_assoc<4, false>;
+    const size_t smem = k1_smem_bytes(K);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, kK1Threads, smem) != cudaSuccess) return 1;
+    return nblk < 1 ? 1 : nblk;
+}
+
+cudaError_t launch_k2(const double* rows, int* status, long long k_begin, long long k_end, int cap, long long* state,
+                      double* out32, int mark_unvisited, cudaStream_t stream) {
+    k2_cap_reduce<<<1, 1024, 0, stream>>>(rows, status, k_begin, k_end, cap, state, out32, mark_unvisited);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform(const double* raw, long long n, const PassConst& c, double* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    k_transform<<<(unsigned)blocks, threads, 0, stream>>>(raw, n, c, out);
+    return cudaGetLastError();
+}
+
+}  // namespace srl

@@ -1,0 +1,111 @@
+// srl_internal.h — internal declarations shared by the .cu/.cpp translation units of libsrlivo_b200.so
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/srlivo_b200.h"
+#include "srl_device.cuh"
+#include "srl_math.cuh"
+
+namespace srl {
+
+constexpr int kK1Warps = 8;
+constexpr int kK1Threads = kK1Warps * 32;
+
+struct K1Args {
+    PassConst c;
+    const Slot* slots;
+    unsigned int mask;
+    const float* blocks;
+    const double* raw;        // sweep, n*3 (device)
+    long long k_begin, k_end; // this rank's shard
+    double* partials;         // [grid][32]
+    unsigned int* ticket;
+    double* out32;            // device, 32 doubles
+    double* rows;             // optional n*8 (J6, h, d^2)
+    int* status;              // optional n
+    double* dbg_world;        // optional debug outputs (device)
+    short* dbg_nbr;
+    double* dbg_nbr_dist;
+    double* dbg_plane;
+};
+
+size_t k1_smem_bytes(int K);
+int k1_max_blocks_per_sm(int K, int nb);
+cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream);
+cudaError_t launch_k2(const double* rows, int* status, long long k_begin, long long k_end, int cap, long long* state,
+                      double* out32, int mark_unvisited, cudaStream_t stream);
+cudaError_t launch_transform(const double* raw, long long n, const PassConst& c, double* out, cudaStream_t stream);
+
+// host-side pass constants from the reference's per-pass inputs (src/optimize.cpp:21-28,55-61)
+void make_pass_const(const srl_frame& f, const srl_icp_params& p, PassConst& c);
+
+}  // namespace srl
+
+// ---- opaque handle definitions ------------------------------------------------------------------
+struct srl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    int64_t launches = 0;
+    // per-pass scratch
+    double* d_partials = nullptr;   // [max_grid][32]
+    int max_grid = 0;
+    unsigned int* d_ticket = nullptr;
+    double* d_out32 = nullptr;
+    double* h_out32 = nullptr;      // pinned
+    long long* d_k2_state = nullptr;
+    // generic scratch (map insert)
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct srl_map {
+    srl_ctx* ctx = nullptr;
+    double voxel_size = 1.0;
+    int cap = 20;
+    size_t max_voxels = 0;
+    size_t capacity = 0;            // slots (power of two)
+    srl::Slot* d_slots = nullptr;
+    float* d_blocks = nullptr;
+    int64_t n_voxels = 0;           // host mirror of the block count
+    long long* d_counters = nullptr;   // [0] n_points, [1] scratch
+};
+
+struct srl_sweep {
+    srl_ctx* ctx = nullptr;
+    size_t capacity = 0;
+    size_t n = 0;
+    size_t shard_begin = 0, shard_end = 0;
+    double* d_raw = nullptr;        // capacity*3
+    double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
+    int* d_status = nullptr;        // capacity, lazily allocated
+    // debug buffers, lazily allocated
+    double* d_dbg_world = nullptr;
+    short* d_dbg_nbr = nullptr;
+    double* d_dbg_nbr_dist = nullptr;
+    double* d_dbg_plane = nullptr;
+    int dbg_K = 0;
+};
+
+namespace srl {
+int set_err(srl_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(srl_ctx* ctx, cudaError_t e, const char* where);
+int ensure_scratch(srl_ctx* ctx, size_t bytes);
+int ensure_pinned(srl_ctx* ctx, size_t bytes);
+}  // namespace srl
+
+#define SRL_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return srl::cuda_fail((ctx), e__, #call); \
+    } while (0)

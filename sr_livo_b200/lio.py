@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's interface for the scan-matching path, over the C ABI.
+
+Names and argument meaning follow the reference so the parity tests read like its call sites:
+
+  voxelHashMap                          include/cloudMap.h:171          -> VoxelHashMap
+  lioOptimization::addPointsToMap       src/lioOptimization.cpp:520-554 -> LioOptimization.addPointsToMap
+  lioOptimization::mapSize              src/lioOptimization.cpp:574-581 -> LioOptimization.mapSize
+  lioOptimization::buildPlaneResiduals  src/optimize.cpp:18-131         -> LioOptimization.buildPlaneResiduals
+  lioOptimization::updateIEKF           src/optimize.cpp:133-314        -> LioOptimization.updateIEKF
+  lioOptimization::optimize             src/optimize.cpp:428-448        -> LioOptimization.optimize (keypoints given)
+  eskfEstimator (state + observe)       src/eskfEstimator.cpp           -> EskfEstimator
+
+Error behaviour: optimizeSummary.success=false <-> OptimizeSummary.success False (SRL_TOO_FEW_RESIDUALS);
+the reference's `throw std::runtime_error("error")` on NaN planarity <-> RuntimeError; everything else raises
+SrlError.  No CPU fallback exists: without the CUDA library/GPU every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import (DebugOut, EskfState, Frame, IcpParams, IekfSummary, NormalEq, SrlError, f64, lib, ptr,
+                   r3live_params)
+
+NS = capi.NS
+
+
+def _check(ctx, rc, ok=(capi.SRL_OK,)):
+    if rc not in ok:
+        raise SrlError(rc, lib().srl_last_error(ctx).decode() if ctx else "")
+    return rc
+
+
+class Context:
+    """srl_ctx: one per host thread / GPU. `stream` may be a raw cudaStream_t (e.g. torch's current stream)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        rc = lib().srl_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != capi.SRL_OK:
+            raise SrlError(rc, "srl_ctx_create failed: no usable CUDA device (this path has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().srl_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(self.h, lib().srl_ctx_synchronize(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().srl_ctx_kernel_launches(self.h))
+
+
+class VoxelHashMap:
+    """HBM-resident voxelHashMap (include/cloudMap.h:171)."""
+
+    def __init__(self, ctx: Context, voxel_size: float = 1.0, max_num_points_in_voxel: int = 20,
+                 max_voxels: int = 1 << 20):
+        self.ctx = ctx
+        self.cap = max_num_points_in_voxel
+        self.voxel_size = voxel_size
+        h = C.c_void_p()
+        _check(ctx.h, lib().srl_map_create(ctx.h, voxel_size, max_num_points_in_voxel, max_voxels, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().srl_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        _check(self.ctx.h, lib().srl_map_clear(self.h))
+
+    def stats(self):
+        nv, npts = C.c_int64(0), C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_stats(self.h, C.byref(nv), C.byref(npts)))
+        return nv.value, npts.value
+
+    def upload(self, keys, counts, xyz):
+        keys = np.ascontiguousarray(keys, np.int16).reshape(-1, 3)
+        counts = np.ascontiguousarray(counts, np.int32)
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(keys.shape[0], self.cap, 3)
+        _check(self.ctx.h, lib().srl_map_upload(self.h, ptr(keys), ptr(counts), ptr(xyz), keys.shape[0]))
+
+    def download(self):
+        nv, _ = self.stats()
+        keys = np.zeros((nv, 3), np.int16)
+        counts = np.zeros(nv, np.int32)
+        xyz = np.zeros((nv, self.cap, 3), np.float32)
+        got = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_download(self.h, ptr(keys), ptr(counts), ptr(xyz), nv, C.byref(got)))
+        return keys, counts, xyz
+
+    def insert(self, xyz_world, min_distance_points: float = 0.15, min_num_points: int = 0) -> int:
+        xyz = f64(xyz_world).reshape(-1, 3)
+        added = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_insert(self.h, ptr(xyz), xyz.shape[0], min_distance_points, min_num_points,
+                                                C.byref(added)))
+        return added.value
+
+    def insert_device(self, d_ptr: int, n: int, min_distance_points: float = 0.15, min_num_points: int = 0) -> int:
+        added = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_insert_device(self.h, C.c_void_p(d_ptr), n, min_distance_points,
+                                                       min_num_points, C.byref(added)))
+        return added.value
+
+
+class Sweep:
+    """The keypoints of one reconstructed sweep, resident in HBM (raw LiDAR-frame points, FP64)."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx = ctx
+        self.capacity = capacity
+        self.n = 0
+        h = C.c_void_p()
+        _check(ctx.h, lib().srl_sweep_create(ctx.h, capacity, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().srl_sweep_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, raw_xyz):
+        raw = f64(raw_xyz).reshape(-1, 3)
+        _check(self.ctx.h, lib().srl_sweep_upload(self.h, ptr(raw), raw.shape[0]))
+        self.n = raw.shape[0]
+
+    def set_device(self, d_ptr: int, n: int):
+        _check(self.ctx.h, lib().srl_sweep_set_device(self.h, C.c_void_p(d_ptr), n))
+        self.n = n
+
+    def set_shard(self, begin: int, end: int):
+        _check(self.ctx.h, lib().srl_sweep_set_shard(self.h, begin, end))
+
+
+@dataclass
+class EskfEstimator:
+    """eskfEstimator state (src/eskfEstimator.cpp:3-21); q = (x, y, z, w)."""
+    p: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    q: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, 0.0, 1.0]))
+    v: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    ba: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    bg: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    g: np.ndarray = field(default_factory=lambda: np.array([0.0, 0.0, 9.81]))
+    cov: np.ndarray = field(default_factory=lambda: np.eye(NS))
+
+    def to_c(self) -> EskfState:
+        return capi.eskf_to_c(self.p, self.q, self.v, self.ba, self.bg, self.g, self.cov)
+
+    @staticmethod
+    def from_c(s: EskfState) -> "EskfEstimator":
+        return EskfEstimator(**capi.eskf_from_c(s))
+
+    def observe(self, d_x) -> "EskfEstimator":
+        """eskfEstimator::observe (src/eskfEstimator.cpp:219-230)."""
+        s = self.to_c()
+        d = f64(d_x)
+        rc = lib().srl_eskf_observe(C.byref(s), ptr(d))
+        if rc != capi.SRL_OK:
+            raise SrlError(rc, "srl_eskf_observe")
+        return EskfEstimator.from_c(s)
+
+
+@dataclass
+class OptimizeSummary:
+    """optimizeSummary (include/lioOptimization.h) + what the GPU pass reports."""
+    success: bool
+    num_residuals_used: int
+    passes_run: int = 1
+    converged: bool = False
+    trace: np.ndarray | None = None
+
+
+@dataclass
+class PlaneResiduals:
+    HTH: np.ndarray
+    HTh: np.ndarray
+    loss_sum: float
+    num_residuals: int
+    num_full_neighborhoods: int
+    num_candidates_scanned: int
+    success: bool
+    world_xyz: np.ndarray | None = None
+    status: np.ndarray | None = None
+    nbr: np.ndarray | None = None
+    nbr_dist: np.ndarray | None = None
+    plane: np.ndarray | None = None
+
+
+def make_frame(q_cur, t_cur, t_last, R_il=None, t_il=None) -> Frame:
+    fr = Frame()
+    for name, val, n in (("q_cur", q_cur, 4), ("t_cur", t_cur, 3), ("t_last", t_last, 3),
+                         ("R_il", np.eye(3) if R_il is None else R_il, 9),
+                         ("t_il", np.zeros(3) if t_il is None else t_il, 3)):
+        a = f64(val).reshape(-1)
+        assert a.size == n, name
+        for i in range(n):
+            getattr(fr, name)[i] = a[i]
+    return fr
+
+
+class LioOptimization:
+    """The scan-matching members of `class lioOptimization` (include/lioOptimization.h:334-353) on one GPU."""
+
+    def __init__(self, device: int = 0, stream: int | None = None, max_voxels: int = 1 << 20,
+                 sweep_capacity: int = 1 << 17, size_voxel_map: float = 1.0, max_num_points_in_voxel: int = 20,
+                 R_imu_lidar=None, t_imu_lidar=None):
+        self.ctx = Context(device, stream)
+        self.voxel_map = VoxelHashMap(self.ctx, size_voxel_map, max_num_points_in_voxel, max_voxels)
+        self.sweep = Sweep(self.ctx, sweep_capacity)
+        self.R_imu_lidar = np.eye(3) if R_imu_lidar is None else f64(R_imu_lidar).reshape(3, 3)
+        self.t_imu_lidar = np.zeros(3) if t_imu_lidar is None else f64(t_imu_lidar)
+        self.eskf_pro = EskfEstimator()
+
+    def close(self):
+        self.sweep.close()
+        self.voxel_map.close()
+        self.ctx.close()
+
+    # ---- src/lioOptimization.cpp:520-554 (voxel_size is the map's own)
+    def addPointsToMap(self, points_world, min_distance_points: float = 0.15, min_num_points: int = 0) -> int:
+        return self.voxel_map.insert(points_world, min_distance_points, min_num_points)
+
+    # ---- src/lioOptimization.cpp:574-581
+    def mapSize(self) -> int:
+        return self.voxel_map.stats()[1]
+
+    def setKeypoints(self, raw_xyz):
+        """std::vector<point3D> keypoints (raw_point members), uploaded once per sweep."""
+        self.sweep.upload(raw_xyz)
+
+    # ---- src/optimize.cpp:18-131 (+ :160-170,:235,:239)
+    def buildPlaneResiduals(self, cur_icp_options: IcpParams, q_cur, t_cur, t_last, debug: bool = False) -> PlaneResiduals:
+        fr = make_frame(q_cur, t_cur, t_last, self.R_imu_lidar, self.t_imu_lidar)
+        ne = NormalEq()
+        n = self.sweep.n
+        K = cur_icp_options.max_number_neighbors
+        arrs = {}
+        dbg = None
+        if debug:
+            arrs = dict(world_xyz=np.zeros((n, 3)), status=np.zeros(n, np.int32), nbr=np.zeros((n, K, 4), np.int16),
+                        nbr_dist=np.zeros((n, K)), plane=np.zeros((n, 16)))
+            dbg = DebugOut(*[ptr(arrs[k]) for k in ("world_xyz", "status", "nbr", "nbr_dist", "plane")])
+        rc = lib().srl_build_plane_residuals(self.ctx.h, self.voxel_map.h, self.sweep.h, C.byref(fr),
+                                             C.byref(cur_icp_options), C.byref(ne),
+                                             C.byref(dbg) if dbg is not None else None)
+        if rc == capi.SRL_NAN_PLANARITY:
+            raise RuntimeError("error")   # src/optimize.cpp:348-350
+        _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
+        return PlaneResiduals(HTH=np.array(ne.HTH).reshape(6, 6), HTh=np.array(ne.HTh), loss_sum=ne.loss_sum,
+                              num_residuals=ne.num_residuals, num_full_neighborhoods=ne.num_full_neighborhoods,
+                              num_candidates_scanned=ne.num_candidates_scanned, success=(rc == capi.SRL_OK), **arrs)
+
+    # ---- src/optimize.cpp:133-314
+    def updateIEKF(self, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None):
+        st = self.eskf_pro.to_c()
+        fq = f64(self.eskf_pro.q if frame_q is None else frame_q).copy()
+        ft = f64(self.eskf_pro.p if frame_t is None else frame_t).copy()
+        tl = f64(t_last)
+        R = f64(self.R_imu_lidar).reshape(9)
+        ti = f64(self.t_imu_lidar)
+        summ = IekfSummary()
+        rc = lib().srl_update_iekf(self.ctx.h, self.voxel_map.h, self.sweep.h, C.byref(st), ptr(fq), ptr(ft), ptr(tl),
+                                   ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ))
+        if rc == capi.SRL_NAN_PLANARITY:
+            raise RuntimeError("error")
+        _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
+        self.eskf_pro = EskfEstimator.from_c(st)
+        trace = np.array([list(summ.trace[i]) for i in range(min(summ.passes_run, 32))])
+        return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
+                               passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft
+
+    # ---- src/optimize.cpp:428-448 with the keypoints already selected (gridSampling is a "next" row)
+    def optimize(self, raw_xyz, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None, want_world: bool = True):
+        raw = f64(raw_xyz).reshape(-1, 3)
+        n = raw.shape[0]
+        st = self.eskf_pro.to_c()
+        fq = f64(self.eskf_pro.q if frame_q is None else frame_q).copy()
+        ft = f64(self.eskf_pro.p if frame_t is None else frame_t).copy()
+        tl = f64(t_last)
+        R = f64(self.R_imu_lidar).reshape(9)
+        ti = f64(self.t_imu_lidar)
+        summ = IekfSummary()
+        world = np.zeros((n, 3)) if want_world else None
+        rc = lib().srl_optimize_host(self.ctx.h, self.voxel_map.h, self.sweep.h, ptr(raw), n, C.byref(st), ptr(fq), ptr(ft),
+                                     ptr(tl), ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ),
+                                     ptr(world) if want_world else None)
+        self.sweep.n = n
+        if rc == capi.SRL_NAN_PLANARITY:
+            raise RuntimeError("error")
+        _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
+        self.eskf_pro = EskfEstimator.from_c(st)
+        trace = np.array([list(summ.trace[i]) for i in range(min(summ.passes_run, 32))])
+        return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
+                               passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft, world
+
+
+__all__ = ["Context", "VoxelHashMap", "Sweep", "EskfEstimator", "LioOptimization", "OptimizeSummary", "PlaneResiduals",
+           "IcpParams", "r3live_params", "make_frame", "SrlError"]
