@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — point-associations/s of the LIO scan-matching hot path (BASELINE.json metric).
+
+Workload (BASELINE config 2, `configs[1]`): 100k-pt Livox-pattern sweep vs a ~10M-pt voxel map, 3 ESIKF passes per
+sweep, r3live.yaml parameters with the residual cap lifted (max_num_residuals >= N) and early convergence disabled so
+that every step runs exactly 3 passes.  A "step" is one sweep = updateIEKF (3 x [fused K1 pass + 256-byte result +
+17x17 host update]).  --gpus N shards the same sweep by point index over N ranks (config 3, strong scaling) with one
+32-double all-reduce per pass.
+
+  value : associations/s with the sweep already resident in HBM (C-ABI srl_update_iekf / sharded loop)
+  e2e   : the same through the host-buffer entry point (srl_optimize_host: H2D of the sweep, passes, final
+          re-transform, D2H of the registered points)
+  --impl reference : the CPU oracle (restated reference algorithm, reference's own robin-map when it was compiled
+          from /root/reference) on all host threads — the reference arm for this tier.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "point-associations/sec per ESIKF iter, 100k-pt sweep vs 10M-pt map"
+UNIT = "associations/s"
+BIG = 2 ** 31 - 1
+N_PASSES = 3
+
+
+def bench_params(mod):
+    # 3 passes exactly: i = -1, 0, 1 (num_iters_icp = 2), never "converged" early
+    return mod.r3live_params(max_num_residuals=BIG, num_iters_icp=N_PASSES - 1, threshold_translation_norm=0.0,
+                             threshold_orientation_norm=0.0, frame_id=100)
+
+
+def make_sweeps(synth, n_points, n_sweeps):
+    out = []
+    for i in range(n_sweeps):
+        pos = (40.0 * ((i % 5) - 2), 3.0 + 40.0 * ((i // 5) % 3 - 1), 1.8)
+        out.append(synth.make_sweep(n_points, seed=1000 + i, yaw=0.5 + 0.37 * i, position=pos))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device_index=0):
+        self.lines = []
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle (restated reference algorithm) on all host threads; wall-clock timed."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle_py as O
+    from sr_livo_b200 import synth
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    pts = synth.sample_map_points(args.map_extent, 60.0, seed=1)
+    om = O.OracleMap()
+    om.add_points(pts)
+    del pts
+    t_map = time.time() - t0
+    sweeps = make_sweeps(synth, args.points, min(8, args.steps + args.warmup))
+    prm = bench_params(O)
+    P = synth.prior_covariance()
+
+    def step(sw):
+        e = O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
+        r = om.update_iekf(sw.raw_xyz, e, sw.t_last, prm, nthreads=cores)
+        assert r["passes"] == N_PASSES, r["passes"]
+        return r
+    for i in range(args.warmup):
+        step(sweeps[i % len(sweeps)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(sweeps[(args.warmup + i) % len(sweeps)])
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = args.points * N_PASSES / dt
+    kind = "port"   # the reference itself cannot be compiled here (Eigen/PCL/ROS absent); the port uses its robin-map
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg2: {args.points}-pt Livox sweep vs {om.num_points}-pt map ({om.num_voxels} voxels), "
+                                   f"{N_PASSES} ESIKF passes/step, r3live params, cap lifted", "container": O.backend(),
+                       "map_build_s": round(t_map, 1)},
+            "sweeps_per_s": 1.0 / dt,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"whole workload: {args.steps} sweeps x {N_PASSES} passes x {args.points} keypoints, "
+                                       f"keypoint ranges over {cores} std::threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=100000)
+    ap.add_argument("--map-extent", type=float, default=600.0, help="side of the square world in m (600 -> ~10M points)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as tdist
+    from sr_livo_b200 import dist, lio, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scan-matching path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+    stream = torch.cuda.current_stream().cuda_stream or 1        # 1 == cudaStreamLegacy
+    L = lio.LioOptimization(device=local, stream=stream, max_voxels=1 << 21 if args.map_extent <= 900 else 1 << 23,
+                            sweep_capacity=max(args.points, 1024))
+    L.ctx.set_timing(True)
+
+    # ---- map: built by the product's own insert kernel (every rank builds its replica from the same seed)
+    t0 = time.time()
+    pts = synth.sample_map_points(args.map_extent, 60.0, seed=1)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    L.addPointsToMap(pts)
+    t_ins = time.time() - t0
+    n_offered = pts.shape[0]
+    del pts
+    n_vox, n_pts = L.voxel_map.stats()
+    sweeps = make_sweeps(synth, args.points, 8)
+    prm = bench_params(lio)
+    P = synth.prior_covariance()
+    d_raw = [torch.from_numpy(s.raw_xyz).to(f"cuda:{local}") for s in sweeps]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    D = dist.DistributedLio(L, rank, world) if world > 1 else None
+
+    def prepare(i):
+        sw = sweeps[i % len(sweeps)]
+        L.sweep.set_device(d_raw[i % len(sweeps)].data_ptr(), sw.raw_xyz.shape[0])
+        if world > 1:
+            L.sweep.set_shard(*dist.shard_range(sw.raw_xyz.shape[0], rank, world))
+        L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
+        return sw
+
+    def step_resident(sw):
+        if world > 1:
+            out = D.updateIEKF(prm, sw.t_last)
+            assert out["success"] and out["passes"] == N_PASSES
+        else:
+            summ, _, _ = L.updateIEKF(prm, sw.t_last)
+            assert summ.success and summ.passes_run == N_PASSES, (summ.success, summ.passes_run)
+
+    world_out = np.zeros((args.points, 3))
+
+    def step_e2e(sw):
+        L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
+        if world > 1:
+            D.set_keypoints(sw.raw_xyz)                                   # H2D, every rank holds the sweep
+            out = D.updateIEKF(prm, sw.t_last)
+            fr_q, fr_t = out["frame_q"], out["frame_t"]
+            dw = torch.empty((sw.raw_xyz.shape[0], 3), dtype=torch.float64, device=f"cuda:{local}")
+            import ctypes as C
+            from sr_livo_b200 import capi
+            R, ti = capi.f64(L.R_imu_lidar).reshape(9), capi.f64(L.t_imu_lidar)
+            rc = capi.lib().srl_sweep_transform_device(L.ctx.h, L.sweep.h, capi.ptr(fr_q), capi.ptr(fr_t), capi.ptr(R), capi.ptr(ti),
+                                                       C.c_void_p(dw.data_ptr()))
+            assert rc == 0
+            world_out[:] = dw.cpu().numpy()                               # D2H of the registered points
+        else:
+            summ, _, _, w = L.optimize(sw.raw_xyz, prm, sw.t_last, want_world=True)
+            assert summ.success and summ.passes_run == N_PASSES
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, with_prepare):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.warmup):
+            sw = prepare(i) if with_prepare else sweeps[i % len(sweeps)]
+            step_fn(sw)
+        L.ctx.pass_time(reset=True)
+        launches0 = L.ctx.kernel_launches
+        barrier()
+        for i in range(args.steps):
+            sw = prepare(args.warmup + i) if with_prepare else sweeps[(args.warmup + i) % len(sweeps)]
+            if not args.no_flush:
+                flush_buf.fill_(i & 0xff)                                  # evict L2 between timed steps (untimed)
+            if world > 1:
+                tdist.barrier()
+            ev[i][0].record()
+            step_fn(sw)
+            ev[i][1].record()
+        barrier()
+        ms = np.array([a.elapsed_time(b) for a, b in ev])
+        k1_ms, k1_n = L.ctx.pass_time(reset=True)
+        return ms, k1_ms, k1_n, L.ctx.kernel_launches - launches0
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_res, k1_ms, k1_n, launches = timed(step_resident, True)
+    clk = clocks.stop()
+    ms_e2e, _, _, _ = timed(step_e2e, False)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+    ms_step = max_over_ranks(float(ms_res.mean()))
+    ms_step_e2e = max_over_ranks(float(ms_e2e.mean()))
+    k1_avg_ms = max_over_ranks(k1_ms / max(k1_n, 1))
+    value = args.points * N_PASSES / (ms_step * 1e-3)
+    e2e_value = args.points * N_PASSES / (ms_step_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (k1_assoc): algorithmic bytes / measured launch duration
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    sw0 = sweeps[0]
+    n_shard = args.points if world == 1 else (dist.shard_range(args.points, rank, world)[1] - dist.shard_range(args.points, rank, world)[0])
+    prepare(0)
+    gp = L.buildPlaneResiduals(prm, sw0.q_init, sw0.t_init, sw0.t_last)
+    bytes_gpu_scanned = 456.0 * n_shard + 12.0 * gp.num_candidates_scanned
+
+    cpu_baseline = None
+    sumC = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle_py as O                                  # the one place bench.py runs the oracle
+        cores = os.cpu_count() or 1
+        keys, counts, xyz = L.voxel_map.download()
+        om = O.OracleMap()
+        om.load(keys, counts, xyz)
+        oprm = bench_params(O)
+        o1 = om.build_plane_residuals(sw0.raw_xyz, sw0.q_init, sw0.t_init, sw0.t_last, oprm, nthreads=cores)
+        sumC = int(o1.sum_candidates)
+        rel = float(np.abs(o1.HTH - gp.HTH).max() / np.abs(o1.HTH).max())
+        ts = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            r = om.update_iekf(sw0.raw_xyz, O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=P.copy()), sw0.t_last, oprm, nthreads=cores)
+            ts.append(time.perf_counter() - t0)
+        t_all = float(np.median(ts))
+        n1 = min(args.points, 20000)
+        t0 = time.perf_counter()
+        om.update_iekf(sw0.raw_xyz[:n1], O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=P.copy()), sw0.t_last, oprm, nthreads=1)
+        t_one = time.perf_counter() - t0
+        cpu_baseline = {"value": args.points * N_PASSES / t_all, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"one sweep ({args.points} keypoints x {N_PASSES} passes), median of 3, {cores} std::threads; "
+                                  f"single-thread (reference as written) on {n1} keypoints x {N_PASSES} passes",
+                        "single_thread_value": n1 * N_PASSES / t_one, "container": O.backend(),
+                        "pass_parity_HTH_rel": rel, "residuals_equal": bool(o1.num_residuals == gp.num_residuals)}
+    if sumC is not None:
+        alg_bytes = 456.0 * n_shard + 12.0 * sumC
+        basis = "reference-visited candidates (oracle sum C_k on sweep 0)"
+    else:
+        alg_bytes = bytes_gpu_scanned
+        basis = "GPU-scanned candidates (oracle leg not run at this N)"
+    achieved = alg_bytes / (k1_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k1_assoc", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_launch": alg_bytes, "bytes_basis": basis,
+                "bytes_gpu_scanned": bytes_gpu_scanned, "k1_avg_ms": k1_avg_ms, "k1_launches": int(k1_n),
+                "k1_share_of_step": k1_avg_ms * N_PASSES / ms_step}
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"cfg{2 if world == 1 else 3}: {args.points}-pt Livox sweep vs {n_pts}-pt map ({n_vox} voxels), "
+                                       f"{N_PASSES} ESIKF passes/step, r3live params, cap lifted",
+                           "parallelism": f"point-index shards x{world}, map replicated, 1 all-reduce(32 f64)/pass" if world > 1 else "single GPU",
+                           "l2": "no flush" if args.no_flush else "256 MB L2 flush between timed steps; 8 distinct sweeps cycled",
+                           "map_offered_points": int(n_offered), "map_gen_s": round(t_gen, 2), "map_insert_s": round(t_ins, 2)},
+                "sweeps_per_s": 1e3 / ms_step, "clocks": clk, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,
+                        "h2d_bytes_per_step": int(args.points * 24), "d2h_bytes_per_step": int(args.points * 24 + N_PASSES * 256)},
+                "roofline": roofline}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+    L.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -121,13 +121,18 @@ typedef struct srl_iekf_summary {
 /* ---- context ------------------------------------------------------------------------------- */
 int srl_abi_version(void);
 const char* srl_build_info(void);
-/* stream == NULL: the library creates its own non-blocking stream; otherwise a cudaStream_t to run on */
+/* stream == NULL: the library creates its own non-blocking stream; otherwise a cudaStream_t to run on
+ * (pass cudaStreamLegacy = (void*)1 for the legacy default stream, whose handle is NULL) */
 int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out);
 void srl_ctx_destroy(srl_ctx* ctx);
 const char* srl_last_error(const srl_ctx* ctx);
 int srl_ctx_synchronize(srl_ctx* ctx);
 /* number of this library's kernels launched on the ctx since creation (bench.py "gpu_launches") */
 int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
+/* CUDA-event timing of the scan-matching kernel (k1_assoc) on the ctx stream: enable, then read the summed device
+ * time and launch count of the passes since the last reset (bench.py "roofline"). Reading synchronises the stream. */
+int srl_ctx_set_timing(srl_ctx* ctx, int enable);
+int srl_ctx_pass_time(srl_ctx* ctx, double* total_ms, int64_t* launches, int reset);
 
 /* ---- map: voxelHashMap + addPointsToMap (include/cloudMap.h:124-184, src/lioOptimization.cpp:400-446,520-554) */
 int srl_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_voxel, size_t max_voxels,

@@ -662,10 +662,10 @@ void buildPlaneResidualsRange(const PassCtx& c, int64_t k_begin, int64_t k_end, 
                     bool have = j < (int)nbrs.size();
                     if (c.dbg->nbr) {
                         int16_t* d = c.dbg->nbr + (k * K + j) * 4;
-                        d[0] = have ? nbrs[j].vx : 0; d[1] = have ? nbrs[j].vy : 0;
-                        d[2] = have ? nbrs[j].vz : 0; d[3] = have ? nbrs[j].idx : -1;
+                        d[0] = have ? nbrs[j].vx : -1; d[1] = have ? nbrs[j].vy : -1;
+                        d[2] = have ? nbrs[j].vz : -1; d[3] = have ? nbrs[j].idx : -1;
                     }
-                    if (c.dbg->nbr_dist) c.dbg->nbr_dist[k * K + j] = have ? nbrs[j].distance : -1.0;
+                    if (c.dbg->nbr_dist) c.dbg->nbr_dist[k * K + j] = have ? nbrs[j].distance : 0.0;
                 }
         }
         if (DIAG) {

@@ -35,6 +35,16 @@ int ensure_pinned(srl_ctx* ctx, size_t bytes) {
     return SRL_OK;
 }
 
+// fold a finished k1 event pair into the running totals (call only when the stream is known to have passed ev1,
+// or accept that an unfinished pair is dropped)
+void timing_collect(srl_ctx* ctx) {
+    if (!ctx->ev_pending) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->k1_ms += ms; ctx->k1_launches += 1; }
+    else cudaGetLastError();
+    ctx->ev_pending = false;
+}
+
 // the per-pass constants of buildPlaneResiduals (src/optimize.cpp:21-28,35,55-61,95)
 void make_pass_const(const srl_frame& f, const srl_icp_params& p, PassConst& c) {
     const double* q = f.q_cur;
@@ -106,6 +116,14 @@ static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
     return SRL_OK;
 }
 
+static cudaError_t timed_launch_k1(srl_ctx* ctx, const K1Args& a, int grid, bool debug) {
+    if (ctx->timing) { timing_collect(ctx); cudaEventRecord(ctx->ev0, ctx->stream); }
+    cudaError_t e = launch_k1(a, grid, debug, ctx->device, ctx->stream);
+    if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    ctx->launches += 1;
+    return e;
+}
+
 extern "C" {
 
 int srl_abi_version(void) { return SRL_ABI_VERSION; }
@@ -147,6 +165,8 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -158,6 +178,25 @@ int srl_ctx_synchronize(srl_ctx* ctx) {
     return SRL_OK;
 }
 int64_t srl_ctx_kernel_launches(const srl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int srl_ctx_set_timing(srl_ctx* ctx, int enable) {
+    if (!ctx) return SRL_BAD_ARG;
+    if (enable && !ctx->ev0) {
+        SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+        SRL_CUDA(ctx, cudaEventCreate(&ctx->ev0));
+        SRL_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+    }
+    ctx->timing = enable != 0;
+    return SRL_OK;
+}
+int srl_ctx_pass_time(srl_ctx* ctx, double* total_ms, int64_t* launches, int reset) {
+    if (!ctx) return SRL_BAD_ARG;
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    timing_collect(ctx);
+    if (total_ms) *total_ms = ctx->k1_ms;
+    if (launches) *launches = ctx->k1_launches;
+    if (reset) { ctx->k1_ms = 0.0; ctx->k1_launches = 0; }
+    return SRL_OK;
+}
 
 // ---- sweep -------------------------------------------------------------------------------------------------
 int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out) {
@@ -229,8 +268,7 @@ int srl_build_plane_residuals_async(srl_ctx* ctx, srl_map* map, srl_sweep* sw, c
     a.out32 = d_out32;
     SRL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n <= 0) { SRL_CUDA(ctx, cudaMemsetAsync(d_out32, 0, 32 * sizeof(double), ctx->stream)); return SRL_OK; }
-    SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), false, ctx->device, ctx->stream));
-    ctx->launches += 1;
+    SRL_CUDA(ctx, timed_launch_k1(ctx, a, pass_grid(ctx, n, a.c.K, a.c.nb), false));
     return SRL_OK;
 }
 
@@ -277,10 +315,10 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
     if (n <= 0) {
         std::memset(h, 0, 32 * sizeof(double));
     } else if (!cap_mode) {
-        SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, K, a.c.nb), debug, ctx->device, ctx->stream));
-        ctx->launches += 1;
+        SRL_CUDA(ctx, timed_launch_k1(ctx, a, pass_grid(ctx, n, K, a.c.nb), debug));
         SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->timing) timing_collect(ctx);
     } else {
         // ordered cap (src/optimize.cpp:107): process keypoints in order, chunk by chunk, until k* is found
         if ((rc = ensure_buf(ctx, &sw->d_rows, sw->capacity * 8)) != SRL_OK) return rc;
@@ -297,9 +335,9 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
             const long long end = std::min(n, begin + chunk);
             K1Args c = a;
             c.k_begin = begin; c.k_end = end;
-            SRL_CUDA(ctx, launch_k1(c, pass_grid(ctx, end - begin, K, a.c.nb), debug, ctx->device, ctx->stream));
+            SRL_CUDA(ctx, timed_launch_k1(ctx, c, pass_grid(ctx, end - begin, K, a.c.nb), debug));
             SRL_CUDA(ctx, launch_k2(sw->d_rows, sw->d_status, begin, end, (int)cap, ctx->d_k2_state, d_cap_out, 0, ctx->stream));
-            ctx->launches += 2;
+            ctx->launches += 1;
             SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             SRL_CUDA(ctx, cudaMemcpyAsync(st, ctx->d_k2_state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
             SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

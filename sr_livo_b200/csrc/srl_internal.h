@@ -55,6 +55,12 @@ struct srl_ctx {
     int sm_count = 148;
     std::string err;
     int64_t launches = 0;
+    // optional CUDA-event timing of k1_assoc
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
+    double k1_ms = 0.0;
+    int64_t k1_launches = 0;
     // per-pass scratch
     double* d_partials = nullptr;   // [max_grid][32]
     int max_grid = 0;
@@ -102,6 +108,7 @@ int set_err(srl_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(srl_ctx* ctx, cudaError_t e, const char* where);
 int ensure_scratch(srl_ctx* ctx, size_t bytes);
 int ensure_pinned(srl_ctx* ctx, size_t bytes);
+void timing_collect(srl_ctx* ctx);
 }  // namespace srl
 
 #define SRL_CUDA(ctx, call)                                             \

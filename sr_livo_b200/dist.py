@@ -1,0 +1,119 @@
+"""Multi-GPU scan matching: one process per GPU, map replicated, keypoints sharded by contiguous index range,
+one 32-double all-reduce of the normal equations per ESIKF pass.
+
+torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo in the CPU tests).  Every rank runs the same
+17x17 host update on the reduced block, so no state broadcast is needed and all ranks stay bit-identical.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import IcpParams, IekfIter, NormalEq, SrlError, lib, ptr
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous keypoint range of `rank`; boundaries fall on multiples of 32 (whole warp groups) so every rank
+    keeps keypoint order (needed for deterministic sums and for the residual-cap semantics)."""
+    groups = (n + 31) // 32
+    b = (groups * rank) // world * 32
+    e = (groups * (rank + 1)) // world * 32
+    return min(b, n), min(e, n)
+
+
+def allreduce_block(block, group=None):
+    """Sum the 32-double result block over ranks, in place. `block` is a torch tensor (cuda for NCCL, cpu for gloo)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
+    return block
+
+
+def unpack_block(block64: np.ndarray) -> NormalEq:
+    ne = NormalEq()
+    b = np.ascontiguousarray(block64, np.float64)
+    rc = lib().srl_normal_eq_unpack(ptr(b), C.byref(ne))
+    if rc != capi.SRL_OK:
+        raise SrlError(rc, "srl_normal_eq_unpack")
+    return ne
+
+
+def iekf_loop(pass_fn, eskf_c, frame_q: np.ndarray, frame_t: np.ndarray, prm: IcpParams, group=None, max_trace: int = 32):
+    """The updateIEKF loop (src/optimize.cpp:147-311) with a sharded pass:
+    pass_fn(frame_q, frame_t) -> torch tensor of 32 doubles holding THIS rank's partial sums
+    (device tensor filled asynchronously is fine).  Returns dict(success, passes, converged, trace)."""
+    it = IekfIter()
+    rc = lib().srl_iekf_begin(C.byref(eskf_c), C.byref(prm), C.byref(it))
+    if rc != capi.SRL_OK:
+        raise SrlError(rc, "srl_iekf_begin")
+    passes = 0
+    trace = []
+    success = True
+    converged = False
+    num_res = 0
+    while True:
+        block = pass_fn(frame_q, frame_t)
+        allreduce_block(block, group)
+        host = block.detach().to("cpu").numpy().astype(np.float64, copy=True)   # D2H of 256 B (syncs the stream)
+        ne = unpack_block(host)
+        passes += 1
+        num_res = ne.num_residuals
+        if ne.nan_planarity:
+            raise RuntimeError("error")                                  # src/optimize.cpp:348-350
+        if ne.num_residuals < prm.min_number_neighbors:                  # :110-123, :155
+            success = False
+            break
+        d_x = np.zeros(17)
+        done = C.c_int32(0)
+        div = C.c_int32(0)
+        rc = lib().srl_iekf_step(C.byref(it), C.byref(ne), C.byref(prm), C.byref(eskf_c), ptr(frame_q), ptr(frame_t),
+                                 ptr(d_x), C.byref(done), C.byref(div))
+        if rc != capi.SRL_OK:
+            raise SrlError(rc, "srl_iekf_step")
+        if len(trace) < max_trace:
+            trace.append(np.concatenate([d_x, frame_t, frame_q]))
+        if done.value:
+            converged = done.value == 2
+            break
+    return dict(success=success, passes=passes, converged=converged, num_residuals_used=int(num_res),
+                trace=np.array(trace))
+
+
+class DistributedLio:
+    """A LioOptimization per rank + the sharded iterated update."""
+
+    def __init__(self, lio_opt, rank: int, world: int, group=None):
+        import torch
+        self.L = lio_opt
+        self.rank, self.world, self.group = rank, world, group
+        self.block = torch.zeros(32, dtype=torch.float64, device=f"cuda:{lio_opt.ctx.device}")
+
+    def set_keypoints(self, raw_xyz):
+        """Every rank holds the whole sweep (2.4 MB for 100k points); only the shard is processed."""
+        self.L.setKeypoints(raw_xyz)
+        b, e = shard_range(self.L.sweep.n, self.rank, self.world)
+        self.L.sweep.set_shard(b, e)
+
+    def _pass(self, prm: IcpParams, t_last):
+        from .lio import make_frame
+
+        def fn(frame_q, frame_t):
+            fr = make_frame(frame_q, frame_t, t_last, self.L.R_imu_lidar, self.L.t_imu_lidar)
+            rc = lib().srl_build_plane_residuals_async(self.L.ctx.h, self.L.voxel_map.h, self.L.sweep.h, C.byref(fr),
+                                                       C.byref(prm), C.c_void_p(self.block.data_ptr()))
+            if rc != capi.SRL_OK:
+                raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
+            return self.block
+        return fn
+
+    def updateIEKF(self, prm: IcpParams, t_last, frame_q=None, frame_t=None):
+        from .lio import EskfEstimator
+        st = self.L.eskf_pro.to_c()
+        fq = capi.f64(self.L.eskf_pro.q if frame_q is None else frame_q).copy()
+        ft = capi.f64(self.L.eskf_pro.p if frame_t is None else frame_t).copy()
+        out = iekf_loop(self._pass(prm, capi.f64(t_last)), st, fq, ft, prm, self.group)
+        self.L.eskf_pro = EskfEstimator.from_c(st)
+        out["frame_q"], out["frame_t"] = fq, ft
+        return out

@@ -63,6 +63,15 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib().srl_ctx_kernel_launches(self.h))
 
+    def set_timing(self, enable: bool = True):
+        _check(self.h, lib().srl_ctx_set_timing(self.h, 1 if enable else 0))
+
+    def pass_time(self, reset: bool = False):
+        """(summed k1_assoc device time in ms, launches) measured with CUDA events on the ctx stream."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        _check(self.h, lib().srl_ctx_pass_time(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
 
 class VoxelHashMap:
     """HBM-resident voxelHashMap (include/cloudMap.h:171)."""

@@ -1,0 +1,66 @@
+"""Generates tests/golden/*.npz with the CPU oracle (the reference itself cannot be built or imported here and
+ships no vectors of its own: SURVEY.md §8(c)), so these fixtures pin the ORACLE's outputs — parity stays
+"unpinned" with respect to the reference.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle_py as O          # noqa: E402
+from sr_livo_b200 import synth             # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BIG = 2 ** 31 - 1
+
+
+def scan_matching_fixture():
+    pts = synth.sample_map_points(40.0, 60.0, seed=21, center=(20.0, 20.0))
+    sw = synth.make_sweep(512, seed=1021, yaw=0.3, position=(5.0, 5.0, 1.7), max_range=25.0)
+    om = O.OracleMap()
+    om.add_points(pts)
+    keys, counts, xyz = om.snapshot()
+    out = dict(map_keys=keys, map_counts=counts, map_xyz=xyz, raw_xyz=sw.raw_xyz, q_init=sw.q_init, t_init=sw.t_init,
+               t_last=sw.t_last, q_true=sw.q_true, t_true=sw.t_true, prior_cov=synth.prior_covariance())
+    for tag, kw in (("nb1", dict(max_num_residuals=BIG, frame_id=100)), ("nb2", dict(max_num_residuals=BIG, frame_id=5)),
+                    ("cap", dict(max_num_residuals=100, frame_id=100))):
+        r = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw), debug=True)
+        assert r.num_fragile == 0
+        out.update({f"{tag}_status": r.status, f"{tag}_nbr": r.nbr, f"{tag}_nbr_dist": r.nbr_dist, f"{tag}_plane": r.plane,
+                    f"{tag}_HTH": r.HTH, f"{tag}_HTh": r.HTh, f"{tag}_loss": np.array(r.loss_sum),
+                    f"{tag}_num_residuals": np.array(r.num_residuals), f"{tag}_world": r.world_xyz,
+                    f"{tag}_sum_candidates": np.array(r.sum_candidates)})
+    e0 = O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+    res = om.update_iekf(sw.raw_xyz, e0, sw.t_last, O.r3live_params(max_num_residuals=BIG))
+    out.update(iekf_passes=np.array(res["passes"]), iekf_trace=res["trace"], iekf_p=res["eskf"].p, iekf_q=res["eskf"].q,
+               iekf_v=res["eskf"].v, iekf_g=res["eskf"].g, iekf_cov=res["eskf"].cov)
+    np.savez_compressed(os.path.join(HERE, "scan_matching.npz"), **out)
+    print("scan_matching.npz:", keys.shape[0], "voxels,", int(counts.sum()), "map points,", sw.raw_xyz.shape[0], "keypoints,",
+          int(r.num_residuals), "residuals(cap case), iekf passes", res["passes"])
+
+
+def map_insert_fixture():
+    rng = synth.rng_for(31)
+    # a 12 m x 12 m ground patch + one wall, offered in two batches (the second into an already-populated map)
+    def patch(n):
+        g = np.stack([rng.random(n) * 12 - 3, rng.random(n) * 12 - 3, np.zeros(n)], 1)
+        g[:, 2] = synth.ground_h(g[:, 0], g[:, 1])
+        w = np.stack([np.full(n // 2, 4.37), rng.random(n // 2) * 12 - 3, rng.random(n // 2) * 5], 1)
+        p = np.concatenate([g, w]) + rng.normal(0, 1e-3, (n + n // 2, 3))
+        return p[rng.permutation(p.shape[0])]
+    a, b = patch(3000), patch(1500)
+    om = O.OracleMap()
+    n1 = om.add_points(a)
+    k1, c1, x1 = om.snapshot()
+    n2 = om.add_points(b)
+    k2, c2, x2 = om.snapshot()
+    np.savez_compressed(os.path.join(HERE, "map_insert.npz"), batch_a=a, batch_b=b, added_a=np.array(n1), added_b=np.array(n2),
+                        keys_a=k1, counts_a=c1, xyz_a=x1, keys_b=k2, counts_b=c2, xyz_b=x2)
+    print("map_insert.npz:", n1, "+", n2, "points,", k2.shape[0], "voxels")
+
+
+if __name__ == "__main__":
+    scan_matching_fixture()
+    map_insert_fixture()

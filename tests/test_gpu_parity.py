@@ -1,0 +1,359 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): point-to-voxel association bit-exact (status + the 20 neighbour ids per keypoint,
+in order); residuals / Jacobians / normal equations / state within 1e-5 relative.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from sr_livo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+BIG = 2 ** 31 - 1
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def L():
+    from sr_livo_b200 import lio
+    obj = lio.LioOptimization(max_voxels=1 << 18, sweep_capacity=1 << 17)
+    yield obj
+    obj.close()
+
+
+def _map_dict(keys, counts, xyz):
+    return {tuple(k): x[:c].copy() for k, c, x in zip(keys.tolist(), counts.tolist(), xyz)}
+
+
+def _assert_map_equal(L, om):
+    g = _map_dict(*L.voxel_map.download())
+    o = _map_dict(*om.snapshot())
+    assert g.keys() == o.keys()
+    bad = [k for k in o if not np.array_equal(g[k], o[k])]
+    assert not bad, bad[:5]
+    assert L.voxel_map.stats() == (om.num_voxels, om.num_points)
+
+
+def _assert_pass_equal(g, o, full_cov=True):
+    assert o.num_fragile == 0
+    assert np.array_equal(g.status, o.status)
+    full = o.status >= 1
+    assert np.array_equal(g.nbr[full], o.nbr[full])
+    assert np.array_equal(g.world_xyz[o.status >= 0], o.world_xyz[o.status >= 0])   # same op order, no FMA: bit-exact
+    assert np.array_equal(g.nbr_dist[full], o.nbr_dist[full])
+    assert g.num_residuals == o.num_residuals and g.num_full_neighborhoods == o.num_full_neighborhoods
+    assert g.num_candidates_scanned <= o.sum_candidates
+    if full.any():
+        ref, got = o.plane[full], g.plane[full]
+        scale = np.maximum(np.abs(ref).max(axis=0), 1e-12)
+        assert np.all(np.abs(got - ref) <= REL * scale)
+    if o.num_residuals:
+        assert np.abs(g.HTH - o.HTH).max() <= REL * np.abs(o.HTH).max()
+        assert np.abs(g.HTh - o.HTh).max() <= REL * max(np.abs(o.HTh).max(), 1e-12)
+        assert abs(g.loss_sum - o.loss_sum) <= REL * o.loss_sum
+    assert g.success == o.success
+
+
+# ---- map: K3 insert / K4 mirror ---------------------------------------------------------------------------------
+def test_map_insert_matches_oracle_including_second_sweep(L, small_world):
+    L.voxel_map.clear()
+    om = O.OracleMap()
+    pts = small_world["pts"]
+    assert L.addPointsToMap(pts) == om.add_points(pts)
+    _assert_map_equal(L, om)
+    for i in range(3):   # three registered sweeps into the populated map (present-voxel path, order dependence)
+        sw = synth.make_sweep(15000, seed=1100 + i, yaw=0.3 * i, position=(1.0 * i, 3.0, 1.8))
+        reg = synth.registered_points(sw)
+        assert L.addPointsToMap(reg) == om.add_points(reg)
+    _assert_map_equal(L, om)
+    # offering the same points again adds nothing (distance 0 to themselves): idempotence
+    assert L.addPointsToMap(reg) == 0 == om.add_points(reg)
+
+
+def test_map_insert_edge_cases(L):
+    L.voxel_map.clear()
+    om = O.OracleMap()
+    assert L.addPointsToMap(np.zeros((0, 3))) == 0                              # empty batch
+    rng = np.random.default_rng(4)
+    neg = rng.uniform(-3, 3, (5000, 3))                                         # keys -2..2 incl. the double-width cell 0
+    assert L.addPointsToMap(neg, min_distance_points=0.05) == om.add_points(neg, min_distance_points=0.05)
+    one = np.array([[100.25, -7.5, 3.125]])
+    assert L.addPointsToMap(one) == om.add_points(one) == 1
+    dup = np.repeat(one, 50, axis=0)                                            # same point 50 times in one batch
+    assert L.addPointsToMap(dup) == om.add_points(dup) == 0
+    edge = np.array([[0.99999999999, 0.1, 0.1], [-0.99999999999, 0.1, 0.1]])    # float rounding moves the key
+    assert L.addPointsToMap(edge) == om.add_points(edge)
+    far = rng.uniform(-3, 3, (300, 3)) + 500.0
+    assert L.addPointsToMap(far, min_num_points=1) == om.add_points(far, min_num_points=1) == 0   # never creates voxels
+    grow = rng.uniform(-3, 3, (3000, 3))
+    assert L.addPointsToMap(grow, min_distance_points=0.05, min_num_points=3) == om.add_points(grow, min_distance_points=0.05, min_num_points=3)
+    _assert_map_equal(L, om)
+
+
+def test_map_upload_download_roundtrip(L, small_world):
+    om = small_world["omap"]
+    keys, counts, xyz = om.snapshot()
+    L.voxel_map.upload(keys, counts, xyz)
+    _assert_map_equal(L, om)
+    from sr_livo_b200 import capi
+    with pytest.raises(capi.SrlError):                                            # duplicate keys are rejected
+        L.voxel_map.upload(np.concatenate([keys[:4], keys[:1]]), np.concatenate([counts[:4], counts[:1]]),
+                           np.concatenate([xyz[:4], xyz[:1]]))
+
+
+def test_map_full_is_reported():
+    from sr_livo_b200 import capi, lio
+    ctx = lio.Context(0)
+    m = lio.VoxelHashMap(ctx, max_voxels=8)
+    pts = np.stack([np.arange(20) + 0.5, np.full(20, 0.5), np.full(20, 0.5)], 1)
+    with pytest.raises(capi.SrlError) as ei:
+        m.insert(pts)
+    assert ei.value.code == capi.SRL_MAP_FULL
+    assert m.stats() == (0, 0)                                                    # nothing was mutated
+    m.close(); ctx.close()
+
+
+# ---- one pass ---------------------------------------------------------------------------------------------------
+def _load_world(L, world):
+    keys, counts, xyz = world["omap"].snapshot()
+    L.voxel_map.upload(keys, counts, xyz)
+    return world["omap"], world["sweep"]
+
+
+@pytest.mark.parametrize("kw", [
+    dict(max_num_residuals=BIG),                                   # steady state nb=1
+    dict(max_num_residuals=BIG, frame_id=5),                       # init frames: nb=2, thr=1
+    dict(max_num_residuals=600),                                   # r3live.yaml cap
+    dict(max_num_residuals=-1),                                    # compiled default: stops after first full keypoint
+    dict(max_num_residuals=BIG, threshold_voxel_occupancy=15),     # sparse voxels ignored
+    dict(max_num_residuals=BIG, max_number_neighbors=10, min_number_neighbors=10),
+    dict(max_num_residuals=BIG, max_number_neighbors=20, min_number_neighbors=5),
+    dict(max_num_residuals=BIG, power_planarity=1.5, max_dist_to_plane_icp=0.05, weight_alpha=0.5, weight_neighborhood=0.5),
+    dict(max_num_residuals=BIG, voxel_neighborhood=0),
+])
+def test_pass_matches_oracle(L, small_world, kw):
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    L.setKeypoints(sw.raw_xyz)
+    g = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
+    o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw), debug=True)
+    _assert_pass_equal(g, o)
+
+
+def test_pass_config1_20k_points_200k_map(L, cfg1_world):
+    """BASELINE config 1: 20k-pt sweep, ~200k-pt map, 1 ESIKF iteration, r3live params (cap lifted and cap 600)."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, cfg1_world)
+    assert 150_000 < om.num_points < 260_000
+    L.setKeypoints(sw.raw_xyz)
+    for cap in (BIG, 600):
+        g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=cap), sw.q_init, sw.t_init, sw.t_last, debug=True)
+        o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=cap), debug=True)
+        _assert_pass_equal(g, o)
+
+
+def test_pass_extrinsics_and_unnormalised_quaternion(L, small_world):
+    """R_il / t_il are applied before the pose; the distance/Jacobian use the UN-normalised quaternion (src/optimize.cpp:95)."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    R_il = synth.quat_to_rot(synth.quat_from_rotvec([0.02, -0.01, 0.03]))
+    t_il = np.array([0.05, -0.02, 0.1])
+    raw = (sw.raw_xyz - t_il) @ R_il            # so that R_il raw + t_il == the original body points
+    q = sw.q_init * 1.0000003                    # slightly un-normalised, as after many compositions
+    L.R_imu_lidar, L.t_imu_lidar = R_il, t_il
+    try:
+        L.setKeypoints(raw)
+        g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=BIG), q, sw.t_init, sw.t_last, debug=True)
+    finally:
+        L.R_imu_lidar, L.t_imu_lidar = np.eye(3), np.zeros(3)
+    o = om.build_plane_residuals(raw, q, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), R_il=R_il, t_il=t_il, debug=True)
+    _assert_pass_equal(g, o)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 257])
+def test_pass_ragged_sizes(L, small_world, n):
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    raw = sw.raw_xyz[:n]
+    if n == 0:
+        L.sweep.upload(np.zeros((0, 3)))
+        L.sweep.n = 0
+        g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=BIG), sw.q_init, sw.t_init, sw.t_last)
+        assert g.num_residuals == 0 and not g.success and np.all(g.HTH == 0)
+        return
+    L.setKeypoints(raw)
+    g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=BIG), sw.q_init, sw.t_init, sw.t_last, debug=True)
+    o = om.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    _assert_pass_equal(g, o)
+
+
+def test_pass_keypoints_outside_the_map_and_empty_map(L, small_world):
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    raw = sw.raw_xyz[:500].copy()
+    raw[::2] += 5000.0                                   # half of them nowhere near the map
+    L.setKeypoints(raw)
+    g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=BIG), sw.q_init, sw.t_init, sw.t_last, debug=True)
+    o = om.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    _assert_pass_equal(g, o)
+    assert np.all(g.status[::2] == 0)
+    L.voxel_map.clear()
+    g = L.buildPlaneResiduals(lio.r3live_params(max_num_residuals=BIG), sw.q_init, sw.t_init, sw.t_last)
+    assert g.num_residuals == 0 and not g.success       # SRL_TOO_FEW_RESIDUALS <-> summary.success = false
+
+
+def test_pass_is_deterministic_and_shards_sum_to_the_whole(L, small_world):
+    from sr_livo_b200 import dist, lio
+    om, sw = _load_world(L, small_world)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz)
+    a = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+    b = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+    assert np.array_equal(a.HTH, b.HTH) and np.array_equal(a.HTh, b.HTh) and a.loss_sum == b.loss_sum   # bitwise
+    n = sw.raw_xyz.shape[0]
+    for world in (2, 4, 8):
+        HTH = np.zeros((6, 6)); HTh = np.zeros(6); res = 0
+        for r in range(world):
+            bgn, end = dist.shard_range(n, r, world)
+            L.sweep.set_shard(bgn, end)
+            p = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+            HTH += p.HTH; HTh += p.HTh; res += p.num_residuals
+        L.sweep.set_shard(0, n)
+        assert res == a.num_residuals
+        assert np.abs(HTH - a.HTH).max() <= 1e-12 * np.abs(a.HTH).max()
+        assert np.abs(HTh - a.HTh).max() <= 1e-11 * np.abs(a.HTh).max()
+
+
+def test_async_pass_into_a_caller_buffer(L, small_world):
+    import torch
+    from sr_livo_b200 import capi, dist, lio
+    om, sw = _load_world(L, small_world)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz)
+    ref = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+    blk = torch.full((32,), -1.0, dtype=torch.float64, device="cuda:0")
+    fr = lio.make_frame(sw.q_init, sw.t_init, sw.t_last)
+    rc = capi.lib().srl_build_plane_residuals_async(L.ctx.h, L.voxel_map.h, L.sweep.h, C.byref(fr), C.byref(prm),
+                                                    C.c_void_p(blk.data_ptr()))
+    assert rc == 0
+    L.ctx.synchronize()
+    ne = dist.unpack_block(blk.cpu().numpy())
+    assert np.array_equal(np.array(ne.HTH).reshape(6, 6), ref.HTH) and ne.num_residuals == ref.num_residuals
+    # the cap is not available on the async form
+    rc = capi.lib().srl_build_plane_residuals_async(L.ctx.h, L.voxel_map.h, L.sweep.h, C.byref(fr),
+                                                    C.byref(lio.r3live_params()), C.c_void_p(blk.data_ptr()))
+    assert rc == capi.SRL_BAD_ARG
+
+
+def test_bad_arguments_are_rejected(L, small_world):
+    from sr_livo_b200 import capi, lio
+    om, sw = _load_world(L, small_world)
+    L.setKeypoints(sw.raw_xyz[:64])
+    for kw in (dict(max_number_neighbors=33), dict(max_number_neighbors=0), dict(min_number_neighbors=0),
+               dict(voxel_neighborhood=3), dict(size_voxel_map=0.5)):
+        with pytest.raises(capi.SrlError) as ei:
+            L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last)
+        assert ei.value.code == capi.SRL_BAD_ARG
+
+
+# ---- the iterated update ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(max_num_residuals=BIG), dict(max_num_residuals=600),
+                                dict(max_num_residuals=BIG, frame_id=5, num_iters_icp=3),
+                                dict(max_num_residuals=BIG, threshold_translation_norm=0.0)])
+def test_update_iekf_matches_oracle(L, small_world, kw):
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    n = 1500 if kw.get("frame_id") == 5 else sw.raw_xyz.shape[0]
+    raw = sw.raw_xyz[:n]
+    P = synth.prior_covariance()
+    L.setKeypoints(raw)
+    L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), v=np.array([0.3, 0.0, 0.0]), cov=P.copy())
+    summ, fq, ft = L.updateIEKF(lio.r3live_params(**kw), sw.t_last)
+    ref = om.update_iekf(raw, O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), v=np.array([0.3, 0.0, 0.0]), cov=P.copy()), sw.t_last,
+                         O.r3live_params(**kw))
+    assert summ.success == ref["success"] and summ.passes_run == ref["passes"]
+    assert summ.num_residuals_used == ref["num_residuals_used"]
+    assert np.allclose(summ.trace, ref["trace"], rtol=REL, atol=1e-9)
+    e, r = L.eskf_pro, ref["eskf"]
+    for f in ("p", "q", "v", "ba", "bg", "g"):
+        assert np.allclose(getattr(e, f), getattr(r, f), rtol=REL, atol=1e-9), f
+    assert np.allclose(e.cov, r.cov, rtol=1e-4, atol=1e-12)
+    assert np.allclose(fq, ref["frame_q"], atol=1e-9) and np.allclose(ft, ref["frame_t"], atol=1e-9)
+    if kw.get("max_num_residuals") == BIG and "frame_id" not in kw:
+        assert np.linalg.norm(e.p - sw.t_true) < 0.01           # it actually registers the sweep
+
+
+def test_update_iekf_reports_too_few_residuals(L, small_world):
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    L.setKeypoints(sw.raw_xyz[:5])
+    L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+    summ, _, _ = L.updateIEKF(lio.r3live_params(max_num_residuals=BIG), sw.t_last)
+    assert not summ.success and summ.passes_run == 1
+    assert np.array_equal(L.eskf_pro.p, sw.t_init)            # state untouched, like the early return at src/optimize.cpp:155
+
+
+def test_optimize_host_end_to_end(L, small_world):
+    """optimize() with host buffers: H2D, updateIEKF, final re-transform of the frame (src/optimize.cpp:441-445)."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+    summ, fq, ft, world = L.optimize(sw.raw_xyz, lio.r3live_params(max_num_residuals=BIG), sw.t_last)
+    ref = om.update_iekf(sw.raw_xyz, O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance()), sw.t_last,
+                         O.r3live_params(max_num_residuals=BIG))
+    assert summ.passes_run == ref["passes"] and np.allclose(ft, ref["frame_t"], atol=1e-9)
+    expect = sw.raw_xyz @ O.quat_to_rot(fq).T + ft
+    assert np.allclose(world, expect, rtol=0, atol=1e-10)
+    # registered points go straight into the map, like stateEstimation (src/lioOptimization.cpp:1027)
+    before = L.mapSize()
+    added = L.addPointsToMap(world)
+    assert L.mapSize() == before + added
+
+
+# ---- BASELINE-size properties (size-independent checks; the oracle would take too long to be the checker) ---------
+def test_full_size_properties_100k_sweep_large_map():
+    from sr_livo_b200 import dist, lio
+    L = lio.LioOptimization(max_voxels=1 << 21, sweep_capacity=1 << 17)
+    try:
+        pts = synth.sample_map_points(400.0, 60.0, seed=2)                 # ~4.5M-point map
+        added = L.addPointsToMap(pts)
+        nv, npts = L.voxel_map.stats()
+        assert added == npts and 3_000_000 < npts < 8_000_000
+        assert L.addPointsToMap(pts[:200000]) == 0                          # re-offering stored points adds nothing
+        keys, counts, xyz = L.voxel_map.download()
+        assert counts.sum() == npts and counts.max() <= 20 and counts.min() >= 1
+        assert len({tuple(k) for k in keys.tolist()}) == nv                  # keys unique
+        cell = np.trunc(xyz.astype(np.float64)).astype(np.int64)             # every stored point lies in its voxel
+        mask = np.arange(20)[None, :] < counts[:, None]
+        assert np.all((cell == keys[:, None, :].astype(np.int64))[mask])
+        sw = synth.make_sweep(100000, seed=1000, yaw=0.5)
+        prm = lio.r3live_params(max_num_residuals=BIG)
+        L.setKeypoints(sw.raw_xyz)
+        a = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        b = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+        assert np.array_equal(a.HTH, b.HTH) and a.num_residuals == b.num_residuals        # deterministic
+        assert a.num_residuals <= a.num_full_neighborhoods <= 100000 and a.num_residuals > 50000
+        assert np.allclose(a.HTH, a.HTH.T) and np.linalg.eigvalsh(a.HTH).min() > 0
+        acc = a.status == 2
+        J, h = a.plane[acc, 6:12], a.plane[acc, 13] * a.plane[acc, 14]
+        assert np.allclose(a.HTH, J.T @ J, rtol=1e-10) and np.allclose(a.HTh, J.T @ h, rtol=1e-9, atol=1e-9)
+        full = a.status >= 1
+        assert np.all(np.diff(a.nbr_dist[full], axis=1) >= 0)               # neighbour lists sorted by distance
+        assert np.all(np.abs(np.linalg.norm(a.plane[full, 3:6], axis=1) - 1) < 1e-12)
+        HTH = np.zeros((6, 6)); res = 0
+        for r in range(8):                                                  # 8-way shard sum == whole
+            L.sweep.set_shard(*dist.shard_range(100000, r, 8))
+            p = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+            HTH += p.HTH; res += p.num_residuals
+        L.sweep.set_shard(0, 100000)
+        assert res == a.num_residuals and np.abs(HTH - a.HTH).max() <= 1e-11 * np.abs(a.HTH).max()
+        L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+        summ, fq, ft = L.updateIEKF(prm, sw.t_last)
+        assert summ.success and np.linalg.norm(L.eskf_pro.p - sw.t_true) < 0.01
+        after = L.buildPlaneResiduals(prm, fq, ft, sw.t_last)
+        assert after.loss_sum < 0.2 * a.loss_sum                            # registration reduced the residual
+    finally:
+        L.close()
