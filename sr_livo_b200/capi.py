@@ -65,7 +65,7 @@ class IekfIter(C.Structure):
 # every symbol include/srlivo_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "srl_abi_version", "srl_build_info", "srl_icp_params_r3live", "srl_ctx_create", "srl_ctx_destroy",
-    "srl_last_error", "srl_ctx_synchronize", "srl_ctx_kernel_launches", "srl_ctx_set_timing", "srl_ctx_pass_time", "srl_map_create", "srl_map_destroy",
+    "srl_last_error", "srl_ctx_synchronize", "srl_ctx_kernel_launches", "srl_ctx_set_timing", "srl_ctx_pass_time", "srl_ctx_set_option", "srl_ctx_get_counter", "srl_map_create", "srl_map_destroy",
     "srl_map_clear", "srl_map_stats", "srl_map_upload", "srl_map_download", "srl_map_insert",
     "srl_map_insert_device", "srl_sweep_create", "srl_sweep_destroy", "srl_sweep_upload", "srl_sweep_set_device",
     "srl_sweep_set_shard", "srl_build_plane_residuals", "srl_build_plane_residuals_async", "srl_normal_eq_unpack",
@@ -96,6 +96,8 @@ def lib():
     L.srl_ctx_synchronize.argtypes = [vp]
     L.srl_ctx_kernel_launches.argtypes = [vp]
     L.srl_ctx_kernel_launches.restype = i64
+    L.srl_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.srl_ctx_get_counter.argtypes = [vp, C.c_char_p, C.POINTER(i64)]
     L.srl_ctx_set_timing.argtypes = [vp, C.c_int]
     L.srl_ctx_pass_time.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64), C.c_int]
     L.srl_map_create.argtypes = [vp, dbl, i32, sz, C.POINTER(vp)]

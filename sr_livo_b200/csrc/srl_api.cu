@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 
 #include "srl_internal.h"
 
@@ -96,7 +97,7 @@ static void unpack32(const double* o, srl_normal_eq* out, long long n_keypoints)
 
 static int pass_grid(srl_ctx* ctx, long long n, int K, int nb) {
     const long long n_groups = (n + 31) / 32;
-    long long want = (n_groups + kK1Warps - 1) / kK1Warps;
+    long long want = n_groups;   // block-minor group assignment: one group per block first, then per warp
     const long long resident = (long long)ctx->sm_count * k1_max_blocks_per_sm(K, nb);
     if (want > resident) want = resident;
     if (want < 1) want = 1;
@@ -150,6 +151,8 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
               cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
     if (!ok) { srl_ctx_destroy(ctx); cudaGetLastError(); return SRL_CUDA_ERROR; }
@@ -161,7 +164,7 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats);
     cudaFree(ctx->d_scratch);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -178,6 +181,30 @@ int srl_ctx_synchronize(srl_ctx* ctx) {
     return SRL_OK;
 }
 int64_t srl_ctx_kernel_launches(const srl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return SRL_BAD_ARG;
+    const std::string n(name);
+    if (n == "force_exact_selection") { ctx->force_exact = value != 0; return SRL_OK; }
+    if (n == "k1_min_blocks") {
+        if (value != 2 && value != 3 && value != 4) return set_err(ctx, SRL_BAD_ARG, "k1_min_blocks must be 2, 3 or 4");
+        k1_set_min_blocks((int)value);
+        return SRL_OK;
+    }
+    return set_err(ctx, SRL_BAD_ARG, "unknown option " + n);
+}
+int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value) {
+    if (!ctx || !name || !value) return SRL_BAD_ARG;
+    const std::string n(name);
+    if (n == "exact_fallbacks") {
+        unsigned long long v = 0;
+        SRL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_stats, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *value = (int64_t)v;
+        return SRL_OK;
+    }
+    if (n == "kernel_launches") { *value = ctx->launches; return SRL_OK; }
+    return set_err(ctx, SRL_BAD_ARG, "unknown counter " + n);
+}
 int srl_ctx_set_timing(srl_ctx* ctx, int enable) {
     if (!ctx) return SRL_BAD_ARG;
     if (enable && !ctx->ev0) {
@@ -254,6 +281,8 @@ static int fill_k1_args(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const srl_fra
     a.slots = map->d_slots; a.mask = (unsigned)(map->capacity - 1); a.blocks = map->d_blocks;
     a.raw = sw->d_raw; a.k_begin = (long long)sw->shard_begin; a.k_end = (long long)sw->shard_end;
     a.partials = ctx->d_partials; a.ticket = ctx->d_ticket; a.out32 = ctx->d_out32;
+    a.stats = ctx->d_stats;
+    a.eps_scale = ctx->force_exact ? std::numeric_limits<float>::infinity() : 1.0f;
     return SRL_OK;
 }
 

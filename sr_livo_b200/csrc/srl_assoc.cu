@@ -20,6 +20,8 @@
 //
 // The 32-double result block: [0..20] HTH upper triangle (row-major a<=b), [21..26] H^T h, [27] sum d^2,
 // [28] residuals, [29] keypoints with a full neighbourhood, [30] map points scanned, [31] NaN-planarity count.
+#include <cstdlib>
+
 #include "srl_internal.h"
 
 namespace srl {
@@ -28,16 +30,23 @@ __constant__ signed char c_off[125 * 4];   // voxel offsets ordered by |offset|^
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NBS = 33;   // padded stride of the per-warp neighbour tile (bank-conflict free both ways)
+typedef unsigned long long u64;
 
-__device__ __forceinline__ bool lex_less(double da, unsigned ia, double db, unsigned ib) {
-    return da < db || (da == db && ia < ib);
+// (distance^2 bits, reference visit index) lexicographic order on integers: distances are non-negative doubles, so
+// their bit patterns order like the values; no FP64 compares, no branches.
+__device__ __forceinline__ bool key_less(u64 da, unsigned ia, u64 db, unsigned ib) {
+    return (da < db) | ((da == db) & (ia < ib));
+}
+__device__ __forceinline__ float warp_min_pos(float x) {   // x >= 0 (or +inf): uint order == float order
+    return __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(x)));
 }
 
-struct SmemNb {
-    const float* x_; const float* y_; const float* z_; int lane;
-    __device__ __forceinline__ float x(int j) const { return x_[j * NBS + lane]; }
-    __device__ __forceinline__ float y(int j) const { return y_[j * NBS + lane]; }
-    __device__ __forceinline__ float z(int j) const { return z_[j * NBS + lane]; }
+// the 20 neighbours of this lane's keypoint: indices into the block pool, gathered from L1/L2 in phase 2
+struct TileNb {
+    const float* blocks; const unsigned* tile; int lane;
+    __device__ __forceinline__ float x(int j) const { return __ldg(blocks + tile[j * NBS + lane]); }
+    __device__ __forceinline__ float y(int j) const { return __ldg(blocks + tile[j * NBS + lane] + kOffY); }
+    __device__ __forceinline__ float z(int j) const { return __ldg(blocks + tile[j * NBS + lane] + kOffZ); }
 };
 
 // 32x32 transpose-reduce: on return lane l holds sum over lanes of v[l] (31 shuffles instead of 160).
@@ -55,8 +64,199 @@ __device__ __forceinline__ double transpose_reduce32(double (&v)[32], int lane) 
     return v[0];
 }
 
-template <int NCH, bool DEBUG>
-__global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
+// one chunk (<= 32 voxels) of the probed neighbourhood, sorted by lower bound: lane r holds the r-th nearest voxel
+struct ChunkView {
+    unsigned cnt, blk;
+    int vis;
+    float lb;
+    int n_present;
+};
+
+__device__ __forceinline__ ChunkView sort_chunk(unsigned cnt, unsigned blk, int vis, float lb, int lane) {
+    unsigned key = cnt ? ((__float_as_uint(lb) & ~31u) | (unsigned)lane) : 0xffffffffu;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const unsigned other = __shfl_xor_sync(FULL, key, j);
+            const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+            key = (lower == up) ? min(key, other) : max(key, other);
+        }
+    }
+    const int src = (int)(key & 31u);
+    ChunkView v;
+    v.cnt = __shfl_sync(FULL, cnt, src);
+    v.blk = __shfl_sync(FULL, blk, src);
+    v.vis = __shfl_sync(FULL, vis, src);
+    v.lb = __uint_as_float(key & ~31u);   // mantissa truncated downward: still a lower bound
+    v.n_present = __popc(__ballot_sync(FULL, key != 0xffffffffu));
+    return v;
+}
+
+struct KpQuery {          // warp-uniform description of the keypoint being associated
+    double px, py, pz;    // world position (FP64, reference operation order)
+    float ofx, ofy, ofz;  // float origin (the keypoint's voxel corner)
+    float rfx, rfy, rfz;  // p - origin, rounded to float
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast selection: FP32 distances with a proven error bound.
+//   d2f differs from the exact FP64 d2 by at most eps (see DESIGN.md "K1 selection"): if the (K+1)-th smallest
+//   d2f over everything that could matter exceeds the K-th by more than 2*eps, the K lanes hold exactly the K
+//   nearest points (as a set); the exact FP64 finish then orders them.  Otherwise the caller falls back to
+//   select_exact.  Voxels are skipped only when their lower bound exceeds kth + 3*eps.
+// ---------------------------------------------------------------------------------------------------------
+template <int NCH>
+__device__ __forceinline__ bool select_fast(const float* __restrict__ blocks, const ChunkView (&cv)[NCH], const KpQuery& q, int K,
+                                            float eps, int lane, float& bf, unsigned& bid, int& nfound, long long& scanned) {
+    const float INF = __int_as_float(0x7f800000);
+    bf = INF; bid = 0xffffffffu;
+    float kth = INF, rej = INF, r_ev = INF;
+    bool empty = true;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        for (int r = 0; r < cv[ch].n_present; ++r) {
+            const float lb_r = __shfl_sync(FULL, cv[ch].lb, r);
+            if (lb_r > kth + 3.f * eps) break;   // every remaining voxel of this chunk is farther still
+            const unsigned b = __shfl_sync(FULL, cv[ch].blk, r);
+            const int cn = (int)__shfl_sync(FULL, cv[ch].cnt, r);
+            const int v = __shfl_sync(FULL, cv[ch].vis, r);
+            scanned += cn;
+            float d2f = INF;
+            unsigned id = 0xffffffffu;
+            if (lane < cn) {
+                const float* bp = blocks + (size_t)b * kBlockFloats;
+                const float dx = (__ldg(bp + lane) - q.ofx) - q.rfx;
+                const float dy = (__ldg(bp + kOffY + lane) - q.ofy) - q.rfy;
+                const float dz = (__ldg(bp + kOffZ + lane) - q.ofz) - q.rfz;
+                d2f = dx * dx + dy * dy + dz * dz;
+                id = ((unsigned)v << 5) | (unsigned)lane;
+            }
+            if (empty) {
+                // first voxel: a bitonic sort of the 32 lanes initialises the list
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const float od = __shfl_xor_sync(FULL, d2f, j);
+                        const unsigned oi = __shfl_xor_sync(FULL, id, j);
+                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                        const bool take = (lower == up) ? (od < d2f) : (d2f < od);
+                        d2f = take ? od : d2f;
+                        id = take ? oi : id;
+                    }
+                }
+                rej = fminf(rej, lane >= K ? d2f : INF);   // sorted entries beyond K are rejections
+                if (lane < K) { bf = d2f; bid = id; }
+                empty = false;
+                kth = __shfl_sync(FULL, bf, K - 1);
+            } else {
+                const bool pass = d2f < kth;
+                rej = fminf(rej, pass ? INF : d2f);
+                unsigned m = __ballot_sync(FULL, pass);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float nv = __shfl_sync(FULL, d2f, j);
+                    const unsigned ni = __shfl_sync(FULL, id, j);
+                    if (nv < kth) {
+                        const int pos = __popc(__ballot_sync(FULL, bf <= nv));
+                        const float uf = __shfl_up_sync(FULL, bf, 1);
+                        const unsigned ui = __shfl_up_sync(FULL, bid, 1);
+                        r_ev = fminf(r_ev, kth);            // the old K-th entry leaves the list
+                        if (lane < K) {
+                            bf = (lane > pos) ? uf : ((lane == pos) ? nv : bf);
+                            bid = (lane > pos) ? ui : ((lane == pos) ? ni : bid);
+                        }
+                        kth = __shfl_sync(FULL, bf, K - 1);
+                    } else {
+                        r_ev = fminf(r_ev, nv);             // threshold tightened meanwhile
+                    }
+                }
+            }
+        }
+    }
+    nfound = __popc(__ballot_sync(FULL, lane < K && bf < INF));
+    if (nfound < K) return true;   // every candidate seen is in the list, nothing was skipped (kth stayed +inf)
+    const float rmin = fminf(warp_min_pos(rej), r_ev);
+    return rmin > kth + 2.f * eps;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Exact selection (fallback for ambiguous keypoints): FP64 distances in the reference's operation order
+// (src/optimize.cpp:394-395), K-best list ordered by (distance^2 bits, reference visit index).
+// ---------------------------------------------------------------------------------------------------------
+template <int NCH>
+__device__ __forceinline__ void select_exact(const float* __restrict__ blocks, const ChunkView (&cv)[NCH], const KpQuery& q, int K,
+                                             int lane, u64& bd, unsigned& bid, int& nfound, long long& scanned) {
+    const u64 KINF = 0x7ff0000000000000ull;
+    bd = KINF; bid = 0xffffffffu;
+    u64 kth_d = KINF;
+    unsigned kth_id = 0xffffffffu;
+    bool empty = true;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        for (int r = 0; r < cv[ch].n_present; ++r) {
+            const float lb_r = __shfl_sync(FULL, cv[ch].lb, r);
+            if ((u64)__double_as_longlong((double)lb_r) > kth_d) break;
+            const unsigned b = __shfl_sync(FULL, cv[ch].blk, r);
+            const int cn = (int)__shfl_sync(FULL, cv[ch].cnt, r);
+            const int v = __shfl_sync(FULL, cv[ch].vis, r);
+            scanned += cn;
+            u64 d = KINF;
+            unsigned id = 0xffffffffu;
+            if (lane < cn) {
+                const float* bp = blocks + (size_t)b * kBlockFloats;
+                const double mx = (double)__ldg(bp + lane), my = (double)__ldg(bp + kOffY + lane), mz = (double)__ldg(bp + kOffZ + lane);
+                const double dx = SRL_SUB(mx, q.px), dy = SRL_SUB(my, q.py), dz = SRL_SUB(mz, q.pz);
+                d = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+                id = ((unsigned)v << 5) | (unsigned)lane;
+            }
+            if (empty) {
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const u64 od = __shfl_xor_sync(FULL, d, j);
+                        const unsigned oi = __shfl_xor_sync(FULL, id, j);
+                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                        const bool take = (lower == up) ? key_less(od, oi, d, id) : key_less(d, id, od, oi);
+                        d = take ? od : d;
+                        id = take ? oi : id;
+                    }
+                }
+                if (lane < K) { bd = d; bid = id; }
+                empty = false;
+            } else {
+                unsigned m = __ballot_sync(FULL, key_less(d, id, kth_d, kth_id));
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u64 nd = __shfl_sync(FULL, d, j);
+                    const unsigned ni = __shfl_sync(FULL, id, j);
+                    if (key_less(nd, ni, kth_d, kth_id)) {
+                        const int pos = __popc(__ballot_sync(FULL, key_less(bd, bid, nd, ni)));
+                        const u64 ud = __shfl_up_sync(FULL, bd, 1);
+                        const unsigned ui = __shfl_up_sync(FULL, bid, 1);
+                        if (lane < K) {
+                            bd = (lane > pos) ? ud : ((lane == pos) ? nd : bd);
+                            bid = (lane > pos) ? ui : ((lane == pos) ? ni : bid);
+                        }
+                        kth_d = __shfl_sync(FULL, bd, K - 1);
+                        kth_id = __shfl_sync(FULL, bid, K - 1);
+                    }
+                }
+                continue;
+            }
+            kth_d = __shfl_sync(FULL, bd, K - 1);
+            kth_id = __shfl_sync(FULL, bid, K - 1);
+        }
+    }
+    nfound = __popc(__ballot_sync(FULL, lane < K && bd < KINF));
+}
+
+template <int NCH, bool DEBUG, int MINB>
+__global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -66,31 +266,32 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
     const int W = 2 * nb + 1;
     const int V = W * W * W;
 
-    // per-warp shared memory: neighbour tile 3 x K x 33 floats, then block index per visited voxel (128 ints)
-    const size_t warp_bytes = (size_t)(3 * K * NBS) * sizeof(float) + 128 * sizeof(int);
-    float* nbx = reinterpret_cast<float*>(smem_raw + warp * warp_bytes);
-    float* nby = nbx + K * NBS;
-    float* nbz = nby + K * NBS;
-    int* sblk = reinterpret_cast<int*>(nbz + K * NBS);
+    // per-warp shared memory: K x 33 point indices (into the block pool), then block index per visited voxel
+    const size_t warp_bytes = (size_t)(K * NBS) * sizeof(unsigned) + 128 * sizeof(int);
+    unsigned* tile = reinterpret_cast<unsigned*>(smem_raw + warp * warp_bytes);
+    int* sblk = reinterpret_cast<int*>(tile + K * NBS);
 
     const float size_f = (float)c.size;
     const float lb_margin = 1e-5f * size_f;
+    const float eps = 1e-4f * size_f * size_f * A.eps_scale;   // bound on |d2f - d2|, with margin
 
     double acc = 0.0;                 // lane i accumulates component i of the 32-double result
     long long scanned = 0;            // warp-uniform: map points whose distance was evaluated
+    unsigned fallbacks = 0;           // warp-uniform: keypoints that needed the exact selection
 
     const long long n = A.k_end - A.k_begin;
     const long long n_groups = (n + 31) / 32;
-    const long long gwarp = (long long)blockIdx.x * kK1Warps + warp;
-    const long long total_warps = (long long)gridDim.x * kK1Warps;
+    // block-minor assignment: consecutive groups go to different blocks (SMs), so every SM gets ~the same share
+    const long long G = gridDim.x;
 
-    for (long long g = gwarp; g < n_groups; g += total_warps) {
+    for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kK1Warps) {
         // ------------------------------------------------------------------ prologue: thread per keypoint
         const long long k = A.k_begin + g * 32 + lane;
         const bool valid = k < A.k_end;
         double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
         int kx = 0, ky = 0, kz = 0;
-        float relx = 0, rely = 0, relz = 0;
+        float relx = 0, rely = 0, relz = 0;       // p - exact voxel corner (for the cell lower bounds)
+        float ofx = 0, ofy = 0, ofz = 0, rfx = 0, rfy = 0, rfz = 0;   // float origin and p - origin
         bool in_range = false;
         if (valid) {
             const double rx = A.raw[3 * k], ry = A.raw[3 * k + 1], rz = A.raw[3 * k + 2];
@@ -103,9 +304,10 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
             in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;   // (short) cast is UB beyond
             if (in_range) {
                 kx = (int)qx; ky = (int)qy; kz = (int)qz;   // truncation toward zero, like static_cast<short>
-                relx = (float)(pwx - (double)kx * c.size);
-                rely = (float)(pwy - (double)ky * c.size);
-                relz = (float)(pwz - (double)kz * c.size);
+                const double cx = (double)kx * c.size, cy = (double)ky * c.size, cz = (double)kz * c.size;
+                relx = (float)(pwx - cx); rely = (float)(pwy - cy); relz = (float)(pwz - cz);
+                ofx = (float)cx; ofy = (float)cy; ofz = (float)cz;
+                rfx = (float)(pwx - (double)ofx); rfy = (float)(pwy - (double)ofy); rfz = (float)(pwz - (double)ofz);
             }
             if (DEBUG && A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
         }
@@ -115,27 +317,30 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
         const int n_in_group = (int)min((long long)32, n - g * 32);
         for (int kp = 0; kp < n_in_group; ++kp) {
             if (!__shfl_sync(FULL, (int)in_range, kp)) continue;
-            const double px = __shfl_sync(FULL, pwx, kp), py = __shfl_sync(FULL, pwy, kp), pz = __shfl_sync(FULL, pwz, kp);
+            KpQuery q;
+            q.px = __shfl_sync(FULL, pwx, kp); q.py = __shfl_sync(FULL, pwy, kp); q.pz = __shfl_sync(FULL, pwz, kp);
+            q.ofx = __shfl_sync(FULL, ofx, kp); q.ofy = __shfl_sync(FULL, ofy, kp); q.ofz = __shfl_sync(FULL, ofz, kp);
+            q.rfx = __shfl_sync(FULL, rfx, kp); q.rfy = __shfl_sync(FULL, rfy, kp); q.rfz = __shfl_sync(FULL, rfz, kp);
             const int ckx = __shfl_sync(FULL, kx, kp), cky = __shfl_sync(FULL, ky, kp), ckz = __shfl_sync(FULL, kz, kp);
             const float rlx = __shfl_sync(FULL, relx, kp), rly = __shfl_sync(FULL, rely, kp), rlz = __shfl_sync(FULL, relz, kp);
 
-            // ---- probes: lane o handles voxel offset o of the chunk
-            unsigned cnt[NCH], blk[NCH];
-            float lb[NCH];
-            int vis[NCH];
+            // ---- probes: lane o handles voxel offset o of the chunk; then order each chunk by lower bound
+            ChunkView cv[NCH];
             int total = 0;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                cnt[ch] = 0; blk[ch] = 0; vis[ch] = 0; lb[ch] = 0.f;
+                unsigned cnt = 0, blk = 0;
+                int vis = 0;
+                float lb = 0.f;
                 const int o = ch * 32 + lane;
                 if (o < V) {
                     const int ox = c_off[4 * o], oy = c_off[4 * o + 1], oz = c_off[4 * o + 2];
                     const int vx = ckx + ox, vy = cky + oy, vz = ckz + oz;
-                    vis[ch] = ((ox + nb) * W + (oy + nb)) * W + (oz + nb);   // reference scan order (:379-381)
+                    vis = ((ox + nb) * W + (oy + nb)) * W + (oz + nb);   // reference scan order (:379-381)
                     unsigned b, cn;
                     if (map_find(A.slots, A.mask, vx, vy, vz, b, cn) && (int)cn >= c.thr_occ) {   // :386-390
-                        cnt[ch] = cn; blk[ch] = b;
-                        sblk[vis[ch]] = (int)b;
+                        cnt = cn; blk = b;
+                        sblk[vis] = (int)b;
                         // conservative lower bound of the distance to any point stored under key (vx,vy,vz):
                         // cell k>0 spans [k,k+1), k<0 spans (k-1,k], k=0 spans (-1,1) (truncation toward zero)
                         const float lox = (float)((vx > 0 ? vx : vx - 1) - ckx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - ckx) * size_f;
@@ -144,107 +349,62 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
                         const float gx = fmaxf(fmaxf(lox - rlx, rlx - hix) - lb_margin, 0.f);
                         const float gy = fmaxf(fmaxf(loy - rly, rly - hiy) - lb_margin, 0.f);
                         const float gz = fmaxf(fmaxf(loz - rlz, rlz - hiz) - lb_margin, 0.f);
-                        lb[ch] = (gx * gx + gy * gy + gz * gz) * 0.999999f;
+                        lb = (gx * gx + gy * gy + gz * gz) * 0.999999f;
                     }
                 }
-                total += (int)cnt[ch];
+                total += (int)cnt;
+                cv[ch] = sort_chunk(cnt, blk, vis, lb, lane);
             }
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) total += __shfl_xor_sync(FULL, total, s);
+            total = __reduce_add_sync(FULL, total);
             if (total < c.Kmin) continue;   // fewer candidates than min_number_neighbors: :78 will skip it
             __syncwarp();                   // sblk[] visible to the whole warp
 
-            // ---- K-best list: lane j holds the j-th smallest (d2, id); lanes >= K hold +inf
-            double best_d2 = CUDART_INF, kth_d2 = CUDART_INF;
-            unsigned best_id = 0xffffffffu, kth_id = 0xffffffffu;
-            bool list_empty = true;
+            // ---- K nearest: FP32 selection with exact FP64 finish, or the exact selection when ambiguous
+            float bf;
+            unsigned bid;
+            int nfound;
+            u64 key = ~0ull;
+            const bool sure = select_fast<NCH>(A.blocks, cv, q, K, eps, lane, bf, bid, nfound, scanned);
+            if (!sure) { select_exact<NCH>(A.blocks, cv, q, K, lane, key, bid, nfound, scanned); ++fallbacks; }
 
-#pragma unroll
-            for (int ch = 0; ch < NCH; ++ch) {
-                // sort this chunk's voxels by lower bound (ascending); absent voxels last
-                unsigned key = cnt[ch] ? ((__float_as_uint(lb[ch]) & ~31u) | (unsigned)lane) : 0xffffffffu;
-#pragma unroll
-                for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-                    for (int j = kk >> 1; j > 0; j >>= 1) {
-                        const unsigned other = __shfl_xor_sync(FULL, key, j);
-                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
-                        key = (lower == up) ? min(key, other) : max(key, other);
+            if (nfound >= c.Kmin) {
+                unsigned pt = 0;
+                if (lane < nfound) {
+                    pt = (unsigned)sblk[bid >> 5] * kBlockFloats + (bid & 31u);
+                    if (sure) {   // exact distance of the selected points, reference operation order (:394-395)
+                        const double mx = (double)__ldg(A.blocks + pt), my = (double)__ldg(A.blocks + pt + kOffY), mz = (double)__ldg(A.blocks + pt + kOffZ);
+                        const double dx = SRL_SUB(mx, q.px), dy = SRL_SUB(my, q.py), dz = SRL_SUB(mz, q.pz);
+                        key = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
                     }
+                } else {
+                    key = ~0ull; bid = 0xffffffffu;
                 }
-                const int src = (int)(key & 31u);
-                const unsigned s_cnt = __shfl_sync(FULL, cnt[ch], src);
-                const unsigned s_blk = __shfl_sync(FULL, blk[ch], src);
-                const int s_vis = __shfl_sync(FULL, vis[ch], src);
-                const float s_lb = __uint_as_float(key & ~31u);   // mantissa truncated downward: still a lower bound
-                const int n_present = __popc(__ballot_sync(FULL, key != 0xffffffffu));
-
-                for (int r = 0; r < n_present; ++r) {
-                    const float lb_r = __shfl_sync(FULL, s_lb, r);
-                    if ((double)lb_r > kth_d2) break;   // every remaining voxel of this chunk is farther
-                    const unsigned b = __shfl_sync(FULL, s_blk, r);
-                    const int cn = (int)__shfl_sync(FULL, s_cnt, r);
-                    const int v = __shfl_sync(FULL, s_vis, r);
-                    scanned += cn;
-                    double d2 = CUDART_INF;
-                    unsigned id = 0xffffffffu;
-                    if (lane < cn) {
-                        const float* bp = A.blocks + (size_t)b * kBlockFloats;
-                        const double mx = (double)__ldg(bp + lane), my = (double)__ldg(bp + kOffY + lane), mz = (double)__ldg(bp + kOffZ + lane);
-                        const double dx = SRL_SUB(mx, px), dy = SRL_SUB(my, py), dz = SRL_SUB(mz, pz);   // :394-395
-                        d2 = SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz)));
-                        id = ((unsigned)v << 5) | (unsigned)lane;
-                    }
-                    if (list_empty) {
-                        // first voxel: bitonic sort of the 32 lanes by (d2, id) initialises the list
+                if (sure) {
+                    // the FP32 order is almost always the exact order; sort exactly only if an inversion shows up
+                    const u64 pk = __shfl_up_sync(FULL, key, 1);
+                    const unsigned pi = __shfl_up_sync(FULL, bid, 1);
+                    const bool inv = lane > 0 && lane < nfound && key_less(key, bid, pk, pi);
+                    if (__any_sync(FULL, inv)) {
 #pragma unroll
                         for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
                             for (int j = kk >> 1; j > 0; j >>= 1) {
-                                const double od = __shfl_xor_sync(FULL, d2, j);
-                                const unsigned oi = __shfl_xor_sync(FULL, id, j);
+                                const u64 od = __shfl_xor_sync(FULL, key, j);
+                                const unsigned oi = __shfl_xor_sync(FULL, bid, j);
                                 const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
-                                const bool take = (lower == up) ? lex_less(od, oi, d2, id) : lex_less(d2, id, od, oi);
-                                if (take) { d2 = od; id = oi; }
+                                const bool take = (lower == up) ? key_less(od, oi, key, bid) : key_less(key, bid, od, oi);
+                                key = take ? od : key;
+                                bid = take ? oi : bid;
                             }
                         }
-                        if (lane < K) { best_d2 = d2; best_id = id; }
-                        list_empty = false;
-                    } else {
-                        unsigned m = __ballot_sync(FULL, lex_less(d2, id, kth_d2, kth_id));
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            m &= m - 1;
-                            const double nd = __shfl_sync(FULL, d2, j);
-                            const unsigned ni = __shfl_sync(FULL, id, j);
-                            if (!lex_less(nd, ni, kth_d2, kth_id)) continue;   // threshold tightened meanwhile
-                            const int pos = __popc(__ballot_sync(FULL, lex_less(best_d2, best_id, nd, ni)));
-                            const double ud = __shfl_up_sync(FULL, best_d2, 1);
-                            const unsigned ui = __shfl_up_sync(FULL, best_id, 1);
-                            if (lane < K) {
-                                if (lane > pos) { best_d2 = ud; best_id = ui; }
-                                else if (lane == pos) { best_d2 = nd; best_id = ni; }
-                            }
-                            kth_d2 = __shfl_sync(FULL, best_d2, K - 1);
-                            kth_id = __shfl_sync(FULL, best_id, K - 1);
-                        }
-                        continue;
+                        if (lane < nfound) pt = (unsigned)sblk[bid >> 5] * kBlockFloats + (bid & 31u);
                     }
-                    kth_d2 = __shfl_sync(FULL, best_d2, K - 1);
-                    kth_id = __shfl_sync(FULL, best_id, K - 1);
                 }
-            }
-
-            const int nfound = __popc(__ballot_sync(FULL, lane < K && best_d2 < CUDART_INF));
-            if (nfound >= c.Kmin) {
                 if (lane < nfound) {
-                    const int v = (int)(best_id >> 5), i = (int)(best_id & 31u);
-                    const float* bp = A.blocks + (size_t)sblk[v] * kBlockFloats;
-                    nbx[lane * NBS + kp] = __ldg(bp + i);
-                    nby[lane * NBS + kp] = __ldg(bp + kOffY + i);
-                    nbz[lane * NBS + kp] = __ldg(bp + kOffZ + i);
+                    tile[lane * NBS + kp] = pt;
                     if (DEBUG) {
                         const long long kk = A.k_begin + g * 32 + kp;
+                        const int v = (int)(bid >> 5), i = (int)(bid & 31u);
                         if (A.dbg_nbr) {
                             short* d = A.dbg_nbr + (kk * K + lane) * 4;
                             d[0] = (short)(ckx + v / (W * W) - nb);
@@ -252,7 +412,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
                             d[2] = (short)(ckz + v % W - nb);
                             d[3] = (short)i;
                         }
-                        if (A.dbg_nbr_dist) A.dbg_nbr_dist[kk * K + lane] = sqrt(best_d2);
+                        if (A.dbg_nbr_dist) A.dbg_nbr_dist[kk * K + lane] = sqrt(__longlong_as_double((long long)key));
                     }
                 }
                 if (lane == kp) my_count = nfound;
@@ -268,7 +428,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
         int status = 0;
         if (valid && my_count > 0) {
             PlaneRow row;
-            SmemNb acc_nb{nbx, nby, nbz, lane};
+            TileNb acc_nb{A.blocks, tile, lane};
             plane_residual(acc_nb, my_count, c, pwx, pwy, pwz, bx, by, bz, row);
             status = row.accepted ? 2 : 1;
             v[29] = 1.0;
@@ -308,6 +468,7 @@ __global__ void __launch_bounds__(kK1Threads, 2) k1_assoc(const K1Args A) {
         __syncwarp();   // the neighbour tile is rewritten by the next group
     }
     if (lane == 30) acc += (double)scanned;
+    if (A.stats && lane == 0 && fallbacks) atomicAdd(A.stats, (unsigned long long)fallbacks);
 
     // ---------------------------------------------------------------------- block + grid reduction
     __shared__ double s_acc[kK1Warps][32];
@@ -472,14 +633,36 @@ static void upload_offsets(int device) {
     if (device >= 0 && device < 64) g_off_uploaded[device] = true;
 }
 
-size_t k1_smem_bytes(int K) { return (size_t)kK1Warps * ((size_t)(3 * K * NBS) * sizeof(float) + 128 * sizeof(int)); }
+size_t k1_smem_bytes(int K) { return (size_t)kK1Warps * ((size_t)(K * NBS) * sizeof(unsigned) + 128 * sizeof(int)); }
+
+typedef void (*K1Fn)(const K1Args);
+static int g_minb = -1;
+void k1_set_min_blocks(int v) { if (v == 2 || v == 3 || v == 4) g_minb = v; }
+int k1_min_blocks() {   // resident blocks per SM the kernel is compiled for; SRL_K1_MINB=2|3|4 selects the variant
+    if (g_minb < 0) {
+        const char* e = getenv("SRL_K1_MINB");
+        int v = e ? atoi(e) : 3;
+        g_minb = (v == 2 || v == 3 || v == 4) ? v : 3;
+    }
+    return g_minb;
+}
+template <int NCH, bool DBG>
+static K1Fn pick_minb() {
+    switch (k1_min_blocks()) {
+        case 2: return k1_assoc<NCH, DBG, 2>;
+        case 4: return k1_assoc<NCH, DBG, 4>;
+        default: return k1_assoc<NCH, DBG, 3>;
+    }
+}
+static K1Fn pick_k1(int nb, bool debug) {
+    if (nb <= 1) return debug ? pick_minb<1, true>() : pick_minb<1, false>();
+    return debug ? pick_minb<4, true>() : pick_minb<4, false>();
+}
 
 cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream) {
     upload_offsets(device);
     const size_t smem = k1_smem_bytes(a.c.K);
-    void (*fn)(const K1Args) = nullptr;
-    if (a.c.nb == 1) fn = debug ? k1_assoc<1, true> : k1_assoc<1, false>;
-    else fn = debug ? k1_assoc<4, true> : k1_assoc<4, false>;
+    K1Fn fn = pick_k1(a.c.nb, debug);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<grid, kK1Threads, smem, stream>>>(a);
@@ -488,7 +671,7 @@ cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStr
 
 int k1_max_blocks_per_sm(int K, int nb) {
     int nblk = 0;
-    void (*fn)(const K1Args) = (nb == 1) ? k1_assoc<1, false> : k1_assoc<4, false>;
+    K1Fn fn = pick_k1(nb, false);
     const size_t smem = k1_smem_bytes(K);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, kK1Threads, smem) != cudaSuccess) return 1;

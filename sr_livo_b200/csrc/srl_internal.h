@@ -33,10 +33,13 @@ struct K1Args {
     short* dbg_nbr;
     double* dbg_nbr_dist;
     double* dbg_plane;
+    unsigned long long* stats;   // optional device counters: [0] keypoints that took the exact-selection fallback
+    float eps_scale;             // 1 normally; +inf forces the exact selection for every keypoint (tests)
 };
 
 size_t k1_smem_bytes(int K);
 int k1_max_blocks_per_sm(int K, int nb);
+void k1_set_min_blocks(int v);
 cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream);
 cudaError_t launch_k2(const double* rows, int* status, long long k_begin, long long k_end, int cap, long long* state,
                       double* out32, int mark_unvisited, cudaStream_t stream);
@@ -68,6 +71,8 @@ struct srl_ctx {
     double* d_out32 = nullptr;
     double* h_out32 = nullptr;      // pinned
     long long* d_k2_state = nullptr;
+    unsigned long long* d_stats = nullptr;   // 4 counters
+    bool force_exact = false;
     // generic scratch (map insert)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;

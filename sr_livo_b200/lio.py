@@ -63,6 +63,14 @@ class Context:
     def kernel_launches(self) -> int:
         return int(lib().srl_ctx_kernel_launches(self.h))
 
+    def set_option(self, name: str, value: int):
+        _check(self.h, lib().srl_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def counter(self, name: str) -> int:
+        v = C.c_int64(0)
+        _check(self.h, lib().srl_ctx_get_counter(self.h, name.encode(), C.byref(v)))
+        return v.value
+
     def set_timing(self, enable: bool = True):
         _check(self.h, lib().srl_ctx_set_timing(self.h, 1 if enable else 0))
 

@@ -45,7 +45,6 @@ def _assert_pass_equal(g, o, full_cov=True):
     assert np.array_equal(g.world_xyz[o.status >= 0], o.world_xyz[o.status >= 0])   # same op order, no FMA: bit-exact
     assert np.array_equal(g.nbr_dist[full], o.nbr_dist[full])
     assert g.num_residuals == o.num_residuals and g.num_full_neighborhoods == o.num_full_neighborhoods
-    assert g.num_candidates_scanned <= o.sum_candidates
     if full.any():
         ref, got = o.plane[full], g.plane[full]
         scale = np.maximum(np.abs(ref).max(axis=0), 1e-12)
@@ -141,6 +140,33 @@ def test_pass_matches_oracle(L, small_world, kw):
     g = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
     o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw), debug=True)
     _assert_pass_equal(g, o)
+
+
+@pytest.mark.parametrize("kw", [dict(max_num_residuals=BIG), dict(max_num_residuals=BIG, frame_id=5)])
+def test_exact_selection_path_matches_oracle(L, small_world, kw):
+    """k1_assoc selects in FP32 with an error bound and redoes ambiguous keypoints exactly; forcing every keypoint
+    through the exact FP64 selection must give the same (oracle-identical) answer, and on normal data the exact
+    path must be the exception."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    n = 1500
+    L.setKeypoints(sw.raw_xyz[:n])
+    o = om.build_plane_residuals(sw.raw_xyz[:n], sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw), debug=True)
+    before = L.ctx.counter("exact_fallbacks")
+    g_fast = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
+    mid = L.ctx.counter("exact_fallbacks")
+    L.ctx.set_option("force_exact_selection", 1)
+    try:
+        g_exact = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
+    finally:
+        L.ctx.set_option("force_exact_selection", 0)
+    after = L.ctx.counter("exact_fallbacks")
+    _assert_pass_equal(g_fast, o)
+    _assert_pass_equal(g_exact, o)
+    assert np.array_equal(g_fast.nbr, g_exact.nbr) and np.array_equal(g_fast.HTH, g_exact.HTH)
+    n_cand = int((o.num_candidates >= 20).sum())
+    assert after - mid == n_cand                       # forced: every keypoint with >= K candidates went the exact way
+    assert mid - before <= 0.1 * n_cand                # normal: the FP32 selection decides almost all of them
 
 
 def test_pass_config1_20k_points_200k_map(L, cfg1_world):
