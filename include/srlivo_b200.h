@@ -132,9 +132,11 @@ int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
 /* CUDA-event timing of the scan-matching kernel (k1_assoc) on the ctx stream: enable, then read the summed device
  * time and launch count of the passes since the last reset (bench.py "roofline"). Reading synchronises the stream. */
 int srl_ctx_set_timing(srl_ctx* ctx, int enable);
-/* tuning / test knobs: "force_exact_selection" (0|1: every keypoint takes the exact FP64 selection path),
- * "k1_min_blocks" (2|3|4: resident-blocks-per-SM variant of k1_assoc).  Counters: "exact_fallbacks" (keypoints whose
- * FP32 selection was ambiguous and were redone exactly), "kernel_launches". */
+/* tuning / test knobs: "force_exact_selection" (0|1: every keypoint takes k1_assoc's exact FP64 selection),
+ * "k1_variant" (0 auto: k1_fast + exact fallback where applicable; 2: k1_assoc only), "k1_min_blocks" (2|3|4) and
+ * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels.  Counters: "exact_fallbacks"
+ * (keypoints whose FP32 selection in k1_assoc was ambiguous and were redone exactly), "fast_ambiguous" (keypoints
+ * k1_fast handed to k1_assoc), "kernel_launches". */
 int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value);
 int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value);
 int srl_ctx_pass_time(srl_ctx* ctx, double* total_ms, int64_t* launches, int reset);

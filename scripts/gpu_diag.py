@@ -103,7 +103,7 @@ ocap = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, opr
 print("cap600: residuals", gcap.num_residuals, ocap.num_residuals, "status equal", np.array_equal(gcap.status, ocap.status),
       "HTH rel", np.abs(gcap.HTH - ocap.HTH).max() / np.abs(ocap.HTH).max())
 
-print("exact fallbacks so far:", L.ctx.counter("exact_fallbacks"))
+print("exact fallbacks so far:", L.ctx.counter("exact_fallbacks"), "fast ambiguous:", L.ctx.counter("fast_ambiguous"))
 # rough timing of the pass
 import torch
 torch.cuda.synchronize()

@@ -117,12 +117,45 @@ static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
     return SRL_OK;
 }
 
-static cudaError_t timed_launch_k1(srl_ctx* ctx, const K1Args& a, int grid, bool debug) {
+// One pass on the ctx stream.  Fast form (k1_fast + k1_assoc on the flagged keypoints) when the configuration allows
+// it, k1_assoc alone otherwise (nb = 2, K != 20, residual cap, forced exact selection).
+static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug) {
+    const long long n = a.k_end - a.k_begin;
+    const bool fast = !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
     if (ctx->timing) { timing_collect(ctx); cudaEventRecord(ctx->ev0, ctx->stream); }
-    cudaError_t e = launch_k1(a, grid, debug, ctx->device, ctx->stream);
+    if (!fast) {
+        SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), debug, ctx->device, ctx->stream));
+        ctx->launches += 1;
+    } else {
+        int rc;
+        if ((rc = ensure_buf(ctx, &sw->d_order, sw->capacity)) != SRL_OK) return rc;
+        if ((rc = ensure_buf(ctx, &sw->d_flags, sw->capacity)) != SRL_OK) return rc;
+        if (!sw->order_valid) {
+            size_t need = 0;
+            sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, nullptr, 0, &need, ctx->stream);
+            if ((rc = ensure_scratch(ctx, need)) != SRL_OK) return rc;
+            SRL_CUDA(ctx, sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, ctx->d_scratch, ctx->scratch_bytes, &need, ctx->stream));
+            sw->order_valid = true;
+            ctx->launches += 1;
+        }
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
+        FastArgs f;
+        std::memset(&f, 0, sizeof(f));
+        f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
+        f.s_begin = a.k_begin; f.s_end = a.k_end;   // the shard is a range of SORTED positions in this form
+        f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
+        f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
+        const long long n_groups = (n + 31) / 32;
+        long long grid = std::min<long long>(n_groups, (long long)ctx->sm_count * k1_fast_max_blocks_per_sm());
+        grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
+        SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
+        K1Args b = a;   // exact selection for the keypoints k1_fast could not decide; its last block adds k1_fast's sums
+        b.k_begin = 0; b.k_end = (long long)sw->n; b.only_flagged = sw->d_flags; b.prev_out32 = ctx->d_fast_out;
+        SRL_CUDA(ctx, launch_k1(b, pass_grid(ctx, (long long)sw->n, b.c.K, b.c.nb), debug, ctx->device, ctx->stream));
+        ctx->launches += 2;
+    }
     if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-    ctx->launches += 1;
-    return e;
+    return SRL_OK;
 }
 
 extern "C" {
@@ -152,6 +185,7 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
               cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_fast_out, 32 * sizeof(double)) == cudaSuccess &&
               cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
@@ -164,7 +198,7 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out);
     cudaFree(ctx->d_scratch);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -185,6 +219,16 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return SRL_BAD_ARG;
     const std::string n(name);
     if (n == "force_exact_selection") { ctx->force_exact = value != 0; return SRL_OK; }
+    if (n == "fast_min_blocks") {
+        if (value != 4 && value != 5 && value != 6 && value != 8) return set_err(ctx, SRL_BAD_ARG, "fast_min_blocks must be 4, 5, 6 or 8");
+        k1_fast_set_min_blocks((int)value);
+        return SRL_OK;
+    }
+    if (n == "k1_variant") {
+        if (value != 0 && value != 2) return set_err(ctx, SRL_BAD_ARG, "k1_variant must be 0 (auto) or 2 (k1_assoc only)");
+        ctx->variant = (int)value;
+        return SRL_OK;
+    }
     if (n == "k1_min_blocks") {
         if (value != 2 && value != 3 && value != 4) return set_err(ctx, SRL_BAD_ARG, "k1_min_blocks must be 2, 3 or 4");
         k1_set_min_blocks((int)value);
@@ -198,6 +242,13 @@ int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value) {
     if (n == "exact_fallbacks") {
         unsigned long long v = 0;
         SRL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_stats, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *value = (int64_t)v;
+        return SRL_OK;
+    }
+    if (n == "fast_ambiguous") {
+        unsigned long long v = 0;
+        SRL_CUDA(ctx, cudaMemcpyAsync(&v, ctx->d_stats + 1, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *value = (int64_t)v;
         return SRL_OK;
@@ -238,7 +289,7 @@ int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out) {
 }
 void srl_sweep_destroy(srl_sweep* s) {
     if (!s) return;
-    cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status);
+    cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status); cudaFree(s->d_order); cudaFree(s->d_flags);
     cudaFree(s->d_dbg_world); cudaFree(s->d_dbg_nbr); cudaFree(s->d_dbg_nbr_dist); cudaFree(s->d_dbg_plane);
     delete s;
 }
@@ -252,7 +303,7 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
     if (rc != SRL_OK) return rc;
     std::memcpy(ctx->h_pinned, raw_xyz, n * 3 * sizeof(double));
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, ctx->h_pinned, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    s->n = n; s->shard_begin = 0; s->shard_end = n;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
@@ -260,7 +311,7 @@ int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     srl_ctx* ctx = s->ctx;
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    s->n = n; s->shard_begin = 0; s->shard_end = n;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
@@ -297,8 +348,7 @@ int srl_build_plane_residuals_async(srl_ctx* ctx, srl_map* map, srl_sweep* sw, c
     a.out32 = d_out32;
     SRL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n <= 0) { SRL_CUDA(ctx, cudaMemsetAsync(d_out32, 0, 32 * sizeof(double), ctx->stream)); return SRL_OK; }
-    SRL_CUDA(ctx, timed_launch_k1(ctx, a, pass_grid(ctx, n, a.c.K, a.c.nb), false));
-    return SRL_OK;
+    return launch_pass(ctx, sw, a, false);
 }
 
 int srl_normal_eq_unpack(const double* h_out32, srl_normal_eq* out) {
@@ -344,7 +394,7 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
     if (n <= 0) {
         std::memset(h, 0, 32 * sizeof(double));
     } else if (!cap_mode) {
-        SRL_CUDA(ctx, timed_launch_k1(ctx, a, pass_grid(ctx, n, K, a.c.nb), debug));
+        if ((rc = launch_pass(ctx, sw, a, debug)) != SRL_OK) return rc;
         SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->timing) timing_collect(ctx);
@@ -364,7 +414,7 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
             const long long end = std::min(n, begin + chunk);
             K1Args c = a;
             c.k_begin = begin; c.k_end = end;
-            SRL_CUDA(ctx, timed_launch_k1(ctx, c, pass_grid(ctx, end - begin, K, a.c.nb), debug));
+            if ((rc = launch_pass(ctx, sw, c, debug)) != SRL_OK) return rc;
             SRL_CUDA(ctx, launch_k2(sw->d_rows, sw->d_status, begin, end, (int)cap, ctx->d_k2_state, d_cap_out, 0, ctx->stream));
             ctx->launches += 1;
             SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -475,22 +525,30 @@ int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const double* r
 // ---- host unit hook for the per-keypoint math (same source as the kernel's phase 2) -------------------------
 struct HostNb {
     const double* p;
-    float x(int j) const { return (float)p[3 * j]; }
-    float y(int j) const { return (float)p[3 * j + 1]; }
-    float z(int j) const { return (float)p[3 * j + 2]; }
+    void get(int j, float& x, float& y, float& z) const { x = (float)p[3 * j]; y = (float)p[3 * j + 1]; z = (float)p[3 * j + 2]; }
 };
 int srl_host_plane_fit(const double* nbr_xyz, int32_t K, double normal[3], double* a2D, double evals[3]) {
     if (!nbr_xyz || K < 1 || !normal || !a2D || !evals) return SRL_BAD_ARG;
-    double mx = 0, my = 0, mz = 0;
     HostNb nb{nbr_xyz};
-    for (int j = 0; j < K; ++j) { mx += (double)nb.x(j); my += (double)nb.y(j); mz += (double)nb.z(j); }
+    // run the same plane_residual the kernel runs, with an identity pose, and read normal / a2D back
+    PassConst c;
+    std::memset(&c, 0, sizeof(c));
+    c.Rq[0] = c.Rq[4] = c.Rq[8] = 1.0; c.Rn[0] = c.Rn[4] = c.Rn[8] = 1.0; c.R_il[0] = c.R_il[4] = c.R_il[8] = 1.0;
+    c.size = 1.0; c.lambda_w = 0.9; c.lambda_n = 0.1; c.power = 2.0; c.dmax = 0.3; c.exp_den = 6.0; c.K = K; c.Kmin = K; c.nb = 1; c.thr_occ = 1;
+    PlaneRow row;
+    plane_residual<0>(nb, K, nbr_xyz[0], nbr_xyz[1], nbr_xyz[2], c, nbr_xyz[0], nbr_xyz[1], nbr_xyz[2], 0.0, 0.0, 0.0, row);
+    normal[0] = row.nx; normal[1] = row.ny; normal[2] = row.nz;
+    // eigenvalues from the same solver
+    double mx = 0, my = 0, mz = 0;
+    for (int j = 0; j < K; ++j) { mx += (double)(float)nbr_xyz[3 * j]; my += (double)(float)nbr_xyz[3 * j + 1]; mz += (double)(float)nbr_xyz[3 * j + 2]; }
     mx /= K; my /= K; mz /= K;
     double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
     for (int j = 0; j < K; ++j) {
-        double dx = (double)nb.x(j) - mx, dy = (double)nb.y(j) - my, dz = (double)nb.z(j) - mz;
+        double dx = (double)(float)nbr_xyz[3 * j] - mx, dy = (double)(float)nbr_xyz[3 * j + 1] - my, dz = (double)(float)nbr_xyz[3 * j + 2] - mz;
         c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
     }
-    eig3_sym(c00, c01, c11, c02, c12, c22, evals, normal[0], normal[1], normal[2]);
+    double n0, n1, n2;
+    eig3_sym(c00, c01, c11, c02, c12, c22, evals, n0, n1, n2);
     *a2D = (std::sqrt(std::fabs(evals[1])) - std::sqrt(std::fabs(evals[0]))) / std::sqrt(std::fabs(evals[2]));
     return SRL_OK;
 }

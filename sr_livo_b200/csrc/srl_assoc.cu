@@ -41,12 +41,13 @@ __device__ __forceinline__ float warp_min_pos(float x) {   // x >= 0 (or +inf): 
     return __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(x)));
 }
 
-// the 20 neighbours of this lane's keypoint: indices into the block pool, gathered from L1/L2 in phase 2
+// the K neighbours of this lane's keypoint: float indices into the block pool, gathered from L1/L2 in phase 2
 struct TileNb {
     const float* blocks; const unsigned* tile; int lane;
-    __device__ __forceinline__ float x(int j) const { return __ldg(blocks + tile[j * NBS + lane]); }
-    __device__ __forceinline__ float y(int j) const { return __ldg(blocks + tile[j * NBS + lane] + kOffY); }
-    __device__ __forceinline__ float z(int j) const { return __ldg(blocks + tile[j * NBS + lane] + kOffZ); }
+    __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + tile[j * NBS + lane]));
+        x = p.x; y = p.y; z = p.z;
+    }
 };
 
 // 32x32 transpose-reduce: on return lane l holds sum over lanes of v[l] (31 shuffles instead of 160).
@@ -125,10 +126,10 @@ __device__ __forceinline__ bool select_fast(const float* __restrict__ blocks, co
             float d2f = INF;
             unsigned id = 0xffffffffu;
             if (lane < cn) {
-                const float* bp = blocks + (size_t)b * kBlockFloats;
-                const float dx = (__ldg(bp + lane) - q.ofx) - q.rfx;
-                const float dy = (__ldg(bp + kOffY + lane) - q.ofy) - q.rfy;
-                const float dz = (__ldg(bp + kOffZ + lane) - q.ofz) - q.rfz;
+                const float4 mp = __ldg(reinterpret_cast<const float4*>(blocks + (size_t)b * kBlockFloats) + lane);
+                const float dx = (mp.x - q.ofx) - q.rfx;
+                const float dy = (mp.y - q.ofy) - q.rfy;
+                const float dz = (mp.z - q.ofz) - q.rfz;
                 d2f = dx * dx + dy * dy + dz * dz;
                 id = ((unsigned)v << 5) | (unsigned)lane;
             }
@@ -206,8 +207,8 @@ __device__ __forceinline__ void select_exact(const float* __restrict__ blocks, c
             u64 d = KINF;
             unsigned id = 0xffffffffu;
             if (lane < cn) {
-                const float* bp = blocks + (size_t)b * kBlockFloats;
-                const double mx = (double)__ldg(bp + lane), my = (double)__ldg(bp + kOffY + lane), mz = (double)__ldg(bp + kOffZ + lane);
+                const float4 mp = __ldg(reinterpret_cast<const float4*>(blocks + (size_t)b * kBlockFloats) + lane);
+                const double mx = (double)mp.x, my = (double)mp.y, mz = (double)mp.z;
                 const double dx = SRL_SUB(mx, q.px), dy = SRL_SUB(my, q.py), dz = SRL_SUB(mz, q.pz);
                 d = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
                 id = ((unsigned)v << 5) | (unsigned)lane;
@@ -287,7 +288,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kK1Warps) {
         // ------------------------------------------------------------------ prologue: thread per keypoint
         const long long k = A.k_begin + g * 32 + lane;
-        const bool valid = k < A.k_end;
+        const bool in_shard = k < A.k_end;
+        // fallback launch: only the keypoints k1_fast flagged are ours
+        const bool valid = in_shard && (!A.only_flagged || A.only_flagged[k] != 0);
+        if (A.only_flagged && !__any_sync(FULL, valid)) continue;
         double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
         int kx = 0, ky = 0, kz = 0;
         float relx = 0, rely = 0, relz = 0;       // p - exact voxel corner (for the cell lower bounds)
@@ -370,9 +374,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
             if (nfound >= c.Kmin) {
                 unsigned pt = 0;
                 if (lane < nfound) {
-                    pt = (unsigned)sblk[bid >> 5] * kBlockFloats + (bid & 31u);
+                    pt = (unsigned)sblk[bid >> 5] * kBlockFloats + 4u * (bid & 31u);
                     if (sure) {   // exact distance of the selected points, reference operation order (:394-395)
-                        const double mx = (double)__ldg(A.blocks + pt), my = (double)__ldg(A.blocks + pt + kOffY), mz = (double)__ldg(A.blocks + pt + kOffZ);
+                        const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pt));
+                        const double mx = (double)mp.x, my = (double)mp.y, mz = (double)mp.z;
                         const double dx = SRL_SUB(mx, q.px), dy = SRL_SUB(my, q.py), dz = SRL_SUB(mz, q.pz);
                         key = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
                     }
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
                                 bid = take ? oi : bid;
                             }
                         }
-                        if (lane < nfound) pt = (unsigned)sblk[bid >> 5] * kBlockFloats + (bid & 31u);
+                        if (lane < nfound) pt = (unsigned)sblk[bid >> 5] * kBlockFloats + 4u * (bid & 31u);
                     }
                 }
                 if (lane < nfound) {
@@ -429,7 +434,9 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
         if (valid && my_count > 0) {
             PlaneRow row;
             TileNb acc_nb{A.blocks, tile, lane};
-            plane_residual(acc_nb, my_count, c, pwx, pwy, pwz, bx, by, bz, row);
+            float n0x, n0y, n0z;
+            acc_nb.get(0, n0x, n0y, n0z);
+            plane_residual<0>(acc_nb, my_count, (double)n0x, (double)n0y, (double)n0z, c, pwx, pwy, pwz, bx, by, bz, row);
             status = row.accepted ? 2 : 1;
             v[29] = 1.0;
             v[31] = (double)row.nan_planarity;
@@ -498,6 +505,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
             double tot = 0.0;
 #pragma unroll
             for (int w = 0; w < kK1Warps; ++w) tot += s_acc[w][lane];
+            if (A.prev_out32) tot += A.prev_out32[lane];   // fallback launch: add k1_fast's sums (fixed order)
             A.out32[lane] = tot;
             if (lane == 0) *A.ticket = 0u;
         }

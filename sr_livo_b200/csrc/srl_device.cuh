@@ -3,10 +3,11 @@
 // Layout (B200-first, not a translation of tsl::robin_map<voxel, voxelBlock>, include/cloudMap.h:171):
 //   slot table : open addressing, power-of-two capacity >= 2 x max_voxels (load <= 0.5), 16-byte slots
 //                { u64 key (x,y,z as u16 | valid bit 48), u32 block, u32 count } -> one LDG.128 per probe.
-//   block pool : one 256-byte block per voxel, SoA inside the block:
-//                float x[20] | y[20] | z[20] | u32 key_lo, key_hi, count, pad
-//                a warp reads a coordinate plane with 20 lanes x 4 B (80 contiguous bytes); points keep the
-//                reference's insertion order, so index i in the block == index in voxelBlock::points.
+//   block pool : one 320-byte block per voxel = 20 x float4 (x, y, z, w): a point is ONE 16-byte load for a
+//                thread that scans candidates (k1_fast), and 20 lanes x 16 B = 320 contiguous bytes for a warp
+//                (k1_assoc).  The unused w lanes carry the block's metadata: pt[0].w / pt[1].w = key bits,
+//                pt[2].w = count.  Points keep the reference's insertion order, so index i in the block == index
+//                in voxelBlock::points.
 // Only key -> block *content* has to match the reference; probe order / hash are our own.
 #pragma once
 
@@ -15,9 +16,9 @@
 
 namespace srl {
 
-constexpr int kBlockFloats = 64;   // 256 B
+constexpr int kBlockFloats = 80;   // 320 B
 constexpr int kBlockCap = 20;      // max_num_points_in_voxel supported by the block layout (all reference configs use 20)
-constexpr int kOffY = 20, kOffZ = 40, kOffMeta = 60;
+constexpr int kMetaKeyLo = 0 * 4 + 3, kMetaKeyHi = 1 * 4 + 3, kMetaCount = 2 * 4 + 3;   // float index of the w lanes used
 
 struct __align__(16) Slot {
     unsigned long long key;   // 0 = empty

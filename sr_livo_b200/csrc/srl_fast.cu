@@ -1,0 +1,395 @@
+// srl_fast.cu — k1_fast: the thread-per-keypoint form of the fused scan-matching pass (sm_100a),
+// and the spatial ordering of a sweep's keypoints that makes it coalesce.
+//
+// Why a second form of K1: the warp-per-keypoint kernel (srl_assoc.cu) is a serial chain of warp shuffles per
+// keypoint (ncu, profiles/r02_*: ~1400 warp instructions per keypoint, 13 cycles between issues of a warp,
+// only ~21 working warps per SM on a 100k-point sweep).  Here one THREAD owns one keypoint:
+//   * keypoints are processed in Morton order of their LiDAR-frame cell (sorted once per sweep), so the 32 lanes
+//     of a warp sit in the same few voxels and their 16-byte point loads hit the same L1 lines;
+//   * each thread probes its 27 voxels (16 B slot loads), keeps the present ones in a private list, and walks the
+//     candidates with ONE float4 load + 9 FP32 ops each;
+//   * the K+1 = 21 best candidates live in registers as packed 32-bit keys (FP32 distance^2 with the low 10
+//     mantissa bits replaced by the candidate's id) and every candidate goes through a 21-stage min/max chain:
+//     no shuffles, no shared memory, no divergence inside the chain;
+//   * the 21st key is the guard: if it is farther than the 20th by more than the total error bound (FP32 rounding +
+//     the 10 truncated bits), the 20 keys are exactly the reference's 20 nearest points (as a set) and the thread
+//     finishes in FP64: exact distances (reference operation order), nearest neighbour, plane fit, residual,
+//     Jacobian, 32-component reduction — identical to srl_assoc.cu from there on;
+//   * otherwise the keypoint is flagged and redone by k1_assoc's exact selection (launched right after, on the
+//     flagged keypoints only), whose final step adds this kernel's sums.
+// Handles voxel_neighborhood <= 1 and max/min_number_neighbors == 20 (every reference config outside the first
+// 20 init frames); anything else goes to k1_assoc alone.
+#include <cstdlib>
+
+#include <cub/cub.cuh>
+
+#include "srl_internal.h"
+
+namespace srl {
+
+__constant__ signed char c_off_fast[27 * 4];   // the 27 offsets of the nb<=1 cube ordered by |offset|^2 (centre first)
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int KF = 20;            // neighbours kept by the fast path
+typedef unsigned long long u64;
+
+__device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const double send = upper ? v[i] : v[i + s];
+            const double keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULLM, send, s);
+        }
+    }
+    return v[0];
+}
+
+struct RegNb {   // the 20 selected points, as float indices into the block pool held in registers
+    const float* blocks;
+    const unsigned (&pt)[KF + 1];
+    __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + pt[j]));
+        x = p.x; y = p.y; z = p.z;
+    }
+};
+
+__device__ __forceinline__ float key_value(unsigned key) {   // packed key -> (truncated) FP32 distance^2
+    return key == 0xffffffffu ? __int_as_float(0x7f800000) : __uint_as_float(key & ~1023u);
+}
+
+template <bool DEBUG, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const PassConst& c = A.c;
+    const int nb = c.nb;
+    const int W = 2 * nb + 1;
+    const int V = W * W * W;
+    const float size_f = (float)c.size;
+    const float lb_margin = 1e-5f * size_f;
+    const float eps_abs = 1e-4f * size_f * size_f;   // FP32 rounding of d2f; the key truncation adds T * 2^-13
+    const float kRel = 1.0f / 2048.0f;
+
+    double acc = 0.0;
+    unsigned long long scanned = 0;
+    const long long n = A.s_end - A.s_begin;
+    const long long n_groups = (n + 31) / 32;
+    const long long G = gridDim.x;
+
+    for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kFastWarps) {
+        const long long s = A.s_begin + g * 32 + lane;
+        const bool valid = s < A.s_end;
+        const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
+        double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        float relx = 0, rely = 0, relz = 0, ofx = 0, ofy = 0, ofz = 0, rfx = 0, rfy = 0, rfz = 0;
+        bool in_range = false;
+        if (valid) {
+            const double rx = A.raw[3 * k], ry = A.raw[3 * k + 1], rz = A.raw[3 * k + 2];
+            double tx, ty, tz;
+            matvec3_exact(c.R_il, rx, ry, rz, tx, ty, tz);
+            bx = SRL_ADD(tx, c.t_il[0]); by = SRL_ADD(ty, c.t_il[1]); bz = SRL_ADD(tz, c.t_il[2]);      // src/optimize.cpp:83
+            matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);
+            pwx = SRL_ADD(tx, c.t[0]); pwy = SRL_ADD(ty, c.t[1]); pwz = SRL_ADD(tz, c.t[2]);            // :38
+            const double qx = SRL_DIV(pwx, c.size), qy = SRL_DIV(pwy, c.size), qz = SRL_DIV(pwz, c.size);   // :372-374
+            in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;
+            if (in_range) {
+                kx = (int)qx; ky = (int)qy; kz = (int)qz;
+                const double cx = (double)kx * c.size, cy = (double)ky * c.size, cz = (double)kz * c.size;
+                relx = (float)(pwx - cx); rely = (float)(pwy - cy); relz = (float)(pwz - cz);
+                ofx = (float)cx; ofy = (float)cy; ofz = (float)cz;
+                rfx = (float)(pwx - (double)ofx); rfy = (float)(pwy - (double)ofy); rfz = (float)(pwz - (double)ofz);
+            }
+            if (DEBUG && A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
+        }
+
+        // ---- probes: this thread's 27 voxels; present ones go to a private list (blk<<5|cnt , lower bound|offset)
+        unsigned ent[27], lbo[27];
+        int n_e = 0, total = 0;
+        if (in_range) {
+            for (int o = 0; o < V; ++o) {
+                const int ox = c_off_fast[4 * o], oy = c_off_fast[4 * o + 1], oz = c_off_fast[4 * o + 2];
+                const int vx = kx + ox, vy = ky + oy, vz = kz + oz;
+                unsigned b, cn;
+                if (map_find(A.slots, A.mask, vx, vy, vz, b, cn) && (int)cn >= c.thr_occ) {            // :386-390
+                    const float lox = (float)((vx > 0 ? vx : vx - 1) - kx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - kx) * size_f;
+                    const float loy = (float)((vy > 0 ? vy : vy - 1) - ky) * size_f, hiy = (float)((vy < 0 ? vy : vy + 1) - ky) * size_f;
+                    const float loz = (float)((vz > 0 ? vz : vz - 1) - kz) * size_f, hiz = (float)((vz < 0 ? vz : vz + 1) - kz) * size_f;
+                    const float gx = fmaxf(fmaxf(lox - relx, relx - hix) - lb_margin, 0.f);
+                    const float gy = fmaxf(fmaxf(loy - rely, rely - hiy) - lb_margin, 0.f);
+                    const float gz = fmaxf(fmaxf(loz - relz, relz - hiz) - lb_margin, 0.f);
+                    const float lb = (gx * gx + gy * gy + gz * gz) * 0.999999f;
+                    ent[n_e] = (b << 5) | cn;
+                    lbo[n_e] = (__float_as_uint(lb) & ~127u) | (unsigned)o;   // truncated downward: still a lower bound
+                    ++n_e;
+                    total += (int)cn;
+                }
+            }
+        }
+        const bool full_cand = in_range && total >= c.Kmin;   // else src/optimize.cpp:78 skips the keypoint
+
+        // ---- scan: every candidate through the 21-stage min/max chain on packed keys
+        unsigned lst[KF + 1];
+#pragma unroll
+        for (int j = 0; j <= KF; ++j) lst[j] = 0xffffffffu;
+        if (full_cand) {
+            int e = -1, i = 0, cnt = 0;
+            const float* bp = nullptr;
+            for (;;) {
+                if (i >= cnt) {   // next voxel of this thread's list that can still matter
+                    const float T = key_value(lst[KF - 1]);
+                    const float lim = T + T * kRel + 3.f * eps_abs;
+                    bool found = false;
+                    while (++e < n_e) {
+                        if (__uint_as_float(lbo[e] & ~127u) <= lim) { found = true; break; }
+                    }
+                    if (!found) break;
+                    cnt = (int)(ent[e] & 31u);
+                    bp = A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats;
+                    i = 0;
+                    scanned += (unsigned)cnt;
+                }
+                const float4 mp = __ldg(reinterpret_cast<const float4*>(bp) + i);
+                const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
+                const float d2f = dx * dx + dy * dy + dz * dz;
+                unsigned key = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)i;
+#pragma unroll
+                for (int j = 0; j <= KF; ++j) {
+                    const unsigned lo = min(lst[j], key);
+                    key = max(lst[j], key);
+                    lst[j] = lo;
+                }
+                ++i;
+            }
+        }
+
+        // ---- verdict: exact set, or flag for the exact kernel
+        bool ambiguous = false;
+        if (full_cand) {
+            const float T = key_value(lst[KF - 1]), R = key_value(lst[KF]);
+            ambiguous = !(R > T + T * kRel + 2.5f * eps_abs);
+        }
+        if (valid && A.flags) A.flags[k] = ambiguous ? 1 : 0;
+        const bool do_fit = full_cand && !ambiguous;
+
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+        int status = 0;
+        if (do_fit) {
+            // ---- FP64 finish: exact distances of the 20 points, nearest neighbour by (distance^2, visit index)
+            u64 best = ~0ull;
+            unsigned best_id = 0xffffffffu;
+            double n0x = 0, n0y = 0, n0z = 0;
+            u64 dkey[DEBUG ? KF : 1];
+            unsigned did[DEBUG ? KF : 1];
+#pragma unroll
+            for (int j = 0; j < KF; ++j) {
+                const unsigned e = (lst[j] >> 5) & 31u, i = lst[j] & 31u;
+                const unsigned pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
+                const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pt));
+                const double mx = (double)mp.x, my = (double)mp.y, mz = (double)mp.z;
+                const double dx = SRL_SUB(mx, pwx), dy = SRL_SUB(my, pwy), dz = SRL_SUB(mz, pwz);              // :394-395
+                const u64 dk = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+                const int o = (int)(lbo[e] & 127u);
+                const int vis = ((c_off_fast[4 * o] + nb) * W + (c_off_fast[4 * o + 1] + nb)) * W + (c_off_fast[4 * o + 2] + nb);
+                const unsigned id = ((unsigned)vis << 5) | i;   // reference visit order: breaks exact distance ties
+                if (dk < best || (dk == best && id < best_id)) { best = dk; best_id = id; n0x = mx; n0y = my; n0z = mz; }
+                if (DEBUG) { dkey[j] = dk; did[j] = id; }
+                lst[j] = pt;
+            }
+            PlaneRow row;
+            RegNb nbv{A.blocks, lst};
+            plane_residual<KF>(nbv, KF, n0x, n0y, n0z, c, pwx, pwy, pwz, bx, by, bz, row);
+            status = row.accepted ? 2 : 1;
+            v[29] = 1.0;
+            v[31] = (double)row.nan_planarity;
+            const double h = row.distance * row.weight;                                                        // :169
+            if (row.accepted) {
+                v[0] = row.J[0] * row.J[0]; v[1] = row.J[0] * row.J[1]; v[2] = row.J[0] * row.J[2];
+                v[3] = row.J[0] * row.J[3]; v[4] = row.J[0] * row.J[4]; v[5] = row.J[0] * row.J[5];
+                v[6] = row.J[1] * row.J[1]; v[7] = row.J[1] * row.J[2]; v[8] = row.J[1] * row.J[3];
+                v[9] = row.J[1] * row.J[4]; v[10] = row.J[1] * row.J[5];
+                v[11] = row.J[2] * row.J[2]; v[12] = row.J[2] * row.J[3]; v[13] = row.J[2] * row.J[4];
+                v[14] = row.J[2] * row.J[5];
+                v[15] = row.J[3] * row.J[3]; v[16] = row.J[3] * row.J[4]; v[17] = row.J[3] * row.J[5];
+                v[18] = row.J[4] * row.J[4]; v[19] = row.J[4] * row.J[5];
+                v[20] = row.J[5] * row.J[5];
+                v[21] = row.J[0] * h; v[22] = row.J[1] * h; v[23] = row.J[2] * h;
+                v[24] = row.J[3] * h; v[25] = row.J[4] * h; v[26] = row.J[5] * h;
+                v[27] = row.distance * row.distance;                                                          // :104
+                v[28] = 1.0;
+            }
+            if (DEBUG) {
+                if (A.dbg_plane) {
+                    double* d = A.dbg_plane + 16 * k;
+                    d[0] = bx; d[1] = by; d[2] = bz; d[3] = row.nx; d[4] = row.ny; d[5] = row.nz;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) d[6 + i] = row.accepted ? row.J[i] : 0.0;
+                    d[12] = row.offset; d[13] = row.distance; d[14] = row.weight; d[15] = row.a2D;
+                }
+                // neighbour list in the reference's order: ascending (distance^2, visit index)
+                for (int a = 1; a < KF; ++a) {
+                    const u64 kd = dkey[a]; const unsigned ki = did[a];
+                    int b = a - 1;
+                    while (b >= 0 && (dkey[b] > kd || (dkey[b] == kd && did[b] > ki))) { dkey[b + 1] = dkey[b]; did[b + 1] = did[b]; --b; }
+                    dkey[b + 1] = kd; did[b + 1] = ki;
+                }
+                for (int j = 0; j < KF; ++j) {
+                    const int vis = (int)(did[j] >> 5), i = (int)(did[j] & 31u);
+                    if (A.dbg_nbr) {
+                        short* d = A.dbg_nbr + (k * KF + j) * 4;
+                        d[0] = (short)(kx + vis / (W * W) - nb);
+                        d[1] = (short)(ky + (vis / W) % W - nb);
+                        d[2] = (short)(kz + vis % W - nb);
+                        d[3] = (short)i;
+                    }
+                    if (A.dbg_nbr_dist) A.dbg_nbr_dist[k * KF + j] = sqrt(__longlong_as_double((long long)dkey[j]));
+                }
+            }
+        }
+        if (valid && A.status && !ambiguous) A.status[k] = status;
+        if (ambiguous && A.stats) atomicAdd(A.stats + 1, 1ull);
+        __syncwarp();
+        acc += transpose_reduce32f(v, lane);
+    }
+    // per-thread scanned counts -> component 30
+    {
+        double sc = (double)scanned;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) sc += __shfl_xor_sync(FULLM, sc, s);
+        if (lane == 30) acc += sc;
+    }
+
+    __shared__ double s_acc[kFastWarps][32];
+    __shared__ bool s_last;
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFastWarps; ++w) s += s_acc[w][lane];
+        A.partials[(size_t)blockIdx.x * 32 + lane] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(A.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = warp; b < (int)gridDim.x; b += kFastWarps) s += __ldcg(A.partials + (size_t)b * 32 + lane);
+        s_acc[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kFastWarps; ++w) tot += s_acc[w][lane];
+            A.out32[lane] = tot;
+            if (lane == 0) *A.ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sweep ordering: Morton code of the LiDAR-frame 1 m cell of every keypoint, stable radix sort -> order[]
+// (a rigid transform keeps neighbours neighbours, so the order is pose independent and computed once per sweep)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 spread21(u64 x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double cell, u64* keys, unsigned* idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double lim = 1048575.0;
+    const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 524288.0, 0.0), lim);
+    const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 524288.0, 0.0), lim);
+    const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 524288.0, 0.0), lim);
+    keys[i] = spread21((u64)fx) | (spread21((u64)fy) << 1) | (spread21((u64)fz) << 2);
+    idx[i] = (unsigned)i;
+}
+
+cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
+                                size_t* needed, cudaStream_t stream) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (u64*)nullptr, (u64*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 63, stream);
+    const size_t need = al(n * 8) * 2 + al(n * 4) + al(tmp);
+    if (needed) *needed = need;
+    if (!scratch || scratch_bytes < need) return cudaSuccess;
+    char* p = static_cast<char*>(scratch);
+    u64* ka = reinterpret_cast<u64*>(p); p += al(n * 8);
+    u64* kb = reinterpret_cast<u64*>(p); p += al(n * 8);
+    unsigned* ia = reinterpret_cast<unsigned*>(p); p += al(n * 4);
+    const int T = 256;
+    k_sweep_keys<<<(unsigned)((n + T - 1) / T), T, 0, stream>>>(d_raw, n, 1.0, ka, ia);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cub::DeviceRadixSort::SortPairs(p, tmp, ka, kb, ia, d_order, (int)n, 0, 63, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static bool g_fast_off_uploaded[64] = {false};
+static void upload_fast_offsets(int device) {
+    if (device >= 0 && device < 64 && g_fast_off_uploaded[device]) return;
+    signed char tab[27 * 4];
+    int n = 0;
+    for (int d2 = 0; d2 <= 3; ++d2)
+        for (int x = -1; x <= 1; ++x)
+            for (int y = -1; y <= 1; ++y)
+                for (int z = -1; z <= 1; ++z) {
+                    if (x * x + y * y + z * z != d2) continue;
+                    tab[4 * n] = (signed char)x; tab[4 * n + 1] = (signed char)y; tab[4 * n + 2] = (signed char)z; tab[4 * n + 3] = 0;
+                    ++n;
+                }
+    cudaMemcpyToSymbol(c_off_fast, tab, sizeof(tab));
+    if (device >= 0 && device < 64) g_fast_off_uploaded[device] = true;
+}
+
+typedef void (*FastFn)(const FastArgs);
+static int g_fast_minb = -1;
+void k1_fast_set_min_blocks(int v) { if (v == 4 || v == 5 || v == 6 || v == 8) g_fast_minb = v; }
+static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant (default 6)
+    if (g_fast_minb < 0) {
+        const char* e = getenv("SRL_FAST_MINB");
+        const int v = e ? atoi(e) : 6;
+        g_fast_minb = (v == 4 || v == 5 || v == 6 || v == 8) ? v : 6;
+    }
+    return g_fast_minb;
+}
+template <bool DBG>
+static FastFn pick_fast() {
+    switch (fast_minb()) {
+        case 4: return k1_fast<DBG, 4>;
+        case 5: return k1_fast<DBG, 5>;
+        case 8: return k1_fast<DBG, 8>;
+        default: return k1_fast<DBG, 6>;
+    }
+}
+
+cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream) {
+    upload_fast_offsets(device);
+    FastFn fn = debug ? pick_fast<true>() : pick_fast<false>();
+    fn<<<grid, kFastThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+int k1_fast_max_blocks_per_sm() {
+    int nblk = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, pick_fast<false>(), kFastThreads, 0) != cudaSuccess) return 1;
+    return nblk < 1 ? 1 : nblk;
+}
+
+}  // namespace srl

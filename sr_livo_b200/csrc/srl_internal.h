@@ -33,9 +33,40 @@ struct K1Args {
     short* dbg_nbr;
     double* dbg_nbr_dist;
     double* dbg_plane;
+    const unsigned char* only_flagged;   // optional: process only keypoints whose flag is set (k1_fast's ambiguous ones)
+    const double* prev_out32;            // optional: 32 doubles added to the final sums
     unsigned long long* stats;   // optional device counters: [0] keypoints that took the exact-selection fallback
     float eps_scale;             // 1 normally; +inf forces the exact selection for every keypoint (tests)
 };
+
+constexpr int kFastWarps = 4;
+constexpr int kFastThreads = kFastWarps * 32;
+
+struct FastArgs {               // k1_fast (srl_fast.cu)
+    PassConst c;
+    const Slot* slots;
+    unsigned int mask;
+    const float* blocks;
+    const double* raw;          // sweep, n*3 (device)
+    const unsigned* order;      // sorted position -> keypoint index (nullptr: identity)
+    long long s_begin, s_end;   // this rank's range of sorted positions
+    double* partials;
+    unsigned int* ticket;
+    double* out32;
+    unsigned char* flags;       // per keypoint: 1 = ambiguous, redo with k1_assoc's exact selection
+    int* status;
+    double* dbg_world;
+    short* dbg_nbr;
+    double* dbg_nbr_dist;
+    double* dbg_plane;
+    unsigned long long* stats;  // [1] += ambiguous keypoints
+};
+
+cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
+int k1_fast_max_blocks_per_sm();
+void k1_fast_set_min_blocks(int v);
+cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
+                                size_t* needed, cudaStream_t stream);
 
 size_t k1_smem_bytes(int K);
 int k1_max_blocks_per_sm(int K, int nb);
@@ -72,7 +103,9 @@ struct srl_ctx {
     double* h_out32 = nullptr;      // pinned
     long long* d_k2_state = nullptr;
     unsigned long long* d_stats = nullptr;   // 4 counters
+    double* d_fast_out = nullptr;            // k1_fast's 32 sums, added by the exact-fallback launch
     bool force_exact = false;
+    int variant = 0;                         // 0 auto (k1_fast + exact fallback when applicable), 2 = k1_assoc only
     // generic scratch (map insert)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -98,6 +131,9 @@ struct srl_sweep {
     size_t n = 0;
     size_t shard_begin = 0, shard_end = 0;
     double* d_raw = nullptr;        // capacity*3
+    unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
+    bool order_valid = false;
+    unsigned char* d_flags = nullptr;   // capacity
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
     int* d_status = nullptr;        // capacity, lazily allocated
     // debug buffers, lazily allocated

@@ -44,16 +44,16 @@ __global__ void k_upload_slots(Slot* slots, unsigned int mask, float* blocks, co
     const int x = keys[3 * v], y = keys[3 * v + 1], z = keys[3 * v + 2];
     const unsigned long long key = pack_key(x, y, z);
     if (slot_claim(slots, mask, key, x, y, z, (unsigned)v, (unsigned)counts[v]) < 0) *dup_flag = 1;
-    unsigned int* meta = reinterpret_cast<unsigned int*>(blocks + (size_t)v * kBlockFloats + kOffMeta);
-    meta[0] = (unsigned int)(key & 0xffffffffu); meta[1] = (unsigned int)(key >> 32); meta[2] = (unsigned)counts[v]; meta[3] = 0;
+    unsigned int* meta = reinterpret_cast<unsigned int*>(blocks + (size_t)v * kBlockFloats);
+    meta[kMetaKeyLo] = (unsigned int)(key & 0xffffffffu); meta[kMetaKeyHi] = (unsigned int)(key >> 32); meta[kMetaCount] = (unsigned)counts[v];
 }
 __global__ void k_upload_points(float* blocks, const float* xyz, long long n_voxels, int cap) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_voxels * cap) return;
     const long long v = e / cap;
     const int i = (int)(e % cap);
-    float* b = blocks + (size_t)v * kBlockFloats;
-    b[i] = xyz[3 * e]; b[kOffY + i] = xyz[3 * e + 1]; b[kOffZ + i] = xyz[3 * e + 2];
+    float* b = blocks + (size_t)v * kBlockFloats + 4 * i;
+    b[0] = xyz[3 * e]; b[1] = xyz[3 * e + 1]; b[2] = xyz[3 * e + 2];
 }
 __global__ void k_download(const float* blocks, long long n_voxels, int cap, short* keys, int* counts, float* xyz) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,17 +61,17 @@ __global__ void k_download(const float* blocks, long long n_voxels, int cap, sho
     const long long v = e / cap;
     const int i = (int)(e % cap);
     const float* b = blocks + (size_t)v * kBlockFloats;
-    const unsigned int* meta = reinterpret_cast<const unsigned int*>(b + kOffMeta);
-    const int cnt = (int)meta[2];
+    const unsigned int* meta = reinterpret_cast<const unsigned int*>(b);
+    const int cnt = (int)meta[kMetaCount];
     if (i == 0) {
         short x, y, z;
-        unpack_key((unsigned long long)meta[0] | ((unsigned long long)meta[1] << 32), x, y, z);
+        unpack_key((unsigned long long)meta[kMetaKeyLo] | ((unsigned long long)meta[kMetaKeyHi] << 32), x, y, z);
         keys[3 * v] = x; keys[3 * v + 1] = y; keys[3 * v + 2] = z;
         counts[v] = cnt;
     }
-    xyz[3 * e] = i < cnt ? b[i] : 0.f;
-    xyz[3 * e + 1] = i < cnt ? b[kOffY + i] : 0.f;
-    xyz[3 * e + 2] = i < cnt ? b[kOffZ + i] : 0.f;
+    xyz[3 * e] = i < cnt ? b[4 * i] : 0.f;
+    xyz[3 * e + 1] = i < cnt ? b[4 * i + 1] : 0.f;
+    xyz[3 * e + 2] = i < cnt ? b[4 * i + 2] : 0.f;
 }
 
 // ---- K3: insertion ------------------------------------------------------------------------------------------
@@ -121,8 +121,8 @@ __global__ void k_seg_claim(Slot* slots, unsigned int mask, float* blocks, const
     unpack_key(key, x, y, z);
     const unsigned int blk = (unsigned int)(block_base + new_rank[s]);
     seg_slot[s] = slot_claim(slots, mask, key, x, y, z, blk, 0u);
-    unsigned int* meta = reinterpret_cast<unsigned int*>(blocks + (size_t)blk * kBlockFloats + kOffMeta);
-    meta[0] = (unsigned int)(key & 0xffffffffu); meta[1] = (unsigned int)(key >> 32); meta[2] = 0; meta[3] = 0;
+    unsigned int* meta = reinterpret_cast<unsigned int*>(blocks + (size_t)blk * kBlockFloats);
+    meta[kMetaKeyLo] = (unsigned int)(key & 0xffffffffu); meta[kMetaKeyHi] = (unsigned int)(key >> 32); meta[kMetaCount] = 0;
 }
 
 // one warp per touched voxel: the reference's per-point rule, replayed in sweep order
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) k_seg_process(Slot* slots, float* blocks,
     int count = (int)slots[slot].count;
     float* bp = blocks + (size_t)blk * kBlockFloats;
     float ex = 0.f, ey = 0.f, ez = 0.f;
-    if (lane < count) { ex = bp[lane]; ey = bp[kOffY + lane]; ez = bp[kOffZ + lane]; }
+    if (lane < count) { ex = bp[4 * lane]; ey = bp[4 * lane + 1]; ez = bp[4 * lane + 2]; }
     const long long start = seg_start[s];
     const unsigned long long key = keys[start];
     const double sq_init = 10 * size * size;            // :413
@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(256) k_seg_process(Slot* slots, float* blocks,
             add = (sq_min > min_sq) && (min_num_points <= 0 || count >= min_num_points);   // :427-433
         }
         if (add) {
-            if (lane == count) { ex = fx; ey = fy; ez = fz; bp[count] = fx; bp[kOffY + count] = fy; bp[kOffZ + count] = fz; }
+            if (lane == count) { ex = fx; ey = fy; ez = fz; bp[4 * count] = fx; bp[4 * count + 1] = fy; bp[4 * count + 2] = fz; }
             ++count; ++added;
         }
     }
     if (lane == 0 && added) {
         slots[slot].count = (unsigned int)count;
-        reinterpret_cast<unsigned int*>(bp + kOffMeta)[2] = (unsigned int)count;
+        reinterpret_cast<unsigned int*>(bp)[kMetaCount] = (unsigned int)count;
         atomicAdd(reinterpret_cast<unsigned long long*>(n_points), (unsigned long long)added);
     }
 }

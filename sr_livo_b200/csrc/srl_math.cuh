@@ -206,20 +206,25 @@ struct PlaneRow {
     int nan_planarity;
 };
 
-// Neighbour accessor NB: NB.x(j), NB.y(j), NB.z(j) return the j-th nearest neighbour (FP32 map
-// coordinates), j ascending in distance, j < K (= vector_neighbors.size(), src/optimize.cpp:73).
-// p = keypoint in world frame, b = R_il*raw + t_il.
-template <class NB>
-SRL_HD void plane_residual(const NB& nbv, int K, const PassConst& c, double px, double py, double pz, double bx,
-                           double by, double bz, PlaneRow& out) {
+// Neighbour accessor NB: nbv.get(j, x, y, z) yields the j-th neighbour (FP32 map coordinates), j < K
+// (= vector_neighbors.size(), src/optimize.cpp:73); (n0x,n0y,n0z) is the NEAREST neighbour (vector_neighbors[0]).
+// p = keypoint in world frame, b = R_il*raw + t_il.  KS > 0 makes the neighbour loops compile-time (registers).
+template <int KS, class NB>
+SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double n0z, const PassConst& c, double px, double py,
+                           double pz, double bx, double by, double bz, PlaneRow& out) {
+    if (KS > 0) K = KS;
     // barycenter: sequential sum then divide (src/optimize.cpp:320-326)
     double mx = 0.0, my = 0.0, mz = 0.0;
-    for (int j = 0; j < K; ++j) { mx += (double)nbv.x(j); my += (double)nbv.y(j); mz += (double)nbv.z(j); }
+#pragma unroll
+    for (int j = 0; j < (KS > 0 ? KS : K); ++j) { float x, y, z; nbv.get(j, x, y, z); mx += (double)x; my += (double)y; mz += (double)z; }
     mx /= (double)K; my /= (double)K; mz /= (double)K;
     // un-normalised scatter, upper triangle (src/optimize.cpp:328-338)
     double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
-    for (int j = 0; j < K; ++j) {
-        double dx = (double)nbv.x(j) - mx, dy = (double)nbv.y(j) - my, dz = (double)nbv.z(j) - mz;
+#pragma unroll
+    for (int j = 0; j < (KS > 0 ? KS : K); ++j) {
+        float x, y, z;
+        nbv.get(j, x, y, z);
+        double dx = (double)x - mx, dy = (double)y - my, dz = (double)z - mz;
         c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
     }
     double ev[3], nx, ny, nz;
@@ -232,7 +237,6 @@ SRL_HD void plane_residual(const NB& nbv, int K, const PassConst& c, double px, 
     // normal flip: world-frame normal against body-frame location, as in the reference (:49-51)
     if (nx * (c.t_last[0] - bx) + (ny * (c.t_last[1] - by) + nz * (c.t_last[2] - bz)) < 0.0) { nx = -nx; ny = -ny; nz = -nz; }
     // weight (:87-88)
-    double n0x = (double)nbv.x(0), n0y = (double)nbv.y(0), n0z = (double)nbv.z(0);
     double ex = n0x - px, ey = n0y - py, ez = n0z - pz;
     double dist0 = sqrt(ex * ex + (ey * ey + ez * ez));
     double weight = c.lambda_w * planarity_weight + c.lambda_n * exp(-dist0 / c.exp_den);
