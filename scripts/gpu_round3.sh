@@ -1,11 +1,11 @@
 #!/bin/bash
-TAG=${1:-r03}
+TAG=${1:-r04}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== diag small"; timeout 300 python scripts/gpu_diag.py small > $OUT/diag_small.log 2>&1; echo "rc=$?"; grep -E "mismatch|parity|HTH rel|iekf|p diff|cap600|fallbacks|timing|Error|error" $OUT/diag_small.log | head -20
 echo "== memcheck small"; timeout 600 compute-sanitizer --tool memcheck python scripts/gpu_diag.py small > $OUT/memcheck.log 2>&1; grep -E "ERROR SUMMARY" $OUT/memcheck.log
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/pytest_gpu.log
-for MB in 4 5 6 8; do
+for MB in 4 5 6; do
   echo "== bench fast_minb=$MB"; SRL_FAST_MINB=$MB timeout 600 python bench.py --no-cpu-baseline --steps 10 > $OUT/bench_fmb$MB.json 2> $OUT/bench_fmb$MB.err; echo "rc=$?"
   python - <<PY
 import json

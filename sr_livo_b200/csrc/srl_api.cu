@@ -145,6 +145,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.s_begin = a.k_begin; f.s_end = a.k_end;   // the shard is a range of SORTED positions in this form
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
+        f.force_amb_mod = ctx->force_amb_mod;
         const long long n_groups = (n + 31) / 32;
         long long grid = std::min<long long>(n_groups, (long long)ctx->sm_count * k1_fast_max_blocks_per_sm());
         grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
@@ -219,6 +220,7 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return SRL_BAD_ARG;
     const std::string n(name);
     if (n == "force_exact_selection") { ctx->force_exact = value != 0; return SRL_OK; }
+    if (n == "fast_force_ambiguous_mod") { ctx->force_amb_mod = (int)value; return SRL_OK; }
     if (n == "fast_min_blocks") {
         if (value != 4 && value != 5 && value != 6 && value != 8) return set_err(ctx, SRL_BAD_ARG, "fast_min_blocks must be 4, 5, 6 or 8");
         k1_fast_set_min_blocks((int)value);
@@ -525,6 +527,7 @@ int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const double* r
 // ---- host unit hook for the per-keypoint math (same source as the kernel's phase 2) -------------------------
 struct HostNb {
     const double* p;
+    bool use(int) const { return true; }
     void get(int j, float& x, float& y, float& z) const { x = (float)p[3 * j]; y = (float)p[3 * j + 1]; z = (float)p[3 * j + 2]; }
 };
 int srl_host_plane_fit(const double* nbr_xyz, int32_t K, double normal[3], double* a2D, double evals[3]) {

@@ -44,6 +44,7 @@ __device__ __forceinline__ float warp_min_pos(float x) {   // x >= 0 (or +inf): 
 // the K neighbours of this lane's keypoint: float indices into the block pool, gathered from L1/L2 in phase 2
 struct TileNb {
     const float* blocks; const unsigned* tile; int lane;
+    __device__ __forceinline__ bool use(int) const { return true; }
     __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
         const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + tile[j * NBS + lane]));
         x = p.x; y = p.y; z = p.z;

@@ -31,6 +31,10 @@ __constant__ signed char c_off_fast[27 * 4];   // the 27 offsets of the nb<=1 cu
 
 constexpr unsigned FULLM = 0xffffffffu;
 constexpr int KF = 20;            // neighbours kept by the fast path
+constexpr int NG = 3;             // guard entries beyond the K-th: boundary candidates are resolved exactly in the finish
+constexpr int NS = KF + NG;       // slots that can end up in the neighbourhood
+constexpr int NL = NS + 1;        // tracked keys; the last one certifies that nothing untracked can matter
+constexpr int NU = 5;             // candidates per round through the min/max grid
 typedef unsigned long long u64;
 
 __device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane) {
@@ -47,9 +51,11 @@ __device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane)
     return v[0];
 }
 
-struct RegNb {   // the 20 selected points, as float indices into the block pool held in registers
+struct RegNb {   // the selected points: float indices into the block pool held in registers + which slots are in
     const float* blocks;
-    const unsigned (&pt)[KF + 1];
+    const unsigned (&pt)[NL];
+    unsigned mask;
+    __device__ __forceinline__ bool use(int j) const { return (mask >> j) & 1u; }
     __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
         const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + pt[j]));
         x = p.x; y = p.y; z = p.z;
@@ -131,46 +137,55 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         }
         const bool full_cand = in_range && total >= c.Kmin;   // else src/optimize.cpp:78 skips the keypoint
 
-        // ---- scan: every candidate through the 21-stage min/max chain on packed keys
-        unsigned lst[KF + 1];
+        // ---- scan: candidates go through the NL-stage min/max grid on packed keys, NU at a time (the NU x NL grid has
+        //      a critical path of NU + NL dependent ops instead of NU * NL: instruction-level parallelism for a thread
+        //      that has few sibling warps to hide latency behind)
+        unsigned lst[NL];
 #pragma unroll
-        for (int j = 0; j <= KF; ++j) lst[j] = 0xffffffffu;
+        for (int j = 0; j < NL; ++j) lst[j] = 0xffffffffu;
         if (full_cand) {
-            int e = -1, i = 0, cnt = 0;
-            const float* bp = nullptr;
-            for (;;) {
-                if (i >= cnt) {   // next voxel of this thread's list that can still matter
-                    const float T = key_value(lst[KF - 1]);
-                    const float lim = T + T * kRel + 3.f * eps_abs;
-                    bool found = false;
-                    while (++e < n_e) {
-                        if (__uint_as_float(lbo[e] & ~127u) <= lim) { found = true; break; }
-                    }
-                    if (!found) break;
-                    cnt = (int)(ent[e] & 31u);
-                    bp = A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats;
-                    i = 0;
-                    scanned += (unsigned)cnt;
-                }
-                const float4 mp = __ldg(reinterpret_cast<const float4*>(bp) + i);
-                const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
-                const float d2f = dx * dx + dy * dy + dz * dz;
-                unsigned key = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)i;
+            for (int e = 0; e < n_e; ++e) {
+                const float T = key_value(lst[KF - 1]);
+                if (__uint_as_float(lbo[e] & ~127u) > T + T * kRel + 3.f * eps_abs) continue;   // voxel cannot matter any more
+                const int cnt = (int)(ent[e] & 31u);
+                const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats);
+                scanned += (unsigned)cnt;
+                for (int i0 = 0; i0 < cnt; i0 += NU) {
+                    unsigned key[NU];
 #pragma unroll
-                for (int j = 0; j <= KF; ++j) {
-                    const unsigned lo = min(lst[j], key);
-                    key = max(lst[j], key);
-                    lst[j] = lo;
+                    for (int u = 0; u < NU; ++u) {
+                        key[u] = 0xffffffffu;
+                        if (i0 + u < cnt) {
+                            const float4 mp = __ldg(bp + i0 + u);
+                            const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
+                            const float d2f = dx * dx + dy * dy + dz * dz;
+                            key[u] = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)(i0 + u);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NL; ++j) {
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) {
+                            const unsigned lo = min(lst[j], key[u]);
+                            key[u] = max(lst[j], key[u]);
+                            lst[j] = lo;
+                        }
+                    }
                 }
-                ++i;
             }
         }
 
-        // ---- verdict: exact set, or flag for the exact kernel
+        // ---- verdict: the slots whose key is within the error window of the K-th can be among the true K nearest; if the
+        //      certifier (last tracked key) is outside the window, the true K nearest are among the first m <= NS slots
         bool ambiguous = false;
+        int m = 0;
         if (full_cand) {
-            const float T = key_value(lst[KF - 1]), R = key_value(lst[KF]);
-            ambiguous = !(R > T + T * kRel + 2.5f * eps_abs);
+            const float T = key_value(lst[KF - 1]);
+            const float lim = T + T * kRel + 2.5f * eps_abs;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) m += (key_value(lst[j]) <= lim) ? 1 : 0;   // keys are sorted: the first m slots
+            ambiguous = !(key_value(lst[NS]) > lim);
+            if (A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob: exercise the hand-over
         }
         if (valid && A.flags) A.flags[k] = ambiguous ? 1 : 0;
         const bool do_fit = full_cand && !ambiguous;
@@ -180,30 +195,61 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         for (int i = 0; i < 32; ++i) v[i] = 0.0;
         int status = 0;
         if (do_fit) {
-            // ---- FP64 finish: exact distances of the 20 points, nearest neighbour by (distance^2, visit index)
+            // ---- FP64 finish: exact distances (reference operation order) of the m boundary-inclusive candidates; the
+            //      K smallest (distance^2, visit index) are the neighbourhood, the smallest is vector_neighbors[0]
             u64 best = ~0ull;
-            unsigned best_id = 0xffffffffu;
-            double n0x = 0, n0y = 0, n0z = 0;
-            u64 dkey[DEBUG ? KF : 1];
-            unsigned did[DEBUG ? KF : 1];
-#pragma unroll
-            for (int j = 0; j < KF; ++j) {
-                const unsigned e = (lst[j] >> 5) & 31u, i = lst[j] & 31u;
-                const unsigned pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
+            unsigned best_id = 0xffffffffu, best_pt = 0;
+            unsigned mask = (1u << KF) - 1u;
+            u64 dkey[DEBUG ? NS : 1];
+            unsigned did[DEBUG ? NS : 1];
+            auto exact_key = [&](unsigned packed, unsigned& pt, unsigned& id) -> u64 {
+                const unsigned e = (packed >> 5) & 31u, i = packed & 31u;
+                pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
                 const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pt));
-                const double mx = (double)mp.x, my = (double)mp.y, mz = (double)mp.z;
-                const double dx = SRL_SUB(mx, pwx), dy = SRL_SUB(my, pwy), dz = SRL_SUB(mz, pwz);              // :394-395
-                const u64 dk = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+                const double dx = SRL_SUB((double)mp.x, pwx), dy = SRL_SUB((double)mp.y, pwy), dz = SRL_SUB((double)mp.z, pwz);   // :394-395
                 const int o = (int)(lbo[e] & 127u);
                 const int vis = ((c_off_fast[4 * o] + nb) * W + (c_off_fast[4 * o + 1] + nb)) * W + (c_off_fast[4 * o + 2] + nb);
-                const unsigned id = ((unsigned)vis << 5) | i;   // reference visit order: breaks exact distance ties
-                if (dk < best || (dk == best && id < best_id)) { best = dk; best_id = id; n0x = mx; n0y = my; n0z = mz; }
-                if (DEBUG) { dkey[j] = dk; did[j] = id; }
-                lst[j] = pt;
+                id = ((unsigned)vis << 5) | i;   // reference visit order: breaks exact distance ties
+                return (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+            };
+            if (m == KF && !DEBUG) {
+                // common case: exactly K candidates inside the window -> they ARE the neighbourhood; find the nearest
+#pragma unroll
+                for (int j = 0; j < KF; ++j) {
+                    unsigned pt, id;
+                    const u64 dk = exact_key(lst[j], pt, id);
+                    if (dk < best || (dk == best && id < best_id)) { best = dk; best_id = id; best_pt = pt; }
+                    lst[j] = pt;
+                }
+            } else {
+                u64 xk[NS];
+                unsigned xi[NS];
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    xk[j] = ~0ull; xi[j] = 0xffffffffu;
+                    if (j < m) { unsigned pt; xk[j] = exact_key(lst[j], pt, xi[j]); lst[j] = pt; }
+                }
+                mask = (1u << m) - 1u;
+                for (int drop = m - KF; drop > 0; --drop) {   // more candidates than K inside the window: drop the farthest
+                    u64 wk = 0; unsigned wi = 0; int wj = -1;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        const bool in = (mask >> j) & 1u;
+                        if (in && (wj < 0 || xk[j] > wk || (xk[j] == wk && xi[j] > wi))) { wk = xk[j]; wi = xi[j]; wj = j; }
+                    }
+                    mask &= ~(1u << wj);
+                }
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const bool in = (mask >> j) & 1u;
+                    if (in && (xk[j] < best || (xk[j] == best && xi[j] < best_id))) { best = xk[j]; best_id = xi[j]; best_pt = lst[j]; }
+                    if (DEBUG) { dkey[j] = in ? xk[j] : ~0ull; did[j] = in ? xi[j] : 0xffffffffu; }
+                }
             }
+            const float4 n0 = __ldg(reinterpret_cast<const float4*>(A.blocks + best_pt));
             PlaneRow row;
-            RegNb nbv{A.blocks, lst};
-            plane_residual<KF>(nbv, KF, n0x, n0y, n0z, c, pwx, pwy, pwz, bx, by, bz, row);
+            RegNb nbv{A.blocks, lst, mask};
+            plane_residual<NS>(nbv, KF, (double)n0.x, (double)n0.y, (double)n0.z, c, pwx, pwy, pwz, bx, by, bz, row);
             status = row.accepted ? 2 : 1;
             v[29] = 1.0;
             v[31] = (double)row.nan_planarity;
@@ -231,8 +277,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                     for (int i = 0; i < 6; ++i) d[6 + i] = row.accepted ? row.J[i] : 0.0;
                     d[12] = row.offset; d[13] = row.distance; d[14] = row.weight; d[15] = row.a2D;
                 }
-                // neighbour list in the reference's order: ascending (distance^2, visit index)
-                for (int a = 1; a < KF; ++a) {
+                // neighbour list in the reference's order: ascending (distance^2, visit index); dropped slots sort last
+                for (int a = 1; a < NS; ++a) {
                     const u64 kd = dkey[a]; const unsigned ki = did[a];
                     int b = a - 1;
                     while (b >= 0 && (dkey[b] > kd || (dkey[b] == kd && did[b] > ki))) { dkey[b + 1] = dkey[b]; did[b + 1] = did[b]; --b; }

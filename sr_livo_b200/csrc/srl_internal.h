@@ -60,6 +60,7 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     double* dbg_nbr_dist;
     double* dbg_plane;
     unsigned long long* stats;  // [1] += ambiguous keypoints
+    int force_amb_mod;          // test knob: > 0 flags every keypoint whose index is a multiple of it
 };
 
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
@@ -105,6 +106,7 @@ struct srl_ctx {
     unsigned long long* d_stats = nullptr;   // 4 counters
     double* d_fast_out = nullptr;            // k1_fast's 32 sums, added by the exact-fallback launch
     bool force_exact = false;
+    int force_amb_mod = 0;                   // test knob for the k1_fast -> k1_assoc hand-over
     int variant = 0;                         // 0 auto (k1_fast + exact fallback when applicable), 2 = k1_assoc only
     // generic scratch (map insert)
     void* d_scratch = nullptr;

@@ -206,22 +206,28 @@ struct PlaneRow {
     int nan_planarity;
 };
 
-// Neighbour accessor NB: nbv.get(j, x, y, z) yields the j-th neighbour (FP32 map coordinates), j < K
-// (= vector_neighbors.size(), src/optimize.cpp:73); (n0x,n0y,n0z) is the NEAREST neighbour (vector_neighbors[0]).
+// Neighbour accessor NB: nbv.get(j, x, y, z) yields the j-th stored neighbour (FP32 map coordinates) and
+// nbv.use(j) says whether slot j is one of the K neighbours (= vector_neighbors, src/optimize.cpp:73); KS > 0 is the
+// compile-time number of SLOTS (>= K).  (n0x,n0y,n0z) is the NEAREST neighbour (vector_neighbors[0]).
 // p = keypoint in world frame, b = R_il*raw + t_il.  KS > 0 makes the neighbour loops compile-time (registers).
 template <int KS, class NB>
 SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double n0z, const PassConst& c, double px, double py,
                            double pz, double bx, double by, double bz, PlaneRow& out) {
-    if (KS > 0) K = KS;
     // barycenter: sequential sum then divide (src/optimize.cpp:320-326)
     double mx = 0.0, my = 0.0, mz = 0.0;
 #pragma unroll
-    for (int j = 0; j < (KS > 0 ? KS : K); ++j) { float x, y, z; nbv.get(j, x, y, z); mx += (double)x; my += (double)y; mz += (double)z; }
+    for (int j = 0; j < (KS > 0 ? KS : K); ++j) {
+        if (!nbv.use(j)) continue;
+        float x, y, z;
+        nbv.get(j, x, y, z);
+        mx += (double)x; my += (double)y; mz += (double)z;
+    }
     mx /= (double)K; my /= (double)K; mz /= (double)K;
     // un-normalised scatter, upper triangle (src/optimize.cpp:328-338)
     double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
 #pragma unroll
     for (int j = 0; j < (KS > 0 ? KS : K); ++j) {
+        if (!nbv.use(j)) continue;
         float x, y, z;
         nbv.get(j, x, y, z);
         double dx = (double)x - mx, dy = (double)y - my, dz = (double)z - mz;

@@ -142,31 +142,64 @@ def test_pass_matches_oracle(L, small_world, kw):
     _assert_pass_equal(g, o)
 
 
+def _close(a, b, rel=1e-12):
+    return np.abs(a - b).max() <= rel * np.abs(b).max()
+
+
 @pytest.mark.parametrize("kw", [dict(max_num_residuals=BIG), dict(max_num_residuals=BIG, frame_id=5)])
 def test_exact_selection_path_matches_oracle(L, small_world, kw):
-    """k1_assoc selects in FP32 with an error bound and redoes ambiguous keypoints exactly; forcing every keypoint
-    through the exact FP64 selection must give the same (oracle-identical) answer, and on normal data the exact
-    path must be the exception."""
+    """Three ways to the same answer: (a) auto = k1_fast (FP32 packed keys + guards + exact finish) where applicable,
+    (b) k1_assoc only (FP32 selection with error bound, exact fallback), (c) k1_assoc with the exact FP64 selection
+    forced for every keypoint.  All must equal the oracle: ids bit-exact, floats to rounding."""
     from sr_livo_b200 import lio
     om, sw = _load_world(L, small_world)
     n = 1500
     L.setKeypoints(sw.raw_xyz[:n])
     o = om.build_plane_residuals(sw.raw_xyz[:n], sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw), debug=True)
-    before = L.ctx.counter("exact_fallbacks")
-    g_fast = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
-    mid = L.ctx.counter("exact_fallbacks")
-    L.ctx.set_option("force_exact_selection", 1)
+    prm = lio.r3live_params(**kw)
+    g_auto = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+    L.ctx.set_option("k1_variant", 2)
     try:
-        g_exact = L.buildPlaneResiduals(lio.r3live_params(**kw), sw.q_init, sw.t_init, sw.t_last, debug=True)
+        before = L.ctx.counter("exact_fallbacks")
+        g_v2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        mid = L.ctx.counter("exact_fallbacks")
+        L.ctx.set_option("force_exact_selection", 1)
+        g_exact = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        after = L.ctx.counter("exact_fallbacks")
     finally:
         L.ctx.set_option("force_exact_selection", 0)
-    after = L.ctx.counter("exact_fallbacks")
-    _assert_pass_equal(g_fast, o)
-    _assert_pass_equal(g_exact, o)
-    assert np.array_equal(g_fast.nbr, g_exact.nbr) and np.array_equal(g_fast.HTH, g_exact.HTH)
+        L.ctx.set_option("k1_variant", 0)
+    for g in (g_auto, g_v2, g_exact):
+        _assert_pass_equal(g, o)
+    assert np.array_equal(g_auto.nbr, g_exact.nbr) and np.array_equal(g_v2.nbr, g_exact.nbr)
+    assert _close(g_auto.HTH, g_exact.HTH) and _close(g_v2.HTH, g_exact.HTH)
     n_cand = int((o.num_candidates >= 20).sum())
     assert after - mid == n_cand                       # forced: every keypoint with >= K candidates went the exact way
     assert mid - before <= 0.1 * n_cand                # normal: the FP32 selection decides almost all of them
+
+
+def test_fast_kernel_hands_ambiguous_keypoints_to_the_exact_kernel(L, small_world):
+    """k1_fast flags what it cannot certify; k1_assoc redoes those and adds k1_fast's sums.  With the guard entries the
+    natural rate is ~0, so the hand-over is also forced on every 7th keypoint."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz)
+    o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    a0 = L.ctx.counter("fast_ambiguous")
+    g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+    a1 = L.ctx.counter("fast_ambiguous")
+    _assert_pass_equal(g, o)
+    assert a1 - a0 <= 0.002 * sw.raw_xyz.shape[0]
+    L.ctx.set_option("fast_force_ambiguous_mod", 7)
+    try:
+        g7 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        a2 = L.ctx.counter("fast_ambiguous")
+    finally:
+        L.ctx.set_option("fast_force_ambiguous_mod", 0)
+    _assert_pass_equal(g7, o)
+    assert a2 - a1 >= int((o.num_candidates[::7] >= 20).sum())
+    assert _close(g7.HTH, g.HTH) and g7.num_residuals == g.num_residuals
 
 
 def test_pass_config1_20k_points_200k_map(L, cfg1_world):
@@ -238,7 +271,7 @@ def test_pass_is_deterministic_and_shards_sum_to_the_whole(L, small_world):
     L.setKeypoints(sw.raw_xyz)
     a = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
     b = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
-    assert np.array_equal(a.HTH, b.HTH) and np.array_equal(a.HTh, b.HTh) and a.loss_sum == b.loss_sum   # bitwise
+    assert np.array_equal(a.HTH, b.HTH) and np.array_equal(a.HTh, b.HTh) and a.loss_sum == b.loss_sum   # bitwise, run to run
     n = sw.raw_xyz.shape[0]
     for world in (2, 4, 8):
         HTH = np.zeros((6, 6)); HTh = np.zeros(6); res = 0
@@ -360,7 +393,9 @@ def test_full_size_properties_100k_sweep_large_map():
         L.setKeypoints(sw.raw_xyz)
         a = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
         b = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
-        assert np.array_equal(a.HTH, b.HTH) and a.num_residuals == b.num_residuals        # deterministic
+        b2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+        assert np.array_equal(b.HTH, b2.HTH) and np.array_equal(b.HTh, b2.HTh)             # bitwise, run to run
+        assert _close(a.HTH, b.HTH) and a.num_residuals == b.num_residuals                 # debug build of the kernel: to rounding
         assert a.num_residuals <= a.num_full_neighborhoods <= 100000 and a.num_residuals > 50000
         assert np.allclose(a.HTH, a.HTH.T) and np.linalg.eigvalsh(a.HTH).min() > 0
         acc = a.status == 2
