@@ -34,7 +34,6 @@ constexpr int KF = 20;            // neighbours kept by the fast path
 constexpr int NG = 3;             // guard entries beyond the K-th: boundary candidates are resolved exactly in the finish
 constexpr int NS = KF + NG;       // slots that can end up in the neighbourhood
 constexpr int NL = NS + 1;        // tracked keys; the last one certifies that nothing untracked can matter
-constexpr int NU = 5;             // candidates per round through the min/max grid
 typedef unsigned long long u64;
 
 __device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane) {
@@ -51,11 +50,10 @@ __device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane)
     return v[0];
 }
 
-struct RegNb {   // the selected points: float indices into the block pool held in registers + which slots are in
+struct SelNb {   // the K selected points: float indices into the block pool (thread-private array)
     const float* blocks;
-    const unsigned (&pt)[NL];
-    unsigned mask;
-    __device__ __forceinline__ bool use(int j) const { return (mask >> j) & 1u; }
+    const unsigned* pt;
+    __device__ __forceinline__ bool use(int) const { return true; }
     __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
         const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + pt[j]));
         x = p.x; y = p.y; z = p.z;
@@ -66,7 +64,8 @@ __device__ __forceinline__ float key_value(unsigned key) {   // packed key -> (t
     return key == 0xffffffffu ? __int_as_float(0x7f800000) : __uint_as_float(key & ~1023u);
 }
 
-template <bool DEBUG, int MINB>
+// NU = candidates per round through the min/max grid
+template <bool DEBUG, int MINB, int NU>
 __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -197,59 +196,49 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         if (do_fit) {
             // ---- FP64 finish: exact distances (reference operation order) of the m boundary-inclusive candidates; the
             //      K smallest (distance^2, visit index) are the neighbourhood, the smallest is vector_neighbors[0]
-            u64 best = ~0ull;
-            unsigned best_id = 0xffffffffu, best_pt = 0;
-            unsigned mask = (1u << KF) - 1u;
-            u64 dkey[DEBUG ? NS : 1];
-            unsigned did[DEBUG ? NS : 1];
-            auto exact_key = [&](unsigned packed, unsigned& pt, unsigned& id) -> u64 {
-                const unsigned e = (packed >> 5) & 31u, i = packed & 31u;
-                pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
+            // (compact code on purpose: thread-private arrays and rolled loops keep this section small in the I-cache;
+            //  it runs once per keypoint, the scan above is where the time goes)
+            unsigned cand[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) cand[j] = lst[j];
+            u64 xk[NS];
+            unsigned xi[NS], xp[NS];
+            for (int j = 0; j < m; ++j) {
+                const unsigned e = (cand[j] >> 5) & 31u, i = cand[j] & 31u;
+                const unsigned pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
                 const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pt));
                 const double dx = SRL_SUB((double)mp.x, pwx), dy = SRL_SUB((double)mp.y, pwy), dz = SRL_SUB((double)mp.z, pwz);   // :394-395
                 const int o = (int)(lbo[e] & 127u);
                 const int vis = ((c_off_fast[4 * o] + nb) * W + (c_off_fast[4 * o + 1] + nb)) * W + (c_off_fast[4 * o + 2] + nb);
-                id = ((unsigned)vis << 5) | i;   // reference visit order: breaks exact distance ties
-                return (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
-            };
-            if (m == KF && !DEBUG) {
-                // common case: exactly K candidates inside the window -> they ARE the neighbourhood; find the nearest
-#pragma unroll
-                for (int j = 0; j < KF; ++j) {
-                    unsigned pt, id;
-                    const u64 dk = exact_key(lst[j], pt, id);
-                    if (dk < best || (dk == best && id < best_id)) { best = dk; best_id = id; best_pt = pt; }
-                    lst[j] = pt;
-                }
-            } else {
-                u64 xk[NS];
-                unsigned xi[NS];
-#pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    xk[j] = ~0ull; xi[j] = 0xffffffffu;
-                    if (j < m) { unsigned pt; xk[j] = exact_key(lst[j], pt, xi[j]); lst[j] = pt; }
-                }
-                mask = (1u << m) - 1u;
-                for (int drop = m - KF; drop > 0; --drop) {   // more candidates than K inside the window: drop the farthest
-                    u64 wk = 0; unsigned wi = 0; int wj = -1;
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        const bool in = (mask >> j) & 1u;
-                        if (in && (wj < 0 || xk[j] > wk || (xk[j] == wk && xi[j] > wi))) { wk = xk[j]; wi = xi[j]; wj = j; }
-                    }
-                    mask &= ~(1u << wj);
-                }
-#pragma unroll
-                for (int j = 0; j < NS; ++j) {
+                xk[j] = (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+                xi[j] = ((unsigned)vis << 5) | i;   // reference visit order: breaks exact distance ties
+                xp[j] = pt;
+            }
+            unsigned mask = (1u << m) - 1u;
+            for (int drop = m - KF; drop > 0; --drop) {   // rare: more candidates than K inside the window: drop the farthest
+                u64 wk = 0; unsigned wi = 0; int wj = -1;
+                for (int j = 0; j < m; ++j) {
                     const bool in = (mask >> j) & 1u;
-                    if (in && (xk[j] < best || (xk[j] == best && xi[j] < best_id))) { best = xk[j]; best_id = xi[j]; best_pt = lst[j]; }
-                    if (DEBUG) { dkey[j] = in ? xk[j] : ~0ull; did[j] = in ? xi[j] : 0xffffffffu; }
+                    if (in && (wj < 0 || xk[j] > wk || (xk[j] == wk && xi[j] > wi))) { wk = xk[j]; wi = xi[j]; wj = j; }
                 }
+                mask &= ~(1u << wj);
+            }
+            u64 best = ~0ull;
+            unsigned best_id = 0xffffffffu, best_pt = 0;
+            unsigned sel[KF];
+            int ns = 0;
+            u64 dkey[DEBUG ? KF : 1];
+            unsigned did[DEBUG ? KF : 1];
+            for (int j = 0; j < m; ++j) {
+                if (!((mask >> j) & 1u)) continue;
+                if (xk[j] < best || (xk[j] == best && xi[j] < best_id)) { best = xk[j]; best_id = xi[j]; best_pt = xp[j]; }
+                if (DEBUG) { dkey[ns] = xk[j]; did[ns] = xi[j]; }
+                sel[ns++] = xp[j];
             }
             const float4 n0 = __ldg(reinterpret_cast<const float4*>(A.blocks + best_pt));
             PlaneRow row;
-            RegNb nbv{A.blocks, lst, mask};
-            plane_residual<NS>(nbv, KF, (double)n0.x, (double)n0.y, (double)n0.z, c, pwx, pwy, pwz, bx, by, bz, row);
+            SelNb nbv{A.blocks, sel};
+            plane_residual<0>(nbv, KF, (double)n0.x, (double)n0.y, (double)n0.z, c, pwx, pwy, pwz, bx, by, bz, row);
             status = row.accepted ? 2 : 1;
             v[29] = 1.0;
             v[31] = (double)row.nan_planarity;
@@ -278,7 +267,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                     d[12] = row.offset; d[13] = row.distance; d[14] = row.weight; d[15] = row.a2D;
                 }
                 // neighbour list in the reference's order: ascending (distance^2, visit index); dropped slots sort last
-                for (int a = 1; a < NS; ++a) {
+                for (int a = 1; a < KF; ++a) {
                     const u64 kd = dkey[a]; const unsigned ki = did[a];
                     int b = a - 1;
                     while (b >= 0 && (dkey[b] > kd || (dkey[b] == kd && did[b] > ki))) { dkey[b + 1] = dkey[b]; did[b + 1] = did[b]; --b; }
@@ -405,23 +394,39 @@ static void upload_fast_offsets(int device) {
 }
 
 typedef void (*FastFn)(const FastArgs);
-static int g_fast_minb = -1;
+static int g_fast_minb = -1, g_fast_nu = -1;
 void k1_fast_set_min_blocks(int v) { if (v == 4 || v == 5 || v == 6 || v == 8) g_fast_minb = v; }
-static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant (default 6)
+static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant (default 5)
     if (g_fast_minb < 0) {
         const char* e = getenv("SRL_FAST_MINB");
-        const int v = e ? atoi(e) : 6;
-        g_fast_minb = (v == 4 || v == 5 || v == 6 || v == 8) ? v : 6;
+        const int v = e ? atoi(e) : 5;
+        g_fast_minb = (v == 4 || v == 5 || v == 6 || v == 8) ? v : 5;
     }
     return g_fast_minb;
 }
+static int fast_nu() {     // SRL_FAST_NU=1|2|5: candidates per min/max round (default 2)
+    if (g_fast_nu < 0) {
+        const char* e = getenv("SRL_FAST_NU");
+        const int v = e ? atoi(e) : 2;
+        g_fast_nu = (v == 1 || v == 2 || v == 5) ? v : 2;
+    }
+    return g_fast_nu;
+}
+template <bool DBG, int NU>
+static FastFn pick_fast_mb() {
+    switch (fast_minb()) {
+        case 4: return k1_fast<DBG, 4, NU>;
+        case 6: return k1_fast<DBG, 6, NU>;
+        case 8: return k1_fast<DBG, 8, NU>;
+        default: return k1_fast<DBG, 5, NU>;
+    }
+}
 template <bool DBG>
 static FastFn pick_fast() {
-    switch (fast_minb()) {
-        case 4: return k1_fast<DBG, 4>;
-        case 5: return k1_fast<DBG, 5>;
-        case 8: return k1_fast<DBG, 8>;
-        default: return k1_fast<DBG, 6>;
+    switch (fast_nu()) {
+        case 1: return pick_fast_mb<DBG, 1>();
+        case 5: return pick_fast_mb<DBG, 5>();
+        default: return pick_fast_mb<DBG, 2>();
     }
 }
 
