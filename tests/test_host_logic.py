@@ -199,3 +199,31 @@ def test_sharded_iekf_loop_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_cpp_adapter_header_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/srlivo_b200_lio.hpp (the C++ host mirror a maintainer includes) builds against the library with the
+    reference's own language level (-std=c++14) and, on a box without a GPU, construction throws instead of falling
+    back to anything."""
+    import torch
+    src = tmp_path / "adapter.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "srlivo_b200_lio.hpp"
+int main() {
+    try {
+        srl::LioBackend lio(0, nullptr, 1 << 12, 1 << 12);
+        srl_icp_params p; srl_icp_params_r3live(&p);
+        std::printf("constructed mapSize=%lld K=%d\n", lio.mapSize(), p.max_number_neighbors);
+        return 0;
+    } catch (const std::exception& e) { std::printf("threw: %s\n", e.what()); return 3; }
+}''')
+    exe = tmp_path / "adapter"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lsrlivo_b200", f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "constructed mapSize=0 K=20" in r.stdout
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout
