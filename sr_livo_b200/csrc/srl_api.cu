@@ -146,8 +146,10 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
-        const long long n_groups = (n + 31) / 32;
-        long long grid = std::min<long long>(n_groups, (long long)ctx->sm_count * k1_fast_max_blocks_per_sm());
+        const long long kpw = 32 / k1_fast_lanes_per_keypoint();
+        const long long n_groups = (n + kpw - 1) / kpw;
+        // one group per warp when it fits (the block scheduler then balances the waves), grid-stride beyond that
+        long long grid = std::min<long long>((n_groups + kFastWarps - 1) / kFastWarps, (long long)ctx->max_grid);
         grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
         SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
         K1Args b = a;   // exact selection for the keypoints k1_fast could not decide; its last block adds k1_fast's sums
@@ -180,7 +182,7 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SRL_CUDA_ERROR; }
         ctx->own_stream = true;
     }
-    ctx->max_grid = ctx->sm_count * 8;
+    ctx->max_grid = 2048;   // rows of the block-partials buffer (>= any grid we launch)
     bool ok = cudaMalloc(&ctx->d_partials, (size_t)ctx->max_grid * 32 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
@@ -221,6 +223,11 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     const std::string n(name);
     if (n == "force_exact_selection") { ctx->force_exact = value != 0; return SRL_OK; }
     if (n == "fast_force_ambiguous_mod") { ctx->force_amb_mod = (int)value; return SRL_OK; }
+    if (n == "fast_lanes_per_keypoint") {
+        if (value != 1 && value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "fast_lanes_per_keypoint must be 1, 2 or 4");
+        k1_fast_set_lanes_per_keypoint((int)value);
+        return SRL_OK;
+    }
     if (n == "fast_min_blocks") {
         if (value != 4 && value != 5 && value != 6 && value != 8) return set_err(ctx, SRL_BAD_ARG, "fast_min_blocks must be 4, 5, 6 or 8");
         k1_fast_set_min_blocks((int)value);

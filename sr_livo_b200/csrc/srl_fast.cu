@@ -64,11 +64,17 @@ __device__ __forceinline__ float key_value(unsigned key) {   // packed key -> (t
     return key == 0xffffffffu ? __int_as_float(0x7f800000) : __uint_as_float(key & ~1023u);
 }
 
-// NU = candidates per round through the min/max grid
-template <bool DEBUG, int MINB, int NU>
+// NU = candidates per round through the min/max grid; LPK = lanes per keypoint (1, 2 or 4): the candidates of every
+// voxel are dealt round-robin to the LPK lanes, each keeps its own top-NL list, the lists are merged with a bitonic
+// network over shuffles and lane 0 of the group finishes.  More lanes per keypoint = shorter dependent chain per
+// thread and more warps in flight (a 100k-point sweep is only 21 warps per SM at LPK = 1).
+template <bool DEBUG, int MINB, int NU, int LPK>
 __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    constexpr int KPW = 32 / LPK;                 // keypoints per warp
+    const int sub = lane % LPK;                   // this lane's share of every voxel's candidates
+    const unsigned gmask = (LPK == 1) ? (1u << lane) : (((1u << LPK) - 1u) << (lane & ~(LPK - 1)));   // lanes of my keypoint
     const PassConst& c = A.c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
@@ -81,11 +87,11 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
     double acc = 0.0;
     unsigned long long scanned = 0;
     const long long n = A.s_end - A.s_begin;
-    const long long n_groups = (n + 31) / 32;
+    const long long n_groups = (n + KPW - 1) / KPW;
     const long long G = gridDim.x;
 
     for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kFastWarps) {
-        const long long s = A.s_begin + g * 32 + lane;
+        const long long s = A.s_begin + g * KPW + lane / LPK;
         const bool valid = s < A.s_end;
         const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
         double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                 ofx = (float)cx; ofy = (float)cy; ofz = (float)cz;
                 rfx = (float)(pwx - (double)ofx); rfy = (float)(pwy - (double)ofy); rfz = (float)(pwz - (double)ofz);
             }
-            if (DEBUG && A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
+            if (DEBUG && A.dbg_world && sub == 0) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
         }
 
         // ---- probes: this thread's 27 voxels; present ones go to a private list (blk<<5|cnt , lower bound|offset)
@@ -144,12 +150,16 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         for (int j = 0; j < NL; ++j) lst[j] = 0xffffffffu;
         if (full_cand) {
             for (int e = 0; e < n_e; ++e) {
-                const float T = key_value(lst[KF - 1]);
+                float T = key_value(lst[KF - 1]);
+                if (LPK > 1) {   // every lane's K-th key bounds the true K-th distance from above: share the tightest
+#pragma unroll
+                    for (int d = 1; d < LPK; d <<= 1) T = fminf(T, __shfl_xor_sync(gmask, T, d));
+                }
                 if (__uint_as_float(lbo[e] & ~127u) > T + T * kRel + 3.f * eps_abs) continue;   // voxel cannot matter any more
                 const int cnt = (int)(ent[e] & 31u);
                 const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats);
-                scanned += (unsigned)cnt;
-                for (int i0 = 0; i0 < cnt; i0 += NU) {
+                if (sub == 0) scanned += (unsigned)cnt;
+                for (int i0 = sub * NU; i0 < cnt; i0 += NU * LPK) {
                     unsigned key[NU];
 #pragma unroll
                     for (int u = 0; u < NU; ++u) {
@@ -171,14 +181,45 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                         }
                     }
                 }
+                if (LPK > 1) __syncwarp(gmask);
             }
         }
+        if (LPK > 1) {
+            // ---- merge the LPK sorted lists: min(a[j], b[31-j]) over 32 padded slots is a bitonic sequence holding the 32
+            //      smallest of both; a 5-stage bitonic merge sorts it; the first NL are the merged list
+            __syncwarp(gmask);
+#pragma unroll
+            for (int d = 1; d < LPK; d <<= 1) {
+                unsigned cmb[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned mine = (j < NL) ? lst[j] : 0xffffffffu;
+                    const int r = 31 - j;
+                    const unsigned theirs_src = (r < NL) ? lst[r] : 0xffffffffu;   // what I send for the partner's slot j
+                    const unsigned theirs = __shfl_xor_sync(gmask, theirs_src, d);
+                    cmb[j] = min(mine, theirs);
+                }
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((j & st) == 0) {
+                            const unsigned lo = min(cmb[j], cmb[j + st]), hi = max(cmb[j], cmb[j + st]);
+                            cmb[j] = lo; cmb[j + st] = hi;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NL; ++j) lst[j] = cmb[j];
+            }
+        }
+        const bool leader = (sub == 0);
 
         // ---- verdict: the slots whose key is within the error window of the K-th can be among the true K nearest; if the
         //      certifier (last tracked key) is outside the window, the true K nearest are among the first m <= NS slots
         bool ambiguous = false;
         int m = 0;
-        if (full_cand) {
+        if (full_cand && leader) {
             const float T = key_value(lst[KF - 1]);
             const float lim = T + T * kRel + 2.5f * eps_abs;
 #pragma unroll
@@ -186,8 +227,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
             ambiguous = !(key_value(lst[NS]) > lim);
             if (A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob: exercise the hand-over
         }
-        if (valid && A.flags) A.flags[k] = ambiguous ? 1 : 0;
-        const bool do_fit = full_cand && !ambiguous;
+        if (valid && leader && A.flags) A.flags[k] = ambiguous ? 1 : 0;
+        const bool do_fit = full_cand && leader && !ambiguous;
 
         double v[32];
 #pragma unroll
@@ -286,7 +327,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                 }
             }
         }
-        if (valid && A.status && !ambiguous) A.status[k] = status;
+        if (valid && leader && A.status && !ambiguous) A.status[k] = status;
         if (ambiguous && A.stats) atomicAdd(A.stats + 1, 1ull);
         __syncwarp();
         acc += transpose_reduce32f(v, lane);
@@ -318,8 +359,15 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
     __syncthreads();
     if (s_last) {
         __threadfence();
-        double s = 0.0;
-        for (int b = warp; b < (int)gridDim.x; b += kFastWarps) s += __ldcg(A.partials + (size_t)b * 32 + lane);
+        // fixed-order sum of the block partials, 8 independent accumulators per thread to pipeline the loads
+        double sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int b = warp;
+        for (; b + 7 * kFastWarps < (int)gridDim.x; b += 8 * kFastWarps) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sacc[u] += __ldcg(A.partials + (size_t)(b + u * kFastWarps) * 32 + lane);
+        }
+        for (; b < (int)gridDim.x; b += kFastWarps) sacc[0] += __ldcg(A.partials + (size_t)b * 32 + lane);
+        const double s = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
         s_acc[warp][lane] = s;
         __syncthreads();
         if (warp == 0) {
@@ -394,8 +442,9 @@ static void upload_fast_offsets(int device) {
 }
 
 typedef void (*FastFn)(const FastArgs);
-static int g_fast_minb = -1, g_fast_nu = -1;
+static int g_fast_minb = -1, g_fast_lpk = -1;
 void k1_fast_set_min_blocks(int v) { if (v == 4 || v == 5 || v == 6 || v == 8) g_fast_minb = v; }
+void k1_fast_set_lanes_per_keypoint(int v) { if (v == 1 || v == 2 || v == 4) g_fast_lpk = v; }
 static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant (default 5)
     if (g_fast_minb < 0) {
         const char* e = getenv("SRL_FAST_MINB");
@@ -404,28 +453,28 @@ static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant
     }
     return g_fast_minb;
 }
-static int fast_nu() {     // SRL_FAST_NU=1|2|5: candidates per min/max round (default 2)
-    if (g_fast_nu < 0) {
-        const char* e = getenv("SRL_FAST_NU");
+int k1_fast_lanes_per_keypoint() {     // SRL_FAST_LPK=1|2|4 (default 2)
+    if (g_fast_lpk < 0) {
+        const char* e = getenv("SRL_FAST_LPK");
         const int v = e ? atoi(e) : 2;
-        g_fast_nu = (v == 1 || v == 2 || v == 5) ? v : 2;
+        g_fast_lpk = (v == 1 || v == 2 || v == 4) ? v : 2;
     }
-    return g_fast_nu;
+    return g_fast_lpk;
 }
-template <bool DBG, int NU>
+template <bool DBG, int LPK>
 static FastFn pick_fast_mb() {
     switch (fast_minb()) {
-        case 4: return k1_fast<DBG, 4, NU>;
-        case 6: return k1_fast<DBG, 6, NU>;
-        case 8: return k1_fast<DBG, 8, NU>;
-        default: return k1_fast<DBG, 5, NU>;
+        case 4: return k1_fast<DBG, 4, 2, LPK>;
+        case 6: return k1_fast<DBG, 6, 2, LPK>;
+        case 8: return k1_fast<DBG, 8, 2, LPK>;
+        default: return k1_fast<DBG, 5, 2, LPK>;
     }
 }
 template <bool DBG>
 static FastFn pick_fast() {
-    switch (fast_nu()) {
+    switch (k1_fast_lanes_per_keypoint()) {
         case 1: return pick_fast_mb<DBG, 1>();
-        case 5: return pick_fast_mb<DBG, 5>();
+        case 4: return pick_fast_mb<DBG, 4>();
         default: return pick_fast_mb<DBG, 2>();
     }
 }

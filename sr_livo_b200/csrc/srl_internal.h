@@ -66,6 +66,8 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
 int k1_fast_max_blocks_per_sm();
 void k1_fast_set_min_blocks(int v);
+void k1_fast_set_lanes_per_keypoint(int v);
+int k1_fast_lanes_per_keypoint();
 cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
                                 size_t* needed, cudaStream_t stream);
 

@@ -202,6 +202,24 @@ def test_fast_kernel_hands_ambiguous_keypoints_to_the_exact_kernel(L, small_worl
     assert _close(g7.HTH, g.HTH) and g7.num_residuals == g.num_residuals
 
 
+@pytest.mark.parametrize("lpk", [1, 2, 4])
+def test_fast_kernel_lanes_per_keypoint_variants(L, small_world, lpk):
+    """k1_fast deals a keypoint's candidates to 1, 2 or 4 lanes and merges their top lists: same answer every way."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz[:3001])
+    o = om.build_plane_residuals(sw.raw_xyz[:3001], sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    L.ctx.set_option("fast_lanes_per_keypoint", lpk)
+    try:
+        g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        g2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+    finally:
+        L.ctx.set_option("fast_lanes_per_keypoint", 2)
+    _assert_pass_equal(g, o)
+    assert g2.num_residuals == o.num_residuals and _close(g2.HTH, o.HTH)
+
+
 def test_pass_config1_20k_points_200k_map(L, cfg1_world):
     """BASELINE config 1: 20k-pt sweep, ~200k-pt map, 1 ESIKF iteration, r3live params (cap lifted and cap 600)."""
     from sr_livo_b200 import lio
