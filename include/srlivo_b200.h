@@ -158,6 +158,11 @@ int srl_map_insert(srl_map* map, const double* xyz_world, size_t n, double min_d
 int srl_map_insert_device(srl_map* map, const double* d_xyz_world, size_t n, double min_distance_points,
                           int32_t min_num_points, int64_t* n_added);
 
+/* stateEstimation's map update without leaving the device (src/lioOptimization.cpp:1027 after src/optimize.cpp:441-445):
+ * transformPoint over the resident sweep with pose (q,t), then addPointsToMap of the registered points, sweep order */
+int srl_map_insert_sweep(srl_map* map, srl_sweep* sweep, const double q[4], const double t[3], const double R_il[9],
+                         const double t_il[3], double min_distance_points, int32_t min_num_points, int64_t* n_added);
+
 /* ---- sweep: the keypoints vector of optimize() (src/optimize.cpp:430) ------------------------ */
 int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out);
 void srl_sweep_destroy(srl_sweep* sweep);

@@ -154,7 +154,9 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
         K1Args b = a;   // exact selection for the keypoints k1_fast could not decide; its last block adds k1_fast's sums
         b.k_begin = 0; b.k_end = (long long)sw->n; b.only_flagged = sw->d_flags; b.prev_out32 = ctx->d_fast_out;
-        SRL_CUDA(ctx, launch_k1(b, pass_grid(ctx, (long long)sw->n, b.c.K, b.c.nb), debug, ctx->device, ctx->stream));
+        // almost always nothing is flagged: a one-block-per-SM grid walks the flags (32 per warp step) and leaves
+        const int fb_grid = (int)std::min<long long>(ctx->sm_count, std::max<long long>(1, ((long long)sw->n + 31) / 32));
+        SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream));
         ctx->launches += 2;
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
@@ -307,11 +309,19 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
     srl_ctx* ctx = s->ctx;
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_upload: n exceeds capacity");
     SRL_CUDA(ctx, cudaSetDevice(ctx->device));
-    // stage through pinned memory so the H2D copy runs at link speed and asynchronously
-    int rc = ensure_pinned(ctx, n * 3 * sizeof(double));
-    if (rc != SRL_OK) return rc;
-    std::memcpy(ctx->h_pinned, raw_xyz, n * 3 * sizeof(double));
-    SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, ctx->h_pinned, n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        // pinned caller memory goes straight to the DMA engine; pageable memory is staged through a pinned buffer
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, raw_xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError();
+            int rc = ensure_pinned(ctx, n * 3 * sizeof(double));
+            if (rc != SRL_OK) return rc;
+            std::memcpy(ctx->h_pinned, raw_xyz, n * 3 * sizeof(double));
+        }
+        SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, pinned ? raw_xyz : static_cast<const double*>(ctx->h_pinned), n * 3 * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    }
     s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }

@@ -453,11 +453,11 @@ static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant
     }
     return g_fast_minb;
 }
-int k1_fast_lanes_per_keypoint() {     // SRL_FAST_LPK=1|2|4 (default 2)
+int k1_fast_lanes_per_keypoint() {     // SRL_FAST_LPK=1|2|4 (default 1: measured fastest, profiles/README.md)
     if (g_fast_lpk < 0) {
         const char* e = getenv("SRL_FAST_LPK");
-        const int v = e ? atoi(e) : 2;
-        g_fast_lpk = (v == 1 || v == 2 || v == 4) ? v : 2;
+        const int v = e ? atoi(e) : 1;
+        g_fast_lpk = (v == 1 || v == 2 || v == 4) ? v : 1;
     }
     return g_fast_lpk;
 }

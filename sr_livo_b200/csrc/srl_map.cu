@@ -390,6 +390,23 @@ int srl_map_insert_device(srl_map* m, const double* d_xyz_world, size_t n, doubl
     return map_insert_impl(m, d_xyz_world, n, min_distance_points, min_num_points, n_added, static_cast<char*>(ctx->d_scratch));
 }
 
+int srl_map_insert_sweep(srl_map* m, srl_sweep* sw, const double q[4], const double t[3], const double R_il[9], const double t_il[3],
+                         double min_distance_points, int32_t min_num_points, int64_t* n_added) {
+    if (!m || !sw || !q || !t || !R_il || !t_il) return SRL_BAD_ARG;
+    if (n_added) *n_added = 0;
+    srl_ctx* ctx = m->ctx;
+    if (sw->ctx != ctx) return set_err(ctx, SRL_BAD_ARG, "map and sweep belong to different contexts");
+    const size_t n = sw->n;
+    if (n == 0) return SRL_OK;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pts_bytes = align_up(n * 3 * sizeof(double));
+    int rc;
+    if ((rc = ensure_scratch(ctx, pts_bytes + insert_scratch_bytes(n))) != SRL_OK) return rc;
+    char* base = static_cast<char*>(ctx->d_scratch);
+    if ((rc = srl_sweep_transform_device(ctx, sw, q, t, R_il, t_il, reinterpret_cast<double*>(base))) != SRL_OK) return rc;
+    return map_insert_impl(m, reinterpret_cast<const double*>(base), n, min_distance_points, min_num_points, n_added, base + pts_bytes);
+}
+
 int srl_map_insert(srl_map* m, const double* xyz_world, size_t n, double min_distance_points, int32_t min_num_points,
                    int64_t* n_added) {
     if (!m || (n && !xyz_world)) return SRL_BAD_ARG;

@@ -264,6 +264,16 @@ class LioOptimization:
     def addPointsToMap(self, points_world, min_distance_points: float = 0.15, min_num_points: int = 0) -> int:
         return self.voxel_map.insert(points_world, min_distance_points, min_num_points)
 
+    def addSweepToMap(self, frame_q, frame_t, min_distance_points: float = 0.15, min_num_points: int = 0) -> int:
+        """stateEstimation's tail (src/lioOptimization.cpp:1027): the resident sweep, re-transformed with the final pose
+        (src/optimize.cpp:441-445), goes into the map without leaving the device."""
+        q, t = f64(frame_q), f64(frame_t)
+        R, ti = f64(self.R_imu_lidar).reshape(9), f64(self.t_imu_lidar)
+        added = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_insert_sweep(self.voxel_map.h, self.sweep.h, ptr(q), ptr(t), ptr(R), ptr(ti),
+                                                      min_distance_points, min_num_points, C.byref(added)))
+        return added.value
+
     # ---- src/lioOptimization.cpp:574-581
     def mapSize(self) -> int:
         return self.voxel_map.stats()[1]
@@ -314,7 +324,10 @@ class LioOptimization:
                                passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft
 
     # ---- src/optimize.cpp:428-448 with the keypoints already selected (gridSampling is a "next" row)
-    def optimize(self, raw_xyz, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None, want_world: bool = True):
+    def optimize(self, raw_xyz, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None, want_world: bool = True,
+                 world_out=None):
+        """world_out: optional (n,3) float64 C-contiguous array to receive the re-transformed frame (pass a pinned
+        buffer to avoid staging); raw_xyz may likewise live in pinned memory."""
         raw = f64(raw_xyz).reshape(-1, 3)
         n = raw.shape[0]
         st = self.eskf_pro.to_c()
@@ -324,7 +337,7 @@ class LioOptimization:
         R = f64(self.R_imu_lidar).reshape(9)
         ti = f64(self.t_imu_lidar)
         summ = IekfSummary()
-        world = np.zeros((n, 3)) if want_world else None
+        world = (world_out if world_out is not None else np.empty((n, 3))) if want_world else None
         rc = lib().srl_optimize_host(self.ctx.h, self.voxel_map.h, self.sweep.h, ptr(raw), n, C.byref(st), ptr(fq), ptr(ft),
                                      ptr(tl), ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ),
                                      ptr(world) if want_world else None)
