@@ -347,12 +347,12 @@ def main():
             added_total += L.addSweepToMap(fq, ft)
             evs[i][2].record()
         torch.cuda.synchronize()
-        t_reg = np.array([a.elapsed_time(b) for a, b, c in evs])
-        t_ins = np.array([b.elapsed_time(c) for a, b, c in evs])
+        st_reg = np.array([a.elapsed_time(b) for a, b, c in evs])
+        st_ins = np.array([b.elapsed_time(c) for a, b, c in evs])
         streaming = {"workload": f"cfg4: {n_stream} sweeps x ({N_PASSES} passes + map insert of the {args.points} registered points)",
-                     "sweeps_per_s": 1e3 / float((t_reg + t_ins).mean()), "register_ms": float(t_reg.mean()),
-                     "insert_ms": float(t_ins.mean()), "points_added_per_sweep": added_total / n_stream,
-                     "realtime_factor_at_10hz": 100.0 / float((t_reg + t_ins).mean())}
+                     "sweeps_per_s": 1e3 / float((st_reg + st_ins).mean()), "register_ms": float(st_reg.mean()),
+                     "insert_ms": float(st_ins.mean()), "points_added_per_sweep": added_total / n_stream,
+                     "realtime_factor_at_10hz": 100.0 / float((st_reg + st_ins).mean())}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
