@@ -134,8 +134,8 @@ int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
 int srl_ctx_set_timing(srl_ctx* ctx, int enable);
 /* tuning / test knobs: "force_exact_selection" (0|1: every keypoint takes k1_assoc's exact FP64 selection),
  * "k1_variant" (0 auto: k1_fast + exact fallback where applicable; 2: k1_assoc only), "k1_min_blocks" (2|3|4) and
- * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_warm_start" (0|1: passes >= 2 of a
- * sweep bound the search with the previous pass's neighbourhoods; results are identical either way), "fast_force_ambiguous_mod" (N > 0:
+ * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_lanes_per_keypoint" (1|2|4:
+ * lanes that share one keypoint's candidate scan in k1_fast), "fast_force_ambiguous_mod" (N > 0:
  * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over).  Counters: "exact_fallbacks"
  * (keypoints whose FP32 selection in k1_assoc was ambiguous and were redone exactly), "fast_ambiguous" (keypoints
  * k1_fast handed to k1_assoc), "kernel_launches". */

@@ -119,7 +119,7 @@ static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
 
 // One pass on the ctx stream.  Fast form (k1_fast + k1_assoc on the flagged keypoints) when the configuration allows
 // it, k1_assoc alone otherwise (nb = 2, K != 20, residual cap, forced exact selection).
-static int launch_pass(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const K1Args& a, bool debug) {
+static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug) {
     const long long n = a.k_end - a.k_begin;
     const bool fast = !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
     if (ctx->timing) { timing_collect(ctx); cudaEventRecord(ctx->ev0, ctx->stream); }
@@ -139,14 +139,6 @@ static int launch_pass(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const K1Args& 
             ctx->launches += 1;
         }
         SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
-        if (ctx->warm_start) {
-            if ((rc = ensure_buf(ctx, &sw->d_prev_nbr, sw->capacity * 20)) != SRL_OK) return rc;
-            if ((rc = ensure_buf(ctx, &sw->d_prev_valid, sw->capacity)) != SRL_OK) return rc;
-            if (!sw->prev_ok || sw->map_epoch != map->epoch) {   // new sweep data or a rebuilt map: nothing to start from
-                SRL_CUDA(ctx, cudaMemsetAsync(sw->d_prev_valid, 0, sw->capacity, ctx->stream));
-                sw->prev_ok = true; sw->map_epoch = map->epoch;
-            }
-        }
         FastArgs f;
         std::memset(&f, 0, sizeof(f));
         f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
@@ -154,9 +146,8 @@ static int launch_pass(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const K1Args& 
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
-        f.prev_nbr = ctx->warm_start ? sw->d_prev_nbr : nullptr;
-        f.prev_valid = ctx->warm_start ? sw->d_prev_valid : nullptr;
-        const long long n_groups = (n + 31) / 32;
+        const long long kpw = 32 / k1_fast_lanes_per_keypoint();
+        const long long n_groups = (n + kpw - 1) / kpw;
         // one group per warp when it fits (the block scheduler then balances the waves), grid-stride beyond that
         long long grid = std::min<long long>((n_groups + kFastWarps - 1) / kFastWarps, (long long)ctx->max_grid);
         grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
@@ -234,7 +225,11 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     const std::string n(name);
     if (n == "force_exact_selection") { ctx->force_exact = value != 0; return SRL_OK; }
     if (n == "fast_force_ambiguous_mod") { ctx->force_amb_mod = (int)value; return SRL_OK; }
-    if (n == "fast_warm_start") { ctx->warm_start = value != 0; return SRL_OK; }
+    if (n == "fast_lanes_per_keypoint") {
+        if (value != 1 && value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "fast_lanes_per_keypoint must be 1, 2 or 4");
+        k1_fast_set_lanes_per_keypoint((int)value);
+        return SRL_OK;
+    }
     if (n == "fast_min_blocks") {
         if (value != 4 && value != 5 && value != 6 && value != 8) return set_err(ctx, SRL_BAD_ARG, "fast_min_blocks must be 4, 5, 6 or 8");
         k1_fast_set_min_blocks((int)value);
@@ -306,7 +301,6 @@ int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out) {
 void srl_sweep_destroy(srl_sweep* s) {
     if (!s) return;
     cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status); cudaFree(s->d_order); cudaFree(s->d_flags);
-    cudaFree(s->d_prev_nbr); cudaFree(s->d_prev_valid);
     cudaFree(s->d_dbg_world); cudaFree(s->d_dbg_nbr); cudaFree(s->d_dbg_nbr_dist); cudaFree(s->d_dbg_plane);
     delete s;
 }
@@ -328,7 +322,7 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
         SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, pinned ? raw_xyz : static_cast<const double*>(ctx->h_pinned), n * 3 * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->prev_ok = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
@@ -336,7 +330,7 @@ int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     srl_ctx* ctx = s->ctx;
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->prev_ok = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
@@ -373,7 +367,7 @@ int srl_build_plane_residuals_async(srl_ctx* ctx, srl_map* map, srl_sweep* sw, c
     a.out32 = d_out32;
     SRL_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n <= 0) { SRL_CUDA(ctx, cudaMemsetAsync(d_out32, 0, 32 * sizeof(double), ctx->stream)); return SRL_OK; }
-    return launch_pass(ctx, map, sw, a, false);
+    return launch_pass(ctx, sw, a, false);
 }
 
 int srl_normal_eq_unpack(const double* h_out32, srl_normal_eq* out) {
@@ -419,7 +413,7 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
     if (n <= 0) {
         std::memset(h, 0, 32 * sizeof(double));
     } else if (!cap_mode) {
-        if ((rc = launch_pass(ctx, map, sw, a, debug)) != SRL_OK) return rc;
+        if ((rc = launch_pass(ctx, sw, a, debug)) != SRL_OK) return rc;
         SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->timing) timing_collect(ctx);
@@ -439,7 +433,7 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
             const long long end = std::min(n, begin + chunk);
             K1Args c = a;
             c.k_begin = begin; c.k_end = end;
-            if ((rc = launch_pass(ctx, map, sw, c, debug)) != SRL_OK) return rc;
+            if ((rc = launch_pass(ctx, sw, c, debug)) != SRL_OK) return rc;
             SRL_CUDA(ctx, launch_k2(sw->d_rows, sw->d_status, begin, end, (int)cap, ctx->d_k2_state, d_cap_out, 0, ctx->stream));
             ctx->launches += 1;
             SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -64,14 +64,17 @@ __device__ __forceinline__ float key_value(unsigned key) {   // packed key -> (t
     return key == 0xffffffffu ? __int_as_float(0x7f800000) : __uint_as_float(key & ~1023u);
 }
 
-// NU = candidates fetched per round; NQ = per-thread queue of candidates that beat the current NL-th key.
-// Only queued candidates go through the NL-stage min/max grid, and the whole warp flushes its queues together, so the
-// grid (the ALU-pipe cost of this kernel) runs for the ~30 % of candidates that can still matter, not for all of them.
-template <bool DEBUG, int MINB>
+// NU = candidates per round through the min/max grid; LPK = lanes per keypoint (1, 2 or 4): the candidates of every
+// voxel are dealt round-robin to the LPK lanes, each keeps its own top-NL list, the lists are merged with a bitonic
+// network over shuffles and lane 0 of the group finishes.  More lanes per keypoint = shorter dependent chain per
+// thread and more warps in flight (a 100k-point sweep is only 21 warps per SM at LPK = 1).
+template <bool DEBUG, int MINB, int NU, int LPK>
 __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) {
-    constexpr int NU = 2, NQ = 6;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    constexpr int KPW = 32 / LPK;                 // keypoints per warp
+    const int sub = lane % LPK;                   // this lane's share of every voxel's candidates
+    const unsigned gmask = (LPK == 1) ? (1u << lane) : (((1u << LPK) - 1u) << (lane & ~(LPK - 1)));   // lanes of my keypoint
     const PassConst& c = A.c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
@@ -80,16 +83,15 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
     const float lb_margin = 1e-5f * size_f;
     const float eps_abs = 1e-4f * size_f * size_f;   // FP32 rounding of d2f; the key truncation adds T * 2^-13
     const float kRel = 1.0f / 2048.0f;
-    const float INF = __int_as_float(0x7f800000);
 
     double acc = 0.0;
     unsigned long long scanned = 0;
     const long long n = A.s_end - A.s_begin;
-    const long long n_groups = (n + 31) / 32;
+    const long long n_groups = (n + KPW - 1) / KPW;
     const long long G = gridDim.x;
 
     for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kFastWarps) {
-        const long long s = A.s_begin + g * 32 + lane;
+        const long long s = A.s_begin + g * KPW + lane / LPK;
         const bool valid = s < A.s_end;
         const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
         double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                 ofx = (float)cx; ofy = (float)cy; ofz = (float)cz;
                 rfx = (float)(pwx - (double)ofx); rfy = (float)(pwy - (double)ofy); rfz = (float)(pwz - (double)ofz);
             }
-            if (DEBUG && A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
+            if (DEBUG && A.dbg_world && sub == 0) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
         }
 
         // ---- probes: this thread's 27 voxels; present ones go to a private list (blk<<5|cnt , lower bound|offset)
@@ -140,119 +142,84 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         }
         const bool full_cand = in_range && total >= c.Kmin;   // else src/optimize.cpp:78 skips the keypoint
 
-        // ---- warm start (passes >= 2 of a sweep): the previous pass's K neighbours still exist in the map, so the largest
-        //      of their distances to the new position bounds the K-th distance from above.  F filters candidates and
-        //      voxels; it is only trusted if, afterwards, the K-th key found lies at least one error window below it.
-        float F = INF;
-        if (full_cand && A.prev_nbr && A.prev_valid && A.prev_valid[k]) {
-            float mx = 0.f;
-            const unsigned* pn = A.prev_nbr + (size_t)k * KF;
-            for (int j = 0; j < KF; ++j) {
-                const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pn[j]));
-                const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
-                mx = fmaxf(mx, dx * dx + dy * dy + dz * dz);
-            }
-            F = mx + mx * (2.f * kRel) + 4.f * eps_abs;
-        }
-
+        // ---- scan: candidates go through the NL-stage min/max grid on packed keys, NU at a time (the NU x NL grid has
+        //      a critical path of NU + NL dependent ops instead of NU * NL: instruction-level parallelism for a thread
+        //      that has few sibling warps to hide latency behind)
         unsigned lst[NL];
-        bool redo = false;
-        do {
-            // ---- scan: warp-synchronous rounds; every lane walks its own voxel list NU candidates at a time
 #pragma unroll
-            for (int j = 0; j < NL; ++j) lst[j] = 0xffffffffu;
-            unsigned q[NQ];
+        for (int j = 0; j < NL; ++j) lst[j] = 0xffffffffu;
+        if (full_cand) {
+            for (int e = 0; e < n_e; ++e) {
+                float T = key_value(lst[KF - 1]);
+                if (LPK > 1) {   // every lane's K-th key bounds the true K-th distance from above: share the tightest
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) q[j] = 0xffffffffu;
-            int qn = 0;
-            int e = -1, i = 0, cnt = 0;
-            const float4* bp = nullptr;
-            bool active = full_cand;
-            const float Fk = redo ? INF : F;
-            while (__any_sync(FULLM, active)) {
-                unsigned key[NU];
-#pragma unroll
-                for (int u = 0; u < NU; ++u) key[u] = 0xffffffffu;
-                if (active && i >= cnt) {   // next voxel of this thread's list that can still matter
-                    const float T = key_value(lst[KF - 1]);
-                    // beyond F + 3 eps every candidate of the voxel has d2f > F and would be dropped below anyway
-                    const float lim = fminf(T + T * kRel + 3.f * eps_abs, Fk + 3.f * eps_abs);
-                    bool found = false;
-                    while (++e < n_e) {
-                        if (__uint_as_float(lbo[e] & ~127u) <= lim) { found = true; break; }
-                    }
-                    if (found) {
-                        cnt = (int)(ent[e] & 31u);
-                        bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats);
-                        i = 0;
-                        scanned += (unsigned)cnt;
-                    } else {
-                        active = false;
-                    }
+                    for (int d = 1; d < LPK; d <<= 1) T = fminf(T, __shfl_xor_sync(gmask, T, d));
                 }
-                if (active) {
+                if (__uint_as_float(lbo[e] & ~127u) > T + T * kRel + 3.f * eps_abs) continue;   // voxel cannot matter any more
+                const int cnt = (int)(ent[e] & 31u);
+                const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent[e] >> 5) * kBlockFloats);
+                if (sub == 0) scanned += (unsigned)cnt;
+                for (int i0 = sub * NU; i0 < cnt; i0 += NU * LPK) {
+                    unsigned key[NU];
 #pragma unroll
                     for (int u = 0; u < NU; ++u) {
-                        if (i + u < cnt) {
-                            const float4 mp = __ldg(bp + i + u);
+                        key[u] = 0xffffffffu;
+                        if (i0 + u < cnt) {
+                            const float4 mp = __ldg(bp + i0 + u);
                             const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
                             const float d2f = dx * dx + dy * dy + dz * dz;
-                            if (d2f <= Fk) key[u] = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)(i + u);
+                            key[u] = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)(i0 + u);
                         }
                     }
-                    i += NU;
-                }
-                // queue the candidates that beat the current NL-th key (a stale, hence looser, threshold: nothing is lost)
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    if (key[u] < lst[NL - 1]) {
-#pragma unroll
-                        for (int j = NQ - 1; j > 0; --j) q[j] = q[j - 1];
-                        q[0] = key[u];
-                        ++qn;
-                    }
-                }
-                if (__any_sync(FULLM, qn > NQ - NU)) {   // somebody's queue could overflow next round: everybody flushes
 #pragma unroll
                     for (int j = 0; j < NL; ++j) {
 #pragma unroll
-                        for (int u = 0; u < NQ; ++u) {
-                            const unsigned lo = min(lst[j], q[u]);
-                            q[u] = max(lst[j], q[u]);
+                        for (int u = 0; u < NU; ++u) {
+                            const unsigned lo = min(lst[j], key[u]);
+                            key[u] = max(lst[j], key[u]);
                             lst[j] = lo;
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < NQ; ++j) q[j] = 0xffffffffu;
-                    qn = 0;
                 }
+                if (LPK > 1) __syncwarp(gmask);
             }
-            if (__any_sync(FULLM, qn > 0)) {
+        }
+        if (LPK > 1) {
+            // ---- merge the LPK sorted lists: min(a[j], b[31-j]) over 32 padded slots is a bitonic sequence holding the 32
+            //      smallest of both; a 5-stage bitonic merge sorts it; the first NL are the merged list
+            __syncwarp(gmask);
 #pragma unroll
-                for (int j = 0; j < NL; ++j) {
+            for (int d = 1; d < LPK; d <<= 1) {
+                unsigned cmb[32];
 #pragma unroll
-                    for (int u = 0; u < NQ; ++u) {
-                        const unsigned lo = min(lst[j], q[u]);
-                        q[u] = max(lst[j], q[u]);
-                        lst[j] = lo;
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned mine = (j < NL) ? lst[j] : 0xffffffffu;
+                    const int r = 31 - j;
+                    const unsigned theirs_src = (r < NL) ? lst[r] : 0xffffffffu;   // what I send for the partner's slot j
+                    const unsigned theirs = __shfl_xor_sync(gmask, theirs_src, d);
+                    cmb[j] = min(mine, theirs);
+                }
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((j & st) == 0) {
+                            const unsigned lo = min(cmb[j], cmb[j + st]), hi = max(cmb[j], cmb[j + st]);
+                            cmb[j] = lo; cmb[j + st] = hi;
+                        }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < NL; ++j) lst[j] = cmb[j];
             }
-            // the warm-start bound is valid only if the K-th key found sits a full window below it
-            bool bad = false;
-            if (full_cand && !redo && F < INF) {
-                const float T = key_value(lst[KF - 1]);
-                // dropped candidates have d2f > F, i.e. a key above F (1 - 2^-13): they are outside the verdict's window iff
-                bad = !(T + T * kRel + 2.5f * eps_abs <= F - F * (1.0f / 4096.0f) - eps_abs);
-            }
-            redo = !redo && __any_sync(FULLM, bad);   // rare (the keypoint changed voxel): the whole warp rescans cold
-        } while (redo);
+        }
+        const bool leader = (sub == 0);
 
         // ---- verdict: the slots whose key is within the error window of the K-th can be among the true K nearest; if the
         //      certifier (last tracked key) is outside the window, the true K nearest are among the first m <= NS slots
         bool ambiguous = false;
         int m = 0;
-        if (full_cand) {
+        if (full_cand && leader) {
             const float T = key_value(lst[KF - 1]);
             const float lim = T + T * kRel + 2.5f * eps_abs;
 #pragma unroll
@@ -260,8 +227,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
             ambiguous = !(key_value(lst[NS]) > lim);
             if (A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob: exercise the hand-over
         }
-        if (valid && A.flags) A.flags[k] = ambiguous ? 1 : 0;
-        const bool do_fit = full_cand && !ambiguous;
+        if (valid && leader && A.flags) A.flags[k] = ambiguous ? 1 : 0;
+        const bool do_fit = full_cand && leader && !ambiguous;
 
         double v[32];
 #pragma unroll
@@ -308,10 +275,6 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                 if (xk[j] < best || (xk[j] == best && xi[j] < best_id)) { best = xk[j]; best_id = xi[j]; best_pt = xp[j]; }
                 if (DEBUG) { dkey[ns] = xk[j]; did[ns] = xi[j]; }
                 sel[ns++] = xp[j];
-            }
-            if (A.prev_nbr) {   // remembered for the warm start of the next pass over this sweep
-                unsigned* pn = A.prev_nbr + (size_t)k * KF;
-                for (int j = 0; j < KF; ++j) pn[j] = sel[j];
             }
             const float4 n0 = __ldg(reinterpret_cast<const float4*>(A.blocks + best_pt));
             PlaneRow row;
@@ -364,8 +327,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
                 }
             }
         }
-        if (valid && A.status && !ambiguous) A.status[k] = status;
-        if (valid && A.prev_valid) A.prev_valid[k] = do_fit ? 1 : 0;
+        if (valid && leader && A.status && !ambiguous) A.status[k] = status;
         if (ambiguous && A.stats) atomicAdd(A.stats + 1, 1ull);
         __syncwarp();
         acc += transpose_reduce32f(v, lane);
@@ -480,8 +442,9 @@ static void upload_fast_offsets(int device) {
 }
 
 typedef void (*FastFn)(const FastArgs);
-static int g_fast_minb = -1;
+static int g_fast_minb = -1, g_fast_lpk = -1;
 void k1_fast_set_min_blocks(int v) { if (v == 4 || v == 5 || v == 6 || v == 8) g_fast_minb = v; }
+void k1_fast_set_lanes_per_keypoint(int v) { if (v == 1 || v == 2 || v == 4) g_fast_lpk = v; }
 static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant (default 5)
     if (g_fast_minb < 0) {
         const char* e = getenv("SRL_FAST_MINB");
@@ -490,13 +453,29 @@ static int fast_minb() {   // SRL_FAST_MINB=4|5|6|8 selects the compiled variant
     }
     return g_fast_minb;
 }
+int k1_fast_lanes_per_keypoint() {     // SRL_FAST_LPK=1|2|4 (default 1: measured fastest, profiles/README.md)
+    if (g_fast_lpk < 0) {
+        const char* e = getenv("SRL_FAST_LPK");
+        const int v = e ? atoi(e) : 1;
+        g_fast_lpk = (v == 1 || v == 2 || v == 4) ? v : 1;
+    }
+    return g_fast_lpk;
+}
+template <bool DBG, int LPK>
+static FastFn pick_fast_mb() {
+    switch (fast_minb()) {
+        case 4: return k1_fast<DBG, 4, 2, LPK>;
+        case 6: return k1_fast<DBG, 6, 2, LPK>;
+        case 8: return k1_fast<DBG, 8, 2, LPK>;
+        default: return k1_fast<DBG, 5, 2, LPK>;
+    }
+}
 template <bool DBG>
 static FastFn pick_fast() {
-    switch (fast_minb()) {
-        case 4: return k1_fast<DBG, 4>;
-        case 6: return k1_fast<DBG, 6>;
-        case 8: return k1_fast<DBG, 8>;
-        default: return k1_fast<DBG, 5>;
+    switch (k1_fast_lanes_per_keypoint()) {
+        case 1: return pick_fast_mb<DBG, 1>();
+        case 4: return pick_fast_mb<DBG, 4>();
+        default: return pick_fast_mb<DBG, 2>();
     }
 }
 

@@ -61,14 +61,13 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     double* dbg_plane;
     unsigned long long* stats;  // [1] += ambiguous keypoints
     int force_amb_mod;          // test knob: > 0 flags every keypoint whose index is a multiple of it
-    unsigned* prev_nbr;         // optional n*20: the previous pass's neighbours (block-pool float indices), read then rewritten
-    unsigned char* prev_valid;  // optional n: 1 if prev_nbr[k] holds a neighbourhood of the CURRENT map and sweep
 };
 
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
 int k1_fast_max_blocks_per_sm();
 void k1_fast_set_min_blocks(int v);
-
+void k1_fast_set_lanes_per_keypoint(int v);
+int k1_fast_lanes_per_keypoint();
 cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
                                 size_t* needed, cudaStream_t stream);
 
@@ -110,7 +109,6 @@ struct srl_ctx {
     double* d_fast_out = nullptr;            // k1_fast's 32 sums, added by the exact-fallback launch
     bool force_exact = false;
     int force_amb_mod = 0;                   // test knob for the k1_fast -> k1_assoc hand-over
-    bool warm_start = true;                  // passes >= 2 of a sweep start from the previous pass's neighbourhoods
     int variant = 0;                         // 0 auto (k1_fast + exact fallback when applicable), 2 = k1_assoc only
     // generic scratch (map insert)
     void* d_scratch = nullptr;
@@ -129,7 +127,6 @@ struct srl_map {
     float* d_blocks = nullptr;
     int64_t n_voxels = 0;           // host mirror of the block count
     long long* d_counters = nullptr;   // [0] n_points, [1] scratch
-    unsigned long long epoch = 1;      // bumped whenever blocks may have been cleared or re-assigned (clear / upload)
 };
 
 struct srl_sweep {
@@ -141,10 +138,6 @@ struct srl_sweep {
     unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
     bool order_valid = false;
     unsigned char* d_flags = nullptr;   // capacity
-    unsigned* d_prev_nbr = nullptr;     // capacity*20, warm start of passes >= 2 (k1_fast)
-    unsigned char* d_prev_valid = nullptr;   // capacity
-    unsigned long long map_epoch = 0;   // map generation the remembered neighbours belong to
-    bool prev_ok = false;               // false: prev_valid must be zeroed before use (new sweep data)
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
     int* d_status = nullptr;        // capacity, lazily allocated
     // debug buffers, lazily allocated

@@ -220,7 +220,6 @@ int srl_map_clear(srl_map* m) {
     SRL_CUDA(ctx, cudaMemsetAsync(m->d_counters, 0, 4 * sizeof(long long), ctx->stream));
     SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     m->n_voxels = 0;
-    m->epoch++;   // remembered neighbourhoods of any sweep no longer refer to this map
     return SRL_OK;
 }
 

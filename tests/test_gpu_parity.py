@@ -202,36 +202,22 @@ def test_fast_kernel_hands_ambiguous_keypoints_to_the_exact_kernel(L, small_worl
     assert _close(g7.HTH, g.HTH) and g7.num_residuals == g.num_residuals
 
 
-def test_warm_start_gives_identical_passes(L, small_world):
-    """Passes >= 2 over the same sweep bound the search with the previous pass's neighbourhoods (k1_fast warm start).
-    The bound is verified per keypoint, so every pass must equal the oracle and equal the cold result bit for bit —
-    including after the pose jumps by a whole voxel (bound invalid -> cold rescan) and after the map is rebuilt."""
+@pytest.mark.parametrize("lpk", [1, 2, 4])
+def test_fast_kernel_lanes_per_keypoint_variants(L, small_world, lpk):
+    """k1_fast deals a keypoint's candidates to 1, 2 or 4 lanes and merges their top lists: same answer every way."""
     from sr_livo_b200 import lio
     om, sw = _load_world(L, small_world)
-    prm, oprm = lio.r3live_params(max_num_residuals=BIG), O.r3live_params(max_num_residuals=BIG)
-    L.setKeypoints(sw.raw_xyz)
-    poses = [(sw.q_init, sw.t_init), (sw.q_true, sw.t_true), (sw.q_true, sw.t_true + np.array([0.003, -0.002, 0.001])),
-             (sw.q_init, sw.t_true + np.array([1.3, 0.4, 0.0])), (sw.q_true, sw.t_true)]
-    warm = []
-    for q, t in poses:
-        g = L.buildPlaneResiduals(prm, q, t, sw.t_last, debug=True)
-        o = om.build_plane_residuals(sw.raw_xyz, q, t, sw.t_last, oprm, debug=True)
-        _assert_pass_equal(g, o)
-        warm.append(L.buildPlaneResiduals(prm, q, t, sw.t_last))
-    L.ctx.set_option("fast_warm_start", 0)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz[:3001])
+    o = om.build_plane_residuals(sw.raw_xyz[:3001], sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    L.ctx.set_option("fast_lanes_per_keypoint", lpk)
     try:
-        for (q, t), w in zip(poses, warm):
-            cold = L.buildPlaneResiduals(prm, q, t, sw.t_last)
-            assert np.array_equal(cold.HTH, w.HTH) and cold.num_residuals == w.num_residuals
+        g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        g2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
     finally:
-        L.ctx.set_option("fast_warm_start", 1)
-    # a rebuilt map invalidates what the sweep remembers
-    keys, counts, xyz = om.snapshot()
-    L.voxel_map.upload(keys[::2], counts[::2], xyz[::2])
-    om2 = O.OracleMap(); om2.load(keys[::2], counts[::2], xyz[::2])
-    g = L.buildPlaneResiduals(prm, sw.q_true, sw.t_true, sw.t_last, debug=True)
-    o = om2.build_plane_residuals(sw.raw_xyz, sw.q_true, sw.t_true, sw.t_last, oprm, debug=True)
+        L.ctx.set_option("fast_lanes_per_keypoint", 1)
     _assert_pass_equal(g, o)
+    assert g2.num_residuals == o.num_residuals and _close(g2.HTH, o.HTH)
 
 
 def test_pass_config1_20k_points_200k_map(L, cfg1_world):
