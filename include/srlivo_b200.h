@@ -193,6 +193,20 @@ typedef struct srl_iekf_iter {
 int srl_iekf_begin(const srl_eskf_state* eskf, const srl_icp_params* prm, srl_iekf_iter* it);
 int srl_iekf_step(srl_iekf_iter* it, const srl_normal_eq* ne, const srl_icp_params* prm, srl_eskf_state* eskf,
                   double frame_q[4], double frame_t[3], double d_x_out[17], int32_t* done, int32_t* diverged);
+/* ---- multi-GPU: one process and ctx per GPU, map replicated, keypoints sharded (srl_sweep_set_shard).  The exchange of
+ * the 32 sums is fused into the pass's last kernel: its final block writes them into every peer's mailbox over NVLink
+ * peer memory (CUDA IPC mapping) and adds the peers' sums in rank order, so every rank ends a pass with the same
+ * totals and runs the same host update.  Setup: create, export the 64-byte handle, exchange handles with any host
+ * transport (rank order), connect.  All ranks must run the same sequence of passes. */
+typedef struct srl_comm srl_comm;
+int srl_comm_create(srl_ctx* ctx, int rank, int world, srl_comm** out);
+void srl_comm_destroy(srl_comm* comm);
+int srl_comm_export(srl_comm* comm, void* handle64);
+int srl_comm_connect(srl_comm* comm, const void* handles /* world x 64 bytes, rank order */);
+int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],
+                         double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
+                         const srl_icp_params* prm, srl_iekf_summary* summary);
+
 /* full loop on one GPU (sweep already resident) */
 int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],
                     double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],

@@ -69,7 +69,8 @@ EXPORTS = [
     "srl_map_clear", "srl_map_stats", "srl_map_upload", "srl_map_download", "srl_map_insert",
     "srl_map_insert_device", "srl_map_insert_sweep", "srl_sweep_create", "srl_sweep_destroy", "srl_sweep_upload", "srl_sweep_set_device",
     "srl_sweep_set_shard", "srl_build_plane_residuals", "srl_build_plane_residuals_async", "srl_normal_eq_unpack",
-    "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_optimize_host", "srl_sweep_transform_device",
+    "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_comm_create", "srl_comm_destroy", "srl_comm_export", "srl_comm_connect",
+    "srl_update_iekf_dist", "srl_optimize_host", "srl_sweep_transform_device",
     "srl_eskf_observe", "srl_host_plane_fit",
 ]
 
@@ -125,6 +126,13 @@ def lib():
                                 vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.srl_update_iekf.argtypes = [vp, vp, vp, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
                                   C.POINTER(IekfSummary)]
+    L.srl_comm_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.srl_comm_destroy.argtypes = [vp]
+    L.srl_comm_destroy.restype = None
+    L.srl_comm_export.argtypes = [vp, vp]
+    L.srl_comm_connect.argtypes = [vp, vp]
+    L.srl_update_iekf_dist.argtypes = [vp, vp, vp, vp, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
+                                       C.POINTER(IekfSummary)]
     L.srl_optimize_host.argtypes = [vp, vp, vp, vp, sz, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
                                     C.POINTER(IekfSummary), vp]
     L.srl_sweep_transform_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]

@@ -508,6 +508,111 @@ int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sw, srl_eskf_state* e
     return SRL_OK;
 }
 
+// ---- multi-GPU -------------------------------------------------------------------------------------------------
+int srl_comm_create(srl_ctx* ctx, int rank, int world, srl_comm** out) {
+    if (!ctx || !out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return SRL_BAD_ARG;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    srl_comm* c = new srl_comm();
+    c->ctx = ctx; c->rank = rank; c->world = world;
+    cudaError_t e = cudaMalloc(&c->d_mail, sizeof(Mailbox));
+    if (e != cudaSuccess) { delete c; return cuda_fail(ctx, e, "srl_comm_create/cudaMalloc"); }
+    e = cudaMemset(c->d_mail, 0, sizeof(Mailbox));
+    if (e != cudaSuccess) { cudaFree(c->d_mail); delete c; return cuda_fail(ctx, e, "srl_comm_create/cudaMemset"); }
+    c->peer[rank] = c->d_mail;
+    c->connected = (world == 1);
+    *out = c;
+    return SRL_OK;
+}
+void srl_comm_destroy(srl_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    for (int r = 0; r < c->world; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    cudaFree(c->d_mail);
+    delete c;
+}
+int srl_comm_export(srl_comm* c, void* handle64) {
+    if (!c || !handle64) return SRL_BAD_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    SRL_CUDA(c->ctx, cudaIpcGetMemHandle(&h, c->d_mail));
+    std::memcpy(handle64, &h, 64);
+    return SRL_OK;
+}
+int srl_comm_connect(srl_comm* c, const void* handles) {
+    if (!c || !handles) return SRL_BAD_ARG;
+    srl_ctx* ctx = c->ctx;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || c->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cuda_fail(ctx, e, "cudaIpcOpenMemHandle (peer mailbox)"); return SRL_COMM_ERROR; }
+        c->peer[r] = static_cast<Mailbox*>(p);
+        c->opened[r] = true;
+    }
+    c->connected = true;
+    return SRL_OK;
+}
+
+int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sw, srl_eskf_state* eskf, double frame_q[4],
+                         double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
+                         const srl_icp_params* prm, srl_iekf_summary* summary) {
+    if (!ctx || !comm || !eskf || !frame_q || !frame_t || !t_last || !R_il || !t_il || !prm) return SRL_BAD_ARG;
+    if (comm->ctx != ctx || !comm->connected) return set_err(ctx, SRL_COMM_ERROR, "srl_comm is not connected");
+    srl_iekf_iter it;
+    int rc = srl_iekf_begin(eskf, prm, &it);
+    if (rc != SRL_OK) return rc;
+    if (summary) { std::memset(summary, 0, sizeof(*summary)); summary->success = 1; }
+    srl_frame fr;
+    std::memcpy(fr.t_last, t_last, sizeof(fr.t_last));
+    std::memcpy(fr.R_il, R_il, sizeof(fr.R_il));
+    std::memcpy(fr.t_il, t_il, sizeof(fr.t_il));
+    int passes = 0;
+    for (;;) {
+        std::memcpy(fr.q_cur, frame_q, sizeof(fr.q_cur));
+        std::memcpy(fr.t_cur, frame_t, sizeof(fr.t_cur));
+        K1Args a;
+        rc = fill_k1_args(ctx, map, sw, &fr, prm, a);
+        if (rc != SRL_OK) return rc;
+        const long long n = a.k_end - a.k_begin;
+        if ((long long)prm->max_num_residuals < (long long)sw->n)
+            return set_err(ctx, SRL_BAD_ARG, "the sharded update does not implement the max_num_residuals cap");
+        a.comm.world = comm->world; a.comm.rank = comm->rank; a.comm.seq = ++comm->seq;
+        for (int r = 0; r < comm->world; ++r) a.comm.mail[r] = comm->peer[r];
+        (void)n;
+        if ((rc = launch_pass(ctx, sw, a, false)) != SRL_OK) return rc;     // also valid for an empty shard
+        double* h = ctx->h_out32;
+        SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->timing) timing_collect(ctx);
+        if (h[0] != h[0]) return set_err(ctx, SRL_COMM_ERROR, "peer exchange timed out (a rank did not reach this pass)");
+        srl_normal_eq ne;
+        unpack32(h, &ne, (long long)sw->n);
+        ++passes;
+        if (summary) { summary->passes_run = passes; summary->num_residuals_used = (int32_t)ne.num_residuals; }
+        if (ne.nan_planarity) return set_err(ctx, SRL_NAN_PLANARITY, "NaN planarity (the reference throws at src/optimize.cpp:348)");
+        if (ne.num_residuals < prm->min_number_neighbors) {
+            if (summary) summary->success = 0;
+            return set_err(ctx, SRL_TOO_FEW_RESIDUALS, "[Optimization] Error : not enough keypoints selected in ct-icp !");
+        }
+        double d_x[17];
+        int32_t done = 0, diverged = 0;
+        rc = srl_iekf_step(&it, &ne, prm, eskf, frame_q, frame_t, d_x, &done, &diverged);
+        if (rc != SRL_OK) return set_err(ctx, rc, "srl_iekf_step failed (singular 17x17)");
+        if (summary && passes <= 32) {
+            double* tr = summary->trace[passes - 1];
+            std::memcpy(tr, d_x, 17 * sizeof(double));
+            std::memcpy(tr + 17, frame_t, 3 * sizeof(double));
+            std::memcpy(tr + 20, frame_q, 4 * sizeof(double));
+        }
+        if (done) { if (summary) summary->converged = (done == 2); break; }
+    }
+    return SRL_OK;
+}
+
 int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sw, const double q[4], const double t[3], const double R_il[9],
                                const double t_il[3], double* d_world_xyz) {
     if (!ctx || !sw || !q || !t || !R_il || !t_il || !d_world_xyz) return SRL_BAD_ARG;

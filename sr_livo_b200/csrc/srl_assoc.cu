@@ -507,6 +507,34 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
 #pragma unroll
             for (int w = 0; w < kK1Warps; ++w) tot += s_acc[w][lane];
             if (A.prev_out32) tot += A.prev_out32[lane];   // fallback launch: add k1_fast's sums (fixed order)
+            if (A.comm.world > 1) {
+                // ---- fused exchange over NVLink peer memory: publish this rank's 32 sums into every rank's mailbox, wait
+                //      for the others' sums of the same pass, add all of them in rank order (bitwise identical everywhere)
+                const CommDev& cm = A.comm;
+                const int par = (int)(cm.seq & 1ull);
+                for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
+                __threadfence_system();
+                __syncwarp();
+                if (lane < cm.world) {
+                    volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
+                    *f = cm.seq;
+                }
+                __threadfence_system();
+                bool ok = true;
+                if (lane < cm.world) {
+                    volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
+                    long long spins = 0;
+                    while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+                }
+                ok = __all_sync(FULL, ok);
+                __threadfence_system();
+                double sum = 0.0;
+                for (int r = 0; r < cm.world; ++r) {
+                    const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
+                    sum += *d;
+                }
+                tot = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);   // NaN marks a failed exchange
+            }
             A.out32[lane] = tot;
             if (lane == 0) *A.ticket = 0u;
         }

@@ -17,6 +17,19 @@ namespace srl {
 constexpr int kK1Warps = 8;
 constexpr int kK1Threads = kK1Warps * 32;
 
+constexpr int kMaxRanks = 8;
+// One mailbox per rank (device memory, exported over CUDA IPC): peers write their 32 sums of a pass into
+// data[parity][their rank] and then set flag[parity][their rank] = pass sequence number.
+struct Mailbox {
+    double data[2][kMaxRanks][32];
+    unsigned long long flag[2][kMaxRanks];
+};
+struct CommDev {              // by-value kernel argument; world <= 1 disables the exchange
+    int world, rank;
+    unsigned long long seq;   // sequence number of this pass (>= 1, same on every rank)
+    Mailbox* mail[kMaxRanks]; // mail[r] = rank r's mailbox as mapped in THIS process (mail[rank] is local memory)
+};
+
 struct K1Args {
     PassConst c;
     const Slot* slots;
@@ -37,6 +50,7 @@ struct K1Args {
     const double* prev_out32;            // optional: 32 doubles added to the final sums
     unsigned long long* stats;   // optional device counters: [0] keypoints that took the exact-selection fallback
     float eps_scale;             // 1 normally; +inf forces the exact selection for every keypoint (tests)
+    CommDev comm;                // multi-GPU: the last block exchanges the 32 sums with the peers over NVLink
 };
 
 constexpr int kFastWarps = 4;
@@ -127,6 +141,16 @@ struct srl_map {
     float* d_blocks = nullptr;
     int64_t n_voxels = 0;           // host mirror of the block count
     long long* d_counters = nullptr;   // [0] n_points, [1] scratch
+};
+
+struct srl_comm {
+    srl_ctx* ctx = nullptr;
+    int rank = 0, world = 1;
+    unsigned long long seq = 0;
+    srl::Mailbox* d_mail = nullptr;                 // this rank's mailbox
+    srl::Mailbox* peer[srl::kMaxRanks] = {nullptr}; // mapped peers (peer[rank] == d_mail)
+    bool opened[srl::kMaxRanks] = {false};
+    bool connected = false;
 };
 
 struct srl_sweep {

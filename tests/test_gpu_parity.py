@@ -471,3 +471,55 @@ def test_full_size_properties_100k_sweep_large_map():
         assert after.loss_sum < 0.2 * a.loss_sum                            # registration reduced the residual
     finally:
         L.close()
+
+
+_DIST_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as tdist
+from oracle import oracle_py as O
+from sr_livo_b200 import dist, lio, synth
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+tdist.init_process_group("gloo", rank=rank, world_size=world)
+dev = rank % torch.cuda.device_count()
+pts = synth.sample_map_points(80.0, 60.0, seed=1)
+sw = synth.make_sweep(4000, seed=1000, yaw=0.5)
+L = lio.LioOptimization(device=dev, max_voxels=1 << 16, sweep_capacity=8192)
+L.addPointsToMap(pts)                                   # every rank builds its replica
+D = dist.DistributedLio(L, rank, world, native=True)
+prm = lio.r3live_params(max_num_residuals=2**31-1)
+for rep in range(3):                                    # several updates in a row: sequence numbers / double buffering
+    D.set_keypoints(sw.raw_xyz)
+    L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+    out = D.updateIEKF(prm, sw.t_last)
+om = O.OracleMap(); om.add_points(pts)
+ref = om.update_iekf(sw.raw_xyz, O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance()), sw.t_last,
+                     O.r3live_params(max_num_residuals=2**31-1))
+assert out["success"] and out["passes"] == ref["passes"], (out["passes"], ref["passes"])
+assert np.allclose(out["trace"], ref["trace"], rtol=1e-5, atol=1e-9)
+assert np.allclose(L.eskf_pro.p, ref["eskf"].p, atol=1e-9) and np.allclose(L.eskf_pro.q, ref["eskf"].q, atol=1e-9)
+t = torch.from_numpy(np.concatenate([L.eskf_pro.p, L.eskf_pro.q, L.eskf_pro.cov.reshape(-1)]))
+lst = [torch.zeros_like(t) for _ in range(world)]
+tdist.all_gather(lst, t)
+assert all(torch.equal(lst[0], x) for x in lst)         # every rank ends bit-identical
+D.close(); L.close(); tdist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_fused_peer_memory_exchange_two_ranks(tmp_path):
+    """The sharded update with the exchange fused into the pass's last kernel (CUDA IPC mailboxes): two processes
+    (on two GPUs if the box has them, else sharing one GPU), each owning half of the keypoints."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "dist_worker.py"
+    script.write_text(_DIST_WORKER)
+    port = 29700 + (os.getpid() % 1000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), root], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
