@@ -138,10 +138,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
             sw->order_valid = true;
             ctx->launches += 1;
         }
-        if (!sw->flags_clean) {   // k1_fast rewrites the flags of its own shard every pass; the rest must read 0
-            SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->capacity, ctx->stream));
-            sw->flags_clean = true;
-        }
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
         FastArgs f;
         std::memset(&f, 0, sizeof(f));
         f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
@@ -325,7 +322,7 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
         SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, pinned ? raw_xyz : static_cast<const double*>(ctx->h_pinned), n * 3 * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
@@ -333,12 +330,12 @@ int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     srl_ctx* ctx = s->ctx;
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
     return SRL_OK;
 }
 int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
     if (!s || begin > end || end > s->n) return SRL_BAD_ARG;
-    s->shard_begin = begin; s->shard_end = end; s->flags_clean = false;
+    s->shard_begin = begin; s->shard_end = end;
     return SRL_OK;
 }
 

@@ -59,17 +59,6 @@ __device__ __forceinline__ bool map_find(const Slot* __restrict__ slots, unsigne
         idx = (idx + 1) & mask;
     }
 }
-// continue a probe whose first slot (already loaded by the caller) held another key
-__device__ __forceinline__ bool map_find_from(const Slot* __restrict__ slots, unsigned int mask, unsigned long long key,
-                                              unsigned int idx, unsigned int& block, unsigned int& count) {
-    for (;;) {
-        idx = (idx + 1) & mask;
-        const uint4 s = __ldg(reinterpret_cast<const uint4*>(slots + idx));
-        const unsigned long long k = (unsigned long long)s.x | ((unsigned long long)s.y << 32);
-        if (k == key) { block = s.z; count = s.w; return true; }
-        if (k == 0ull) return false;
-    }
-}
 #endif
 
 }  // namespace srl

@@ -121,44 +121,22 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
         unsigned ent[27], lbo[27];
         int n_e = 0, total = 0;
         if (in_range) {
-            // the first slot of 9 voxels at a time: 9 independent 16-byte loads in flight instead of a chain of 27
-            constexpr int PB = 9;
-            for (int base = 0; base < V; base += PB) {
-                uint4 sl[PB];
-                unsigned sidx[PB];
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const int o = base + u;
-                    if (o < V) {
-                        const int vx = kx + c_off_fast[4 * o], vy = ky + c_off_fast[4 * o + 1], vz = kz + c_off_fast[4 * o + 2];
-                        sidx[u] = hash_key(vx, vy, vz) & A.mask;
-                        sl[u] = __ldg(reinterpret_cast<const uint4*>(A.slots + sidx[u]));
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const int o = base + u;
-                    if (o < V) {
-                        const int vx = kx + c_off_fast[4 * o], vy = ky + c_off_fast[4 * o + 1], vz = kz + c_off_fast[4 * o + 2];
-                        const unsigned long long key = pack_key(vx, vy, vz);
-                        const unsigned long long k0 = (unsigned long long)sl[u].x | ((unsigned long long)sl[u].y << 32);
-                        unsigned b = sl[u].z, cn = sl[u].w;
-                        bool found = (k0 == key);
-                        if (!found && k0 != 0ull) found = map_find_from(A.slots, A.mask, key, sidx[u], b, cn);   // collision chain
-                        if (found && (int)cn >= c.thr_occ) {                                              // :386-390
-                            const float lox = (float)((vx > 0 ? vx : vx - 1) - kx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - kx) * size_f;
-                            const float loy = (float)((vy > 0 ? vy : vy - 1) - ky) * size_f, hiy = (float)((vy < 0 ? vy : vy + 1) - ky) * size_f;
-                            const float loz = (float)((vz > 0 ? vz : vz - 1) - kz) * size_f, hiz = (float)((vz < 0 ? vz : vz + 1) - kz) * size_f;
-                            const float gx = fmaxf(fmaxf(lox - relx, relx - hix) - lb_margin, 0.f);
-                            const float gy = fmaxf(fmaxf(loy - rely, rely - hiy) - lb_margin, 0.f);
-                            const float gz = fmaxf(fmaxf(loz - relz, relz - hiz) - lb_margin, 0.f);
-                            const float lb = (gx * gx + gy * gy + gz * gz) * 0.999999f;
-                            ent[n_e] = (b << 5) | cn;
-                            lbo[n_e] = (__float_as_uint(lb) & ~127u) | (unsigned)o;   // truncated downward: still a lower bound
-                            ++n_e;
-                            total += (int)cn;
-                        }
-                    }
+            for (int o = 0; o < V; ++o) {
+                const int ox = c_off_fast[4 * o], oy = c_off_fast[4 * o + 1], oz = c_off_fast[4 * o + 2];
+                const int vx = kx + ox, vy = ky + oy, vz = kz + oz;
+                unsigned b, cn;
+                if (map_find(A.slots, A.mask, vx, vy, vz, b, cn) && (int)cn >= c.thr_occ) {            // :386-390
+                    const float lox = (float)((vx > 0 ? vx : vx - 1) - kx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - kx) * size_f;
+                    const float loy = (float)((vy > 0 ? vy : vy - 1) - ky) * size_f, hiy = (float)((vy < 0 ? vy : vy + 1) - ky) * size_f;
+                    const float loz = (float)((vz > 0 ? vz : vz - 1) - kz) * size_f, hiz = (float)((vz < 0 ? vz : vz + 1) - kz) * size_f;
+                    const float gx = fmaxf(fmaxf(lox - relx, relx - hix) - lb_margin, 0.f);
+                    const float gy = fmaxf(fmaxf(loy - rely, rely - hiy) - lb_margin, 0.f);
+                    const float gz = fmaxf(fmaxf(loz - relz, relz - hiz) - lb_margin, 0.f);
+                    const float lb = (gx * gx + gy * gy + gz * gz) * 0.999999f;
+                    ent[n_e] = (b << 5) | cn;
+                    lbo[n_e] = (__float_as_uint(lb) & ~127u) | (unsigned)o;   // truncated downward: still a lower bound
+                    ++n_e;
+                    total += (int)cn;
                 }
             }
         }
@@ -266,8 +244,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
             for (int j = 0; j < NS; ++j) cand[j] = lst[j];
             u64 xk[NS];
             unsigned xi[NS], xp[NS];
-#pragma unroll 4
-            for (int j = 0; j < m; ++j) {   // independent iterations: the unroll keeps 4 point loads in flight
+            for (int j = 0; j < m; ++j) {
                 const unsigned e = (cand[j] >> 5) & 31u, i = cand[j] & 31u;
                 const unsigned pt = (ent[e] >> 5) * kBlockFloats + 4u * i;
                 const float4 mp = __ldg(reinterpret_cast<const float4*>(A.blocks + pt));

@@ -162,7 +162,6 @@ struct srl_sweep {
     unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
     bool order_valid = false;
     unsigned char* d_flags = nullptr;   // capacity
-    bool flags_clean = false;           // flags outside the current shard are known to be zero
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
     int* d_status = nullptr;        // capacity, lazily allocated
     // debug buffers, lazily allocated
