@@ -227,3 +227,18 @@ int main() {
         assert r.returncode == 0 and "constructed mapSize=0 K=20" in r.stdout
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs the CPU oracle only (no GPU) and prints one JSON line with the contract's keys."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--points", "3000", "--map-extent", "80"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and line["value"] > 0
+    assert "workload" in line["config"]
