@@ -264,8 +264,8 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     ms_res, k1_ms, k1_n, launches = timed(step_resident, True)
-    clk = clocks.stop()
     ms_e2e, _, _, _ = timed(step_e2e, False)
+    clk = clocks.stop()   # sampled over both timed regions
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")

@@ -384,23 +384,23 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
 // sweep ordering: Morton code of the LiDAR-frame 1 m cell of every keypoint, stable radix sort -> order[]
 // (a rigid transform keeps neighbours neighbours, so the order is pose independent and computed once per sweep)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 spread21(u64 x) {
-    x &= 0x1fffffull;
-    x = (x | x << 32) & 0x1f00000000ffffull;
-    x = (x | x << 16) & 0x1f0000ff0000ffull;
-    x = (x | x << 8) & 0x100f00f00f00f00full;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-    x = (x | x << 2) & 0x1249249249249249ull;
+// 10 bits per axis (1 m cells within +-512 m of the sensor; farther points are clamped, which only costs locality):
+// 30-bit Morton keys -> 4 radix passes
+__device__ __forceinline__ unsigned spread10(unsigned x) {
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
     return x;
 }
-__global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double cell, u64* keys, unsigned* idx) {
+__global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double cell, unsigned* keys, unsigned* idx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double lim = 1048575.0;
-    const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 524288.0, 0.0), lim);
-    const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 524288.0, 0.0), lim);
-    const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 524288.0, 0.0), lim);
-    keys[i] = spread21((u64)fx) | (spread21((u64)fy) << 1) | (spread21((u64)fz) << 2);
+    const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 512.0, 0.0), 1023.0);
+    const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 512.0, 0.0), 1023.0);
+    const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 512.0, 0.0), 1023.0);
+    keys[i] = spread10((unsigned)fx) | (spread10((unsigned)fy) << 1) | (spread10((unsigned)fz) << 2);
     idx[i] = (unsigned)i;
 }
 
@@ -408,19 +408,19 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
                                 size_t* needed, cudaStream_t stream) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (u64*)nullptr, (u64*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 63, stream);
-    const size_t need = al(n * 8) * 2 + al(n * 4) + al(tmp);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 30, stream);
+    const size_t need = al(n * 4) * 3 + al(tmp);
     if (needed) *needed = need;
     if (!scratch || scratch_bytes < need) return cudaSuccess;
     char* p = static_cast<char*>(scratch);
-    u64* ka = reinterpret_cast<u64*>(p); p += al(n * 8);
-    u64* kb = reinterpret_cast<u64*>(p); p += al(n * 8);
+    unsigned* ka = reinterpret_cast<unsigned*>(p); p += al(n * 4);
+    unsigned* kb = reinterpret_cast<unsigned*>(p); p += al(n * 4);
     unsigned* ia = reinterpret_cast<unsigned*>(p); p += al(n * 4);
     const int T = 256;
     k_sweep_keys<<<(unsigned)((n + T - 1) / T), T, 0, stream>>>(d_raw, n, 1.0, ka, ia);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return cub::DeviceRadixSort::SortPairs(p, tmp, ka, kb, ia, d_order, (int)n, 0, 63, stream);
+    return cub::DeviceRadixSort::SortPairs(p, tmp, ka, kb, ia, d_order, (int)n, 0, 30, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
