@@ -222,6 +222,14 @@ int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, const double
 int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sweep, const double q[4], const double t[3],
                                const double R_il[9], const double t_il[3], double* d_world_xyz);
 
+/* ---- keypoint selection: gridSampling / subSampleFrame (src/utility.cpp:167-201), called at
+ * src/optimize.cpp:431.  One point per cell of size_voxel_subsampling (the first in frame order), emitted in the
+ * reference's order, i.e. the iteration order of its std::tr1::unordered_map<voxel, ...> grid.  The dedupe over the n
+ * points runs on the GPU; the order is produced by replaying the unique cells through the same libstdc++ container.
+ * xyz_world: host n*3 doubles (point3D::point); keypoint_index_out: capacity n; indices into the frame. */
+int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double size_voxel_subsampling,
+                      uint32_t* keypoint_index_out, size_t* n_keypoints);
+
 /* eskfEstimator::observe (src/eskfEstimator.cpp:219-230) — host math, exported for parity tests */
 int srl_eskf_observe(srl_eskf_state* eskf, const double d_x[17]);
 

@@ -122,6 +122,8 @@ def lib(prefer_tsl: bool = True):
     L.orc_update_iekf.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(EskfState)] + [C.c_void_p] * 5 + [
         C.POINTER(IcpParams), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_int32]
     L.orc_update_iekf.restype = C.c_int32
+    L.orc_grid_sampling.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    L.orc_grid_sampling.restype = C.c_int64
     L.orc_quat_to_rot.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_eig3_sym.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_eskf_observe.argtypes = [C.POINTER(EskfState), C.c_void_p]
@@ -293,6 +295,14 @@ class Eskf:
         d = _f64(dx)
         lib().orc_eskf_observe(C.byref(st), _ptr(d))
         return Eskf.from_c(st)
+
+
+def grid_sampling(xyz, size_voxel_subsampling: float) -> np.ndarray:
+    """gridSampling (src/utility.cpp:188-201): frame indices of the keypoints, reference order."""
+    xyz = _f64(xyz).reshape(-1, 3)
+    out = np.zeros(xyz.shape[0], np.int32)
+    m = lib().orc_grid_sampling(_ptr(xyz), xyz.shape[0], size_voxel_subsampling, _ptr(out))
+    return out[:m].copy()
 
 
 def quat_to_rot(q) -> np.ndarray:

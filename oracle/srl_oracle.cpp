@@ -52,6 +52,8 @@
 #include <tuple>
 #include <vector>
 
+#include <tr1/unordered_map>
+
 #ifdef SRL_ORACLE_TSL
 #include <tsl/robin_map.h>
 #else
@@ -1146,6 +1148,22 @@ int32_t orc_update_iekf(void* map, const double* raw_xyz, int64_t n, orc_eskf_st
     }
     if (passes_run) *passes_run = passes;
     return success;
+}
+
+// subSampleFrame (src/utility.cpp:167-186) as called by gridSampling (:188-201); vectors hold frame indices instead of
+// point3D copies, everything else (container type, hash, key expression, push_back, "n.second[0]") as written
+int64_t orc_grid_sampling(const double* xyz, int64_t n, double size_voxel, int32_t* out) {
+    std::tr1::unordered_map<voxel, std::vector<int32_t>, voxel_hash> grid;
+    for (int i = 0; i < (int)n; i++) {
+        auto kx = static_cast<short>(xyz[3 * i] / size_voxel);
+        auto ky = static_cast<short>(xyz[3 * i + 1] / size_voxel);
+        auto kz = static_cast<short>(xyz[3 * i + 2] / size_voxel);
+        grid[voxel(kx, ky, kz)].push_back(i);
+    }
+    int64_t m = 0;
+    for (const auto& g : grid)
+        if (g.second.size() > 0) out[m++] = g.second[0];
+    return m;
 }
 
 void orc_quat_to_rot(const double q[4], double R[9]) {

@@ -116,6 +116,10 @@ int32_t orc_update_iekf(void* map, const double* raw_xyz, int64_t n, orc_eskf_st
                         int32_t nthreads, int32_t* passes_run, int32_t* num_residuals_used,
                         double* trace, int32_t max_trace_rows);
 
+/* gridSampling / subSampleFrame (src/utility.cpp:167-201): indices of the kept points in the reference's order (the
+ * iteration order of its std::tr1::unordered_map grid). out has capacity n; returns the number of keypoints */
+int64_t orc_grid_sampling(const double* xyz, int64_t n, double size_voxel_subsampling, int32_t* out);
+
 /* small pieces exported for self-checks */
 void orc_quat_to_rot(const double q[4], double R[9]);                 /* Eigen toRotationMatrix */
 void orc_eig3_sym(const double S[9], double evals[3], double evecs[9]); /* SelfAdjointEigenSolver<Matrix3d> */

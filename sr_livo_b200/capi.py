@@ -71,7 +71,7 @@ EXPORTS = [
     "srl_sweep_set_shard", "srl_build_plane_residuals", "srl_build_plane_residuals_async", "srl_normal_eq_unpack",
     "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_comm_create", "srl_comm_destroy", "srl_comm_export", "srl_comm_connect",
     "srl_update_iekf_dist", "srl_optimize_host", "srl_sweep_transform_device",
-    "srl_eskf_observe", "srl_host_plane_fit",
+    "srl_grid_sampling", "srl_eskf_observe", "srl_host_plane_fit",
 ]
 
 _lib = None
@@ -136,6 +136,7 @@ def lib():
     L.srl_optimize_host.argtypes = [vp, vp, vp, vp, sz, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
                                     C.POINTER(IekfSummary), vp]
     L.srl_sweep_transform_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.srl_grid_sampling.argtypes = [vp, vp, sz, dbl, vp, C.POINTER(sz)]
     L.srl_eskf_observe.argtypes = [C.POINTER(EskfState), vp]
     L.srl_host_plane_fit.argtypes = [vp, i32, vp, vp, vp]
     for name in EXPORTS:

@@ -9,6 +9,8 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <tr1/unordered_map>
+
 #include "srl_internal.h"
 
 namespace srl {
@@ -175,6 +177,26 @@ __global__ void __launch_bounds__(256) k_seg_process(Slot* slots, float* blocks,
         reinterpret_cast<unsigned int*>(bp)[kMetaCount] = (unsigned int)count;
         atomicAdd(reinterpret_cast<unsigned long long*>(n_points), (unsigned long long)added);
     }
+}
+
+// ---- N2: gridSampling / subSampleFrame (src/utility.cpp:167-201) ----------------------------------------------------
+// cell key from the DOUBLE coordinate (src/utility.cpp:171-173: static_cast<short>(frame[i].point[k] / size_voxel))
+__global__ void k_cell_keys(const double* __restrict__ xyz, long long n, double size, unsigned long long* keys, unsigned int* idx) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qx = __ddiv_rn(xyz[3 * i], size), qy = __ddiv_rn(xyz[3 * i + 1], size), qz = __ddiv_rn(xyz[3 * i + 2], size);
+    unsigned long long key = kInvalidKey;
+    if (fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0) key = pack_key((int)qx, (int)qy, (int)qz);
+    keys[i] = key;
+    idx[i] = (unsigned int)i;
+}
+// after the stable sort by cell: the head of each run is the cell's first point in frame order; flag it at its own index
+__global__ void k_first_in_cell(const unsigned long long* __restrict__ keys_sorted, const unsigned int* __restrict__ idx_sorted,
+                                long long n, unsigned char* is_first) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long k = keys_sorted[j];
+    is_first[idx_sorted[j]] = (k != kInvalidKey && (j == 0 || keys_sorted[j - 1] != k)) ? 1 : 0;
 }
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -375,6 +397,77 @@ static int map_insert_impl(srl_map* m, const double* d_xyz, size_t n, double min
 static size_t insert_scratch_bytes(size_t n) {
     // generous upper bound: arrays + CUB temp (radix sort of 64-bit keys needs ~ (8+4)*n + small)
     return n * (8 + 8 + 4 + 4 + 12 + 1 + 4 + 4 + 4 + 4) + n * 16 + (1u << 20) + 16 * 256;
+}
+
+namespace {
+struct CellKey { short x, y, z; bool operator==(const CellKey& o) const { return x == o.x && y == o.y && z == o.z; } };
+struct CellHash {   // std::hash<voxel> of the reference (include/cloudMap.h:173-184)
+    std::size_t operator()(const CellKey& v) const {
+        const std::size_t kP1 = 73856093, kP2 = 19349669, kP3 = 83492791;
+        return v.x * kP1 + v.y * kP2 + v.z * kP3;
+    }
+};
+}  // namespace
+
+int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double size, uint32_t* out, size_t* n_out) {
+    if (!ctx || (n && (!xyz_world || !out)) || !n_out || !(size > 0)) return SRL_BAD_ARG;
+    *n_out = 0;
+    if (n == 0) return SRL_OK;
+    if (n > 0x7fffffffULL) return set_err(ctx, SRL_BAD_ARG, "srl_grid_sampling: n must fit in int32");
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t tmp_sort = 0, tmp_sel = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr,
+                                    (unsigned int*)nullptr, (int)n, 0, 50, st);
+    cub::DeviceSelect::Flagged(nullptr, tmp_sel, thrust::counting_iterator<unsigned int>(0), (unsigned char*)nullptr,
+                               (unsigned int*)nullptr, (int*)nullptr, (int)n, st);
+    const size_t tmp_bytes = std::max(tmp_sort, tmp_sel);
+    const size_t need = align_up(n * 24) + 2 * align_up(n * 8) + 3 * align_up(n * 4) + align_up(n) + 256 + align_up(tmp_bytes);
+    int rc = ensure_scratch(ctx, need);
+    if (rc != SRL_OK) return rc;
+    char* p = static_cast<char*>(ctx->d_scratch);
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
+    double* d_xyz = reinterpret_cast<double*>(take(n * 24));
+    unsigned long long* ka = reinterpret_cast<unsigned long long*>(take(n * 8));
+    unsigned long long* kb = reinterpret_cast<unsigned long long*>(take(n * 8));
+    unsigned int* ia = reinterpret_cast<unsigned int*>(take(n * 4));
+    unsigned int* ib = reinterpret_cast<unsigned int*>(take(n * 4));
+    unsigned int* sel = reinterpret_cast<unsigned int*>(take(n * 4));
+    unsigned char* is_first = reinterpret_cast<unsigned char*>(take(n));
+    int* d_count = reinterpret_cast<int*>(take(256));
+    void* d_tmp = take(tmp_bytes);
+    SRL_CUDA(ctx, cudaMemcpyAsync(d_xyz, xyz_world, n * 24, cudaMemcpyHostToDevice, st));
+    const int T = 256;
+    const unsigned gb = (unsigned)((n + T - 1) / T);
+    k_cell_keys<<<gb, T, 0, st>>>(d_xyz, (long long)n, size, ka, ia);
+    size_t tb = tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(d_tmp, tb, ka, kb, ia, ib, (int)n, 0, 50, st);
+    k_first_in_cell<<<gb, T, 0, st>>>(kb, ib, (long long)n, is_first);
+    tb = tmp_bytes;
+    cub::DeviceSelect::Flagged(d_tmp, tb, thrust::counting_iterator<unsigned int>(0), is_first, sel, d_count, (int)n, st);
+    ctx->launches += 2;
+    SRL_CUDA(ctx, cudaGetLastError());
+    int m = 0;
+    SRL_CUDA(ctx, cudaMemcpyAsync(&m, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SRL_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<unsigned int> first((size_t)m);
+    if (m) SRL_CUDA(ctx, cudaMemcpy(first.data(), sel, (size_t)m * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    // `first` = the frame indices that open a new cell, in frame order: exactly the sequence of node insertions the
+    // reference's grid sees (later points of a cell only push_back into an existing node).  Replaying it through the same
+    // libstdc++ container gives the reference's iteration order (src/utility.cpp:180-187).
+    std::tr1::unordered_map<CellKey, unsigned int, CellHash> grid;
+    for (int j = 0; j < m; ++j) {
+        const unsigned int i = first[(size_t)j];
+        CellKey k;
+        k.x = static_cast<short>(xyz_world[3 * (size_t)i] / size);
+        k.y = static_cast<short>(xyz_world[3 * (size_t)i + 1] / size);
+        k.z = static_cast<short>(xyz_world[3 * (size_t)i + 2] / size);
+        grid[k] = i;
+    }
+    size_t w = 0;
+    for (std::tr1::unordered_map<CellKey, unsigned int, CellHash>::const_iterator it = grid.begin(); it != grid.end(); ++it) out[w++] = it->second;
+    *n_out = w;
+    return SRL_OK;
 }
 
 int srl_map_insert_device(srl_map* m, const double* d_xyz_world, size_t n, double min_distance_points, int32_t min_num_points,

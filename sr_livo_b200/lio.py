@@ -278,6 +278,15 @@ class LioOptimization:
     def mapSize(self) -> int:
         return self.voxel_map.stats()[1]
 
+    # ---- src/utility.cpp:188-201, called at src/optimize.cpp:431
+    def gridSampling(self, points_world, size_voxel_subsampling: float) -> np.ndarray:
+        """Frame indices of the keypoints (first point of every cell), in the reference's order."""
+        xyz = f64(points_world).reshape(-1, 3)
+        out = np.zeros(xyz.shape[0], np.uint32)
+        m = C.c_size_t(0)
+        _check(self.ctx.h, lib().srl_grid_sampling(self.ctx.h, ptr(xyz), xyz.shape[0], size_voxel_subsampling, ptr(out), C.byref(m)))
+        return out[:m.value].copy()
+
     def setKeypoints(self, raw_xyz):
         """std::vector<point3D> keypoints (raw_point members), uploaded once per sweep."""
         self.sweep.upload(raw_xyz)

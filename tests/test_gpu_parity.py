@@ -220,6 +220,34 @@ def test_fast_kernel_lanes_per_keypoint_variants(L, small_world, lpk):
     assert g2.num_residuals == o.num_residuals and _close(g2.HTH, o.HTH)
 
 
+@pytest.mark.parametrize("size,cap_pts", [(0.5, 20), (2.0, 20), (0.7, 12)])
+def test_other_voxel_sizes_and_caps(size, cap_pts):
+    """Nothing in the kernels may assume the 1 m / 20-point configuration the reference ships: map insert, keys, cell
+    lower bounds and the FP32 error window all scale with size_voxel_map (0.7 is not exactly representable)."""
+    from sr_livo_b200 import lio
+    pts = synth.sample_map_points(80.0, 120.0 if size < 1 else 40.0, seed=5)
+    sw = synth.make_sweep(3000, seed=1005, yaw=0.4)
+    Lx = lio.LioOptimization(max_voxels=1 << 19, sweep_capacity=4096, size_voxel_map=size, max_num_points_in_voxel=cap_pts)
+    try:
+        om = O.OracleMap()
+        md = 0.15 * size
+        assert Lx.addPointsToMap(pts, min_distance_points=md) == om.add_points(pts, voxel_size=size, max_num_points_in_voxel=cap_pts,
+                                                                               min_distance_points=md)
+        g_keys, g_cnt, g_xyz = Lx.voxel_map.download()
+        o_keys, o_cnt, o_xyz = om.snapshot(cap=cap_pts)
+        gd, od = _map_dict(g_keys, g_cnt, g_xyz), _map_dict(o_keys, o_cnt, o_xyz)
+        assert gd.keys() == od.keys() and all(np.array_equal(gd[k], od[k]) for k in od)
+        kw = dict(max_num_residuals=BIG, size_voxel_map=size, max_dist_to_plane_icp=0.3 * size)
+        Lx.setKeypoints(sw.raw_xyz)
+        for extra in (dict(), dict(frame_id=5)):
+            g = Lx.buildPlaneResiduals(lio.r3live_params(**kw, **extra), sw.q_init, sw.t_init, sw.t_last, debug=True)
+            o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, O.r3live_params(**kw, **extra), debug=True)
+            _assert_pass_equal(g, o)
+            assert o.num_full_neighborhoods > 300
+    finally:
+        Lx.close()
+
+
 def test_pass_config1_20k_points_200k_map(L, cfg1_world):
     """BASELINE config 1: 20k-pt sweep, ~200k-pt map, 1 ESIKF iteration, r3live params (cap lifted and cap 600)."""
     from sr_livo_b200 import lio
@@ -423,6 +451,34 @@ def test_streaming_sweeps_insert_then_query(L, small_world):
         assert np.allclose(w, world, atol=1e-12)
         assert added == om.add_points(w)
     _assert_map_equal(L, om)
+
+
+def test_grid_sampling_matches_the_reference_order(L, small_world):
+    """Row N2: gridSampling (src/utility.cpp:188-201).  Same keypoints in the same order as the reference's
+    std::tr1::unordered_map walk (order matters: the max_num_residuals cap takes keypoints in that order)."""
+    from sr_livo_b200 import lio
+    sw = synth.make_sweep(60000, seed=1400, yaw=0.3)
+    w = synth.registered_points(sw)
+    for size in (1.5, 0.25, 7.0):
+        g = L.gridSampling(w, size)
+        o = O.grid_sampling(w, size)
+        assert np.array_equal(g.astype(np.int64), o.astype(np.int64))
+    assert L.gridSampling(np.zeros((0, 3)), 1.5).size == 0
+    assert np.array_equal(L.gridSampling(w[:1], 1.5), [0])
+    neg = -w[:5000]
+    assert np.array_equal(L.gridSampling(neg, 1.5).astype(np.int64), O.grid_sampling(neg, 1.5).astype(np.int64))
+    # end to end like optimize(): keypoints from gridSampling, then the capped update (r3live.yaml: 600 residuals)
+    om, sw0 = _load_world(L, small_world)
+    w0 = synth.registered_points(sw0, sw0.q_init, sw0.t_init)
+    kp = L.gridSampling(w0, 0.4)
+    assert np.array_equal(kp.astype(np.int64), O.grid_sampling(w0, 0.4).astype(np.int64)) and kp.size > 700
+    raw = sw0.raw_xyz[kp]
+    L.setKeypoints(raw)
+    L.eskf_pro = lio.EskfEstimator(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=synth.prior_covariance())
+    summ, fq, ft = L.updateIEKF(lio.r3live_params(), sw0.t_last)
+    ref = om.update_iekf(raw, O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=synth.prior_covariance()), sw0.t_last, O.r3live_params())
+    assert summ.passes_run == ref["passes"] and summ.num_residuals_used == ref["num_residuals_used"] == 600
+    assert np.allclose(ft, ref["frame_t"], atol=1e-9) and np.allclose(fq, ref["frame_q"], atol=1e-9)
 
 
 # ---- BASELINE-size properties (size-independent checks; the oracle would take too long to be the checker) ---------

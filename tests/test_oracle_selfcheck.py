@@ -306,3 +306,18 @@ def test_update_iekf_pass_count_rules(small_world):
     # too few residuals -> success false after the first pass
     r3 = om.update_iekf(sw.raw_xyz[:5], e0, sw.t_last, O.r3live_params(max_num_residuals=BIG))
     assert not r3["success"] and r3["passes"] == 1
+
+
+# ---- gridSampling / subSampleFrame (src/utility.cpp:167-201) -------------------------------------------------------
+def test_grid_sampling_keeps_the_first_point_of_every_cell(small_world):
+    sw = small_world["sweep"]
+    w = synth.registered_points(sw)
+    for size in (1.5, 0.4):
+        idx = O.grid_sampling(w, size)
+        cells = np.trunc(w / size).astype(np.int64)           # static_cast<short>: truncation toward zero
+        uniq, first = np.unique(cells, axis=0, return_index=True)
+        assert len(idx) == len(uniq) == len(set(idx.tolist()))
+        assert set(idx.tolist()) == set(first.tolist())       # n.second[0] = first point pushed into the cell
+    # the order is the hash container's, not the frame's (which is why it has to be reproduced, not re-invented)
+    assert not np.array_equal(idx, np.sort(idx))
+    assert O.grid_sampling(np.zeros((0, 3)), 1.5).size == 0
