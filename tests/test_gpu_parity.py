@@ -481,6 +481,31 @@ def test_grid_sampling_matches_the_reference_order(L, small_world):
     assert np.allclose(ft, ref["frame_t"], atol=1e-9) and np.allclose(fq, ref["frame_q"], atol=1e-9)
 
 
+def test_randomized_parity_many_sweeps_and_poses(L, cfg1_world):
+    """A few hundred thousand associations over random sensor poses, sweep patterns and pose errors: every neighbour
+    list must equal the oracle's (the FP32 window / guard / fallback logic has to hold on all of them, not on average)."""
+    import os
+    from sr_livo_b200 import lio
+    om, _ = _load_world(L, cfg1_world)
+    prm, oprm = lio.r3live_params(max_num_residuals=BIG), O.r3live_params(max_num_residuals=BIG)
+    rng = np.random.default_rng(77)
+    total = full = 0
+    amb0 = L.ctx.counter("fast_ambiguous")
+    for trial in range(12):
+        pos = (float(rng.uniform(-30, 30)), float(rng.uniform(-8, 8)), float(rng.uniform(1.0, 4.0)))
+        sw = synth.make_sweep(20000, seed=2000 + trial, yaw=float(rng.uniform(-3.1, 3.1)), position=pos,
+                              pattern="spinning" if trial % 3 == 2 else "livox", dp_max=float(rng.uniform(0.0, 0.3)),
+                              dth_max_deg=float(rng.uniform(0.0, 3.0)), pose_seed=trial)
+        L.setKeypoints(sw.raw_xyz)
+        g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, oprm, nthreads=min(32, os.cpu_count() or 1), debug=True)
+        _assert_pass_equal(g, o)
+        total += sw.raw_xyz.shape[0]
+        full += int((o.status >= 1).sum())
+    assert total == 240000 and full > 100000
+    assert L.ctx.counter("fast_ambiguous") - amb0 <= 0.001 * full
+
+
 # ---- BASELINE-size properties (size-independent checks; the oracle would take too long to be the checker) ---------
 def test_full_size_properties_100k_sweep_large_map():
     from sr_livo_b200 import dist, lio
