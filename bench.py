@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--passes", type=int, default=3, help="ESIKF passes per sweep (config 2: 3, config 5: 5)")
     ap.add_argument("--pattern", default="livox", choices=["livox", "spinning"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k1-variant", type=int, default=0, help="0 auto, 1 k1_fast, 2 k1_assoc only, 3 k1_scan + k1_fit (A/B runs)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     args = ap.parse_args()
     global N_PASSES
@@ -173,6 +174,8 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream or 1        # 1 == cudaStreamLegacy
     L = lio.LioOptimization(device=local, stream=stream, max_voxels=1 << 21 if args.map_extent <= 900 else 1 << 23,
                             sweep_capacity=max(args.points, 1024))
+    if args.k1_variant:
+        L.ctx.set_option("k1_variant", args.k1_variant)
     L.ctx.set_timing(True)
 
     # ---- map: built by the product's own insert kernel (every rank builds its replica from the same seed)

@@ -133,7 +133,8 @@ int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
  * time and launch count of the passes since the last reset (bench.py "roofline"). Reading synchronises the stream. */
 int srl_ctx_set_timing(srl_ctx* ctx, int enable);
 /* tuning / test knobs: "force_exact_selection" (0|1: every keypoint takes k1_assoc's exact FP64 selection),
- * "k1_variant" (0 auto: k1_fast + exact fallback where applicable; 2: k1_assoc only), "k1_min_blocks" (2|3|4) and
+ * "k1_variant" (0 auto; 1: k1_fast, 3: k1_scan + k1_fit, both with the exact fallback where applicable; 2: k1_assoc
+ * only), "split_lanes_per_keypoint" (2|4: lanes per keypoint in k1_scan), "k1_min_blocks" (2|3|4) and
  * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_lanes_per_keypoint" (1|2|4:
  * lanes that share one keypoint's candidate scan in k1_fast), "fast_force_ambiguous_mod" (N > 0:
  * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over).  Counters: "exact_fallbacks"

@@ -95,6 +95,8 @@ static void unpack32(const double* o, srl_normal_eq* out, long long n_keypoints)
     out->reserved = 0;
 }
 
+constexpr bool kDefaultSplit = false;   // variant 0 (auto): k1_fast unless the split form measures faster (profiles/README.md)
+
 static int pass_grid(srl_ctx* ctx, long long n, int K, int nb) {
     const long long n_groups = (n + 31) / 32;
     long long want = n_groups;   // block-minor group assignment: one group per block first, then per warp
@@ -146,12 +148,20 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
-        const long long kpw = 32 / k1_fast_lanes_per_keypoint();
-        const long long n_groups = (n + kpw - 1) / kpw;
-        // one group per warp when it fits (the block scheduler then balances the waves), grid-stride beyond that
-        long long grid = std::min<long long>((n_groups + kFastWarps - 1) / kFastWarps, (long long)ctx->max_grid);
-        grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
-        SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
+        const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
+        if (split) {
+            if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)32)) != SRL_OK) return rc;
+            f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
+            SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
+            ctx->launches += 1;
+        } else {
+            const long long kpw = 32 / k1_fast_lanes_per_keypoint();
+            const long long n_groups = (n + kpw - 1) / kpw;
+            // one group per warp when it fits (the block scheduler then balances the waves), grid-stride beyond that
+            long long grid = std::min<long long>((n_groups + kFastWarps - 1) / kFastWarps, (long long)ctx->max_grid);
+            grid = std::max<long long>(1, std::min<long long>(grid, ctx->max_grid));
+            SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
+        }
         K1Args b = a;   // exact selection for the keypoints k1_fast could not decide; its last block adds k1_fast's sums
         b.k_begin = 0; b.k_end = (long long)sw->n; b.only_flagged = sw->d_flags; b.prev_out32 = ctx->d_fast_out;
         // almost always nothing is flagged: a one-block-per-SM grid walks the flags (32 per warp step) and leaves
@@ -191,6 +201,8 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
               cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_fast_out, 32 * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_scan_count, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->d_scan_count, 0, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
@@ -203,7 +215,7 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out); cudaFree(ctx->d_scan_count);
     cudaFree(ctx->d_scratch);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -230,13 +242,18 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
         k1_fast_set_lanes_per_keypoint((int)value);
         return SRL_OK;
     }
+    if (n == "split_lanes_per_keypoint") {
+        if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");
+        k1_split_set_lanes_per_keypoint((int)value);
+        return SRL_OK;
+    }
     if (n == "fast_min_blocks") {
         if (value != 4 && value != 5 && value != 6 && value != 8) return set_err(ctx, SRL_BAD_ARG, "fast_min_blocks must be 4, 5, 6 or 8");
         k1_fast_set_min_blocks((int)value);
         return SRL_OK;
     }
     if (n == "k1_variant") {
-        if (value != 0 && value != 2) return set_err(ctx, SRL_BAD_ARG, "k1_variant must be 0 (auto) or 2 (k1_assoc only)");
+        if (value < 0 || value > 3) return set_err(ctx, SRL_BAD_ARG, "k1_variant must be 0 (auto), 1 (k1_fast), 2 (k1_assoc only) or 3 (k1_scan + k1_fit)");
         ctx->variant = (int)value;
         return SRL_OK;
     }
@@ -300,7 +317,7 @@ int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out) {
 }
 void srl_sweep_destroy(srl_sweep* s) {
     if (!s) return;
-    cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status); cudaFree(s->d_order); cudaFree(s->d_flags);
+    cudaFree(s->d_raw); cudaFree(s->d_rows); cudaFree(s->d_status); cudaFree(s->d_order); cudaFree(s->d_flags); cudaFree(s->d_cand_rows);
     cudaFree(s->d_dbg_world); cudaFree(s->d_dbg_nbr); cudaFree(s->d_dbg_nbr_dist); cudaFree(s->d_dbg_plane);
     delete s;
 }

@@ -19,6 +19,7 @@
 //     flagged keypoints only), whose final step adds this kernel's sums.
 // Handles voxel_neighborhood <= 1 and max/min_number_neighbors == 20 (every reference config outside the first
 // 20 init frames); anything else goes to k1_assoc alone.
+#include <algorithm>
 #include <cstdlib>
 
 #include <cub/cub.cuh>
@@ -380,6 +381,458 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
     }
 }
 
+// =========================================================================================================
+// Split form of the pass: k1_scan (LPK lanes per keypoint, FP32 selection) -> k1_fit (thread per keypoint, FP64).
+//
+// k1_fast is bound by the length of ONE thread's dependent chain (a 100k-point sweep is a single wave of 21 warps per
+// SM: time = latency of a warp that probes, scans ~270 candidates, finishes and fits, profiles/README.md).  The split
+// form cuts that chain where it can be cut:
+//   * k1_scan gives every keypoint LPK lanes: the 27 probes are dealt to the lanes (results shared through shared
+//     memory), every voxel's candidates are dealt round-robin, each lane keeps only its NLS best packed keys (NLS < NL:
+//     a lane that could have dropped a relevant key flags the keypoint instead), with all NLS stages of an insertion
+//     independent of each other.  The group's bound for the voxel skip is the largest of the lanes' ceil(K/LPK)-th
+//     keys (LPK * ceil(K/LPK) >= K tracked candidates are at least that close).  The lanes' lists are merged with an
+//     in-register bitonic network over shuffles, the verdict is the one of k1_fast, and the boundary-inclusive
+//     candidates go to HBM/L2 as (block * 20 + index, offset id) per sorted position (coalesced for k1_fit).
+//   * k1_fit is k1_fast's exact FP64 finish + plane fit + residual + reduction, one thread per keypoint.
+// Four times as many, four times shorter warps in the scan; no idle lanes in the fit.
+// =========================================================================================================
+constexpr int kScanThreads = 128;
+constexpr unsigned KINF = 0xffffffffu;
+constexpr int kZone0 = 12;     // k1_fit resolves the K-th boundary among slots >= kZone0 (k1_scan flags anything wider)
+constexpr int kBestMax = 4;    // ... and the nearest neighbour among the first kBestMax slots
+static_assert(NS == kSplitSlots, "srl_internal.h: kSplitSlots must equal NS");
+
+// the 32 smallest (sorted) of my sorted list and the partner lane's (xor distance d); only the first NV entries of the
+// inputs can be finite.  min(a[j], b[31-j]) is a bitonic sequence of the 32 smallest; 5 half-cleaner stages sort it.
+template <int NV>
+__device__ __forceinline__ void merge_with_partner(unsigned (&l)[32], unsigned gmask, int d) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int r = 31 - j;
+        const unsigned a = l[j], b = l[r];
+        unsigned ta = KINF, tb = KINF;
+        if (r < NV) ta = __shfl_xor_sync(gmask, b, d);   // partner's l[31-j] meets my l[j]
+        if (j < NV) tb = __shfl_xor_sync(gmask, a, d);   // partner's l[j] meets my l[31-j]
+        l[j] = min(a, ta);
+        l[r] = min(b, tb);
+    }
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if ((j & st) == 0) {
+                const unsigned lo = min(l[j], l[j + st]), hi = max(l[j], l[j + st]);
+                l[j] = lo; l[j + st] = hi;
+            }
+        }
+    }
+}
+
+template <int LPK, int NLS, int MINB>
+__global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) {
+    static_assert(LPK == 2 || LPK == 4, "lanes per keypoint");
+    constexpr int KPW = 32 / LPK;                 // keypoints per warp
+    constexpr int KPB = kScanThreads / LPK;       // keypoints per block
+    constexpr int Q = (KF + LPK - 1) / LPK;       // the largest of the lanes' Q-th keys bounds the K-th overall from above
+    static_assert(NLS >= Q && NLS <= NL, "per-lane list length");
+    __shared__ unsigned s_ent[KPB][27];           // (block << 5 | count) of the voxel at offset o, 0 = absent / too few points
+    __shared__ unsigned s_lb[KPB][27];            // lower bound of the squared distance to that voxel (FP32 bits)
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPK;
+    const int kp = threadIdx.x / LPK;
+    const unsigned gmask = ((1u << LPK) - 1u) << (lane & ~(LPK - 1));
+    const PassConst& c = A.c;
+    const int nb = c.nb;
+    const int W = 2 * nb + 1;
+    const int V = W * W * W;
+    const float size_f = (float)c.size;
+    const float lb_margin = 1e-5f * size_f;
+    const float eps_abs = 1e-4f * size_f * size_f;
+    const float kRel = 1.0f / 2048.0f;
+
+    unsigned long long scanned = 0;
+    const long long n = A.s_end - A.s_begin;
+    const long long n_groups = (n + KPW - 1) / KPW;
+    const long long G = gridDim.x;
+
+    for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * (kScanThreads / 32)) {
+        const long long s = A.s_begin + g * KPW + lane / LPK;
+        const bool valid = s < A.s_end;
+        const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
+        int kx = 0, ky = 0, kz = 0;
+        float relx = 0, rely = 0, relz = 0, ofx = 0, ofy = 0, ofz = 0, rfx = 0, rfy = 0, rfz = 0;
+        bool in_range = false;
+        if (valid) {
+            const double rx = A.raw[3 * k], ry = A.raw[3 * k + 1], rz = A.raw[3 * k + 2];
+            double tx, ty, tz;
+            matvec3_exact(c.R_il, rx, ry, rz, tx, ty, tz);
+            const double bx = SRL_ADD(tx, c.t_il[0]), by = SRL_ADD(ty, c.t_il[1]), bz = SRL_ADD(tz, c.t_il[2]);   // src/optimize.cpp:83
+            matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);
+            const double pwx = SRL_ADD(tx, c.t[0]), pwy = SRL_ADD(ty, c.t[1]), pwz = SRL_ADD(tz, c.t[2]);         // :38
+            const double qx = SRL_DIV(pwx, c.size), qy = SRL_DIV(pwy, c.size), qz = SRL_DIV(pwz, c.size);        // :372-374
+            in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;
+            if (in_range) {
+                kx = (int)qx; ky = (int)qy; kz = (int)qz;
+                const double cx = (double)kx * c.size, cy = (double)ky * c.size, cz = (double)kz * c.size;
+                relx = (float)(pwx - cx); rely = (float)(pwy - cy); relz = (float)(pwz - cz);
+                ofx = (float)cx; ofy = (float)cy; ofz = (float)cz;
+                rfx = (float)(pwx - (double)ofx); rfy = (float)(pwy - (double)ofy); rfz = (float)(pwz - (double)ofz);
+            }
+        }
+
+        // ---- probes: the group's 27 voxels dealt to its lanes; the present ones are packed (in offset order: nearest
+        //      voxels first) into the group's shared-memory rows
+        int total = 0, n_e = 0;
+        for (int o0 = 0; o0 < V; o0 += LPK) {
+            const int o = o0 + sub;
+            unsigned e_out = 0, l_out = 0;
+            if (in_range && o < V) {
+                const int ox = c_off_fast[4 * o], oy = c_off_fast[4 * o + 1], oz = c_off_fast[4 * o + 2];
+                const int vx = kx + ox, vy = ky + oy, vz = kz + oz;
+                unsigned b, cn;
+                if (map_find(A.slots, A.mask, vx, vy, vz, b, cn) && (int)cn >= c.thr_occ) {            // :386-390
+                    const float lox = (float)((vx > 0 ? vx : vx - 1) - kx) * size_f, hix = (float)((vx < 0 ? vx : vx + 1) - kx) * size_f;
+                    const float loy = (float)((vy > 0 ? vy : vy - 1) - ky) * size_f, hiy = (float)((vy < 0 ? vy : vy + 1) - ky) * size_f;
+                    const float loz = (float)((vz > 0 ? vz : vz - 1) - kz) * size_f, hiz = (float)((vz < 0 ? vz : vz + 1) - kz) * size_f;
+                    const float gx = fmaxf(fmaxf(lox - relx, relx - hix) - lb_margin, 0.f);
+                    const float gy = fmaxf(fmaxf(loy - rely, rely - hiy) - lb_margin, 0.f);
+                    const float gz = fmaxf(fmaxf(loz - relz, relz - hiz) - lb_margin, 0.f);
+                    e_out = (b << 5) | cn;
+                    l_out = (__float_as_uint((gx * gx + gy * gy + gz * gz) * 0.999999f) & ~127u) | (unsigned)o;   // truncated downward: still a lower bound
+                    total += (int)cn;
+                }
+            }
+            const unsigned present = (__ballot_sync(gmask, e_out != 0u) >> (lane & ~(LPK - 1))) & ((1u << LPK) - 1u);
+            if (e_out != 0u) {
+                const int pos = n_e + __popc(present & ((1u << sub) - 1u));
+                s_ent[kp][pos] = e_out;
+                s_lb[kp][pos] = l_out;
+            }
+            n_e += __popc(present);
+        }
+#pragma unroll
+        for (int d = 1; d < LPK; d <<= 1) total += __shfl_xor_sync(gmask, total, d);
+        __syncwarp(gmask);
+        const bool full_cand = in_range && total >= c.Kmin;   // else src/optimize.cpp:78 skips the keypoint
+
+        // ---- scan: this lane's share of every voxel's candidates through its own NLS-entry sorted list
+        unsigned lst[NLS];
+#pragma unroll
+        for (int j = 0; j < NLS; ++j) lst[j] = KINF;
+        if (full_cand) {
+            for (int e = 0; e < n_e; ++e) {
+                const unsigned ent = s_ent[kp][e];
+                const int cnt = (int)(ent & 31u);
+                const unsigned lbo = s_lb[kp][e];
+                unsigned tq = lst[Q - 1];
+#pragma unroll
+                for (int d = 1; d < LPK; d <<= 1) tq = max(tq, __shfl_xor_sync(gmask, tq, d));
+                const float T = key_value(tq);
+                if (__uint_as_float(lbo & ~127u) > T + T * kRel + 3.f * eps_abs) continue;   // voxel cannot matter any more
+                const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent >> 5) * kBlockFloats);
+                if (sub == 0) scanned += (unsigned)cnt;
+                for (int i = sub; i < cnt; i += LPK) {
+                    const float4 mp = __ldg(bp + i);
+                    const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
+                    const float d2f = dx * dx + dy * dy + dz * dz;
+                    const unsigned key = (__float_as_uint(d2f) & ~1023u) | ((unsigned)e << 5) | (unsigned)i;
+#pragma unroll
+                    for (int j = NLS - 1; j >= 1; --j) lst[j] = min(lst[j], max(lst[j - 1], key));   // stages independent of each other
+                    lst[0] = min(lst[0], key);
+                }
+            }
+        }
+
+        // ---- merge the lanes' lists (every lane ends up with the group's sorted best 32)
+        unsigned l32[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) l32[j] = (j < NLS) ? lst[j] : KINF;
+        const unsigned own_last = lst[NLS - 1];
+        __syncwarp(gmask);
+        merge_with_partner<NLS>(l32, gmask, 1);
+        if (LPK == 4) merge_with_partner<(2 * NLS < NL ? 2 * NLS : NL)>(l32, gmask, 2);
+
+        // ---- verdict (k1_fast's) + the lane certificate: what a lane dropped is not below its last tracked key
+        //      j0 = leading slots that are certainly among the K nearest (even their upper bound is below the (K+1)-th
+        //      key), b1 = leading slots that can be THE nearest; k1_fit computes exact distances only for [j0, m) and [0, b1)
+        bool ambiguous = false;
+        int m = 0, j0 = 0, b1 = 0;
+        if (full_cand) {
+            const float T = key_value(l32[KF - 1]);
+            const float lim = T + T * kRel + 2.5f * eps_abs;
+            const float kvK = key_value(l32[KF]);
+            const float v0 = key_value(l32[0]);
+            const float lim0 = v0 + v0 * kRel + 2.5f * eps_abs;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                const float kv = key_value(l32[j]);
+                m += (kv <= lim) ? 1 : 0;
+                b1 += (kv <= lim0) ? 1 : 0;
+                if (j < KF) j0 += (kv + kv * kRel + 2.5f * eps_abs < kvK) ? 1 : 0;
+            }
+            ambiguous = !(key_value(l32[NS]) > lim) || !(key_value(own_last) > lim) ||
+                        (m > KF && j0 < kZone0) || b1 > kBestMax || b1 > j0;
+        }
+        ambiguous = __any_sync(gmask, ambiguous);
+        if (full_cand && A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob
+        if (valid) {
+            // one 128-byte row per sorted position: 24 x u32 (block * 20 + index), 24 x u8 offset id, verdict byte
+            unsigned* row = A.cand_rows + (size_t)s * 32;
+            unsigned char* rowb = reinterpret_cast<unsigned char*>(row);
+            if (sub == 0) {
+                row[30] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
+                if (ambiguous) { A.flags[k] = 1; if (A.stats) atomicAdd(A.stats + 1, 1ull); }
+            }
+            if (full_cand && !ambiguous) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    if ((j % LPK) == sub && j < m) {
+                        const unsigned key = l32[j];
+                        const unsigned e = (key >> 5) & 31u, i = key & 31u;
+                        row[j] = (s_ent[kp][e] >> 5) * (unsigned)kBlockCap + i;
+                        rowb[96 + j] = (unsigned char)(s_lb[kp][e] & 127u);
+                    }
+                }
+            }
+        }
+        __syncwarp(gmask);   // the group's shared-memory rows are rewritten by the next group
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) scanned += __shfl_xor_sync(FULLM, scanned, sft);
+    if (lane == 0 && scanned) atomicAdd(A.scan_count, scanned);
+}
+
+// neighbour slots of one candidate row: point id (block * 20 + index) per slot and the mask of the K selected slots
+struct RowNb {
+    const float* blocks;
+    const unsigned (&cp)[24];
+    unsigned mask;
+    __device__ __forceinline__ bool use(int j) const { return (mask >> j) & 1u; }
+    __device__ __forceinline__ void get(int j, float& x, float& y, float& z) const {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(blocks + (size_t)cp[j] * 4u));
+        x = p.x; y = p.y; z = p.z;
+    }
+};
+
+// exact squared distance (reference operation order, src/optimize.cpp:394-395) as sortable bits
+__device__ __forceinline__ u64 exact_d2_bits(const float* blocks, unsigned cp, double pwx, double pwy, double pwz) {
+    const float4 mp = __ldg(reinterpret_cast<const float4*>(blocks + (size_t)cp * 4u));
+    const double dx = SRL_SUB((double)mp.x, pwx), dy = SRL_SUB((double)mp.y, pwy), dz = SRL_SUB((double)mp.z, pwz);
+    return (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
+}
+// (visit index of the voxel in the reference's loop order) << 5 | index in block: breaks exact distance ties
+__device__ __forceinline__ unsigned visit_id(unsigned cp, unsigned o, int nb, int W) {
+    const int vis = ((c_off_fast[4 * o] + nb) * W + (c_off_fast[4 * o + 1] + nb)) * W + (c_off_fast[4 * o + 2] + nb);
+    return ((unsigned)vis << 5) | (cp % (unsigned)kBlockCap);
+}
+
+template <bool DEBUG, int MINB>
+__global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const PassConst& c = A.c;
+    const int nb = c.nb;
+    const int W = 2 * nb + 1;
+
+    double acc = 0.0;
+    const long long n = A.s_end - A.s_begin;
+    const long long n_groups = (n + 31) / 32;
+    const long long G = gridDim.x;
+
+    for (long long g = (long long)blockIdx.x + (long long)warp * G; g < n_groups; g += G * kFastWarps) {
+        const long long s = A.s_begin + g * 32 + lane;
+        const bool valid = s < A.s_end;
+        const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
+        unsigned cp[24], visw[6], head = 0;
+#pragma unroll
+        for (int q = 0; q < 24; ++q) cp[q] = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) visw[q] = 0;
+        if (valid) {   // the keypoint's row, written by k1_scan just before: L2, all 8 loads in flight
+            const uint4* rp = reinterpret_cast<const uint4*>(A.cand_rows + (size_t)s * 32);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const uint4 w = __ldcg(rp + q);
+                cp[4 * q] = w.x; cp[4 * q + 1] = w.y; cp[4 * q + 2] = w.z; cp[4 * q + 3] = w.w;
+            }
+            const uint4 w6 = __ldcg(rp + 6), w7 = __ldcg(rp + 7);
+            visw[0] = w6.x; visw[1] = w6.y; visw[2] = w6.z; visw[3] = w6.w; visw[4] = w7.x; visw[5] = w7.y;
+            head = w7.z;
+        }
+        const int vd = (int)(head & 255u);
+        const bool ambiguous = vd == 255;
+        const bool do_fit = vd >= KF && vd <= NS;
+        const int m = do_fit ? vd : 0;
+        const int j0 = (int)((head >> 8) & 255u), b1 = (int)((head >> 16) & 255u);
+        double bx = 0, by = 0, bz = 0, pwx = 0, pwy = 0, pwz = 0;
+        int kx = 0, ky = 0, kz = 0;
+        if (valid) {
+            const double rx = A.raw[3 * k], ry = A.raw[3 * k + 1], rz = A.raw[3 * k + 2];
+            double tx, ty, tz;
+            matvec3_exact(c.R_il, rx, ry, rz, tx, ty, tz);
+            bx = SRL_ADD(tx, c.t_il[0]); by = SRL_ADD(ty, c.t_il[1]); bz = SRL_ADD(tz, c.t_il[2]);      // src/optimize.cpp:83
+            matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);
+            pwx = SRL_ADD(tx, c.t[0]); pwy = SRL_ADD(ty, c.t[1]); pwz = SRL_ADD(tz, c.t[2]);            // :38
+            if (DEBUG) {
+                if (do_fit) { kx = (int)SRL_DIV(pwx, c.size); ky = (int)SRL_DIV(pwy, c.size); kz = (int)SRL_DIV(pwz, c.size); }
+                if (A.dbg_world) { A.dbg_world[3 * k] = pwx; A.dbg_world[3 * k + 1] = pwy; A.dbg_world[3 * k + 2] = pwz; }
+            }
+        }
+
+        double v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+        int status = 0;
+        if (do_fit) {
+            // ---- the K-th boundary: slots [0, j0) are in; of the uncertain slots [j0, m) the m - K farthest by exact
+            //      (distance^2, visit index) are out.  Usually m == K and there is nothing to decide.
+            unsigned mask = (1u << m) - 1u;
+            if (m > KF) {
+                u64 zk[NS - kZone0];
+                unsigned zi[NS - kZone0];
+#pragma unroll
+                for (int j = kZone0; j < NS; ++j) {
+                    zk[j - kZone0] = 0ull; zi[j - kZone0] = 0u;
+                    if (j >= j0 && j < m) {
+                        zk[j - kZone0] = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
+                        zi[j - kZone0] = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                    }
+                }
+                for (int drop = m - KF; drop > 0; --drop) {
+                    u64 wk = 0; unsigned wi = 0; int wj = -1;
+#pragma unroll
+                    for (int j = kZone0; j < NS; ++j) {
+                        const bool in = j >= j0 && j < m && ((mask >> j) & 1u);
+                        if (in && (wj < 0 || zk[j - kZone0] > wk || (zk[j - kZone0] == wk && zi[j - kZone0] > wi))) {
+                            wk = zk[j - kZone0]; wi = zi[j - kZone0]; wj = j;
+                        }
+                    }
+                    mask &= ~(1u << wj);
+                }
+            }
+            // ---- vector_neighbors[0]: the exact nearest among the first b1 slots (usually b1 == 1)
+            unsigned best_cp = cp[0];
+            if (b1 > 1) {
+                u64 best = ~0ull;
+                unsigned best_id = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < kBestMax; ++j) {
+                    if (j < b1) {
+                        const u64 d = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
+                        const unsigned id = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                        if (d < best || (d == best && id < best_id)) { best = d; best_id = id; best_cp = cp[j]; }
+                    }
+                }
+            }
+            const float4 n0 = __ldg(reinterpret_cast<const float4*>(A.blocks + (size_t)best_cp * 4u));
+            PlaneRow row;
+            RowNb nbv{A.blocks, cp, mask};
+            plane_residual<NS>(nbv, KF, (double)n0.x, (double)n0.y, (double)n0.z, c, pwx, pwy, pwz, bx, by, bz, row);
+            status = row.accepted ? 2 : 1;
+            v[29] = 1.0;
+            v[31] = (double)row.nan_planarity;
+            const double h = row.distance * row.weight;                                                        // :169
+            if (row.accepted) {
+                v[0] = row.J[0] * row.J[0]; v[1] = row.J[0] * row.J[1]; v[2] = row.J[0] * row.J[2];
+                v[3] = row.J[0] * row.J[3]; v[4] = row.J[0] * row.J[4]; v[5] = row.J[0] * row.J[5];
+                v[6] = row.J[1] * row.J[1]; v[7] = row.J[1] * row.J[2]; v[8] = row.J[1] * row.J[3];
+                v[9] = row.J[1] * row.J[4]; v[10] = row.J[1] * row.J[5];
+                v[11] = row.J[2] * row.J[2]; v[12] = row.J[2] * row.J[3]; v[13] = row.J[2] * row.J[4];
+                v[14] = row.J[2] * row.J[5];
+                v[15] = row.J[3] * row.J[3]; v[16] = row.J[3] * row.J[4]; v[17] = row.J[3] * row.J[5];
+                v[18] = row.J[4] * row.J[4]; v[19] = row.J[4] * row.J[5];
+                v[20] = row.J[5] * row.J[5];
+                v[21] = row.J[0] * h; v[22] = row.J[1] * h; v[23] = row.J[2] * h;
+                v[24] = row.J[3] * h; v[25] = row.J[4] * h; v[26] = row.J[5] * h;
+                v[27] = row.distance * row.distance;                                                          // :104
+                v[28] = 1.0;
+            }
+            if (DEBUG) {
+                if (A.dbg_plane) {
+                    double* d = A.dbg_plane + 16 * k;
+                    d[0] = bx; d[1] = by; d[2] = bz; d[3] = row.nx; d[4] = row.ny; d[5] = row.nz;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) d[6 + i] = row.accepted ? row.J[i] : 0.0;
+                    d[12] = row.offset; d[13] = row.distance; d[14] = row.weight; d[15] = row.a2D;
+                }
+                // neighbour list in the reference's order: ascending (distance^2, visit index)
+                u64 dkey[KF];
+                unsigned did[KF];
+                int ns = 0;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    if (((mask >> j) & 1u) && ns < KF) {
+                        dkey[ns] = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
+                        did[ns] = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                        ++ns;
+                    }
+                }
+                for (int a = 1; a < KF; ++a) {
+                    const u64 kd = dkey[a]; const unsigned ki = did[a];
+                    int b = a - 1;
+                    while (b >= 0 && (dkey[b] > kd || (dkey[b] == kd && did[b] > ki))) { dkey[b + 1] = dkey[b]; did[b + 1] = did[b]; --b; }
+                    dkey[b + 1] = kd; did[b + 1] = ki;
+                }
+                for (int j = 0; j < KF; ++j) {
+                    const int vis = (int)(did[j] >> 5), i = (int)(did[j] & 31u);
+                    if (A.dbg_nbr) {
+                        short* d = A.dbg_nbr + (k * KF + j) * 4;
+                        d[0] = (short)(kx + vis / (W * W) - nb);
+                        d[1] = (short)(ky + (vis / W) % W - nb);
+                        d[2] = (short)(kz + vis % W - nb);
+                        d[3] = (short)i;
+                    }
+                    if (A.dbg_nbr_dist) A.dbg_nbr_dist[k * KF + j] = sqrt(__longlong_as_double((long long)dkey[j]));
+                }
+            }
+        }
+        if (valid && A.status && !ambiguous) A.status[k] = status;
+        __syncwarp();
+        acc += transpose_reduce32f(v, lane);
+    }
+
+    __shared__ double s_acc[kFastWarps][32];
+    __shared__ bool s_last;
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFastWarps; ++w) s += s_acc[w][lane];
+        A.partials[(size_t)blockIdx.x * 32 + lane] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(A.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fixed-order sum of the block partials, 8 loads in flight per thread
+        int b = warp;
+        for (; b + 7 * kFastWarps < (int)gridDim.x; b += 8 * kFastWarps) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) sacc[u] += __ldcg(A.partials + (size_t)(b + u * kFastWarps) * 32 + lane);
+        }
+        for (; b < (int)gridDim.x; b += kFastWarps) sacc[0] += __ldcg(A.partials + (size_t)b * 32 + lane);
+        const double s = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
+        s_acc[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < kFastWarps; ++w) tot += s_acc[w][lane];
+            if (lane == 30) { tot += (double)__ldcg(A.scan_count); *A.scan_count = 0ull; }   // k1_scan's visit count
+            A.out32[lane] = tot;
+            if (lane == 0) *A.ticket = 0u;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // sweep ordering: Morton code of the LiDAR-frame 1 m cell of every keypoint, stable radix sort -> order[]
 // (a rigid transform keeps neighbours neighbours, so the order is pose independent and computed once per sweep)
@@ -483,6 +936,33 @@ cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, 
     upload_fast_offsets(device);
     FastFn fn = debug ? pick_fast<true>() : pick_fast<false>();
     fn<<<grid, kFastThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+static int g_split_lpk = -1;
+void k1_split_set_lanes_per_keypoint(int v) { if (v == 2 || v == 4) g_split_lpk = v; }
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+// k1_scan then k1_fit on the same stream.  SRL_SPLIT_LPK=2|4 (lanes per keypoint), SRL_SCAN_MINB / SRL_FIT_MINB pick
+// the compiled register budgets.
+cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream) {
+    upload_fast_offsets(device);
+    if (g_split_lpk < 0) { const int v = env_int("SRL_SPLIT_LPK", 4); g_split_lpk = (v == 2) ? 2 : 4; }
+    static const int scan_minb = env_int("SRL_SCAN_MINB", 8), fit_minb = env_int("SRL_FIT_MINB", 5);
+    const long long kpw = 32 / g_split_lpk;
+    const long long n_groups = (n + kpw - 1) / kpw;
+    const long long grid_a = std::max<long long>(1, std::min<long long>((n_groups + 3) / 4, 1 << 20));
+    FastFn scan;
+    if (g_split_lpk == 4) scan = scan_minb == 6 ? k1_scan<4, 14, 6> : k1_scan<4, 14, 8>;
+    else scan = scan_minb == 6 ? k1_scan<2, 20, 6> : k1_scan<2, 20, 8>;
+    scan<<<(unsigned)grid_a, kScanThreads, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long long grid_b = std::max<long long>(1, std::min<long long>(((n + 31) / 32 + kFastWarps - 1) / kFastWarps, max_grid));
+    FastFn fit;
+    if (debug) fit = k1_fit<true, 4>;
+    else fit = fit_minb == 6 ? k1_fit<false, 6> : (fit_minb == 4 ? k1_fit<false, 4> : k1_fit<false, 5>);
+    fit<<<(unsigned)grid_b, kFastThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -75,9 +75,17 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     double* dbg_plane;
     unsigned long long* stats;  // [1] += ambiguous keypoints
     int force_amb_mod;          // test knob: > 0 flags every keypoint whose index is a multiple of it
+    // split form (k1_scan -> k1_fit): per sorted position, the NS boundary-inclusive candidates of the keypoint
+    unsigned* cand_rows;        // one 128-byte row per sorted position: 24 x u32 (block * 20 + index in block), 24 x u8
+                                // offset-table id, byte 120 = verdict (0: < K candidates, 1..NS: candidates inside the
+                                // window, 255: ambiguous)
+    unsigned long long* scan_count;   // candidates visited by k1_scan, folded into component 30 by k1_fit's last block
 };
 
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
+constexpr int kSplitSlots = 23;   // = NS of srl_fast.cu: candidate slots k1_scan hands to k1_fit per keypoint
+cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream);
+void k1_split_set_lanes_per_keypoint(int v);
 int k1_fast_max_blocks_per_sm();
 void k1_fast_set_min_blocks(int v);
 void k1_fast_set_lanes_per_keypoint(int v);
@@ -123,7 +131,8 @@ struct srl_ctx {
     double* d_fast_out = nullptr;            // k1_fast's 32 sums, added by the exact-fallback launch
     bool force_exact = false;
     int force_amb_mod = 0;                   // test knob for the k1_fast -> k1_assoc hand-over
-    int variant = 0;                         // 0 auto (k1_fast + exact fallback when applicable), 2 = k1_assoc only
+    int variant = 0;                         // 0 auto, 1 = k1_fast, 2 = k1_assoc only, 3 = k1_scan + k1_fit (1 and 3 with the exact fallback)
+    unsigned long long* d_scan_count = nullptr;
     // generic scratch (map insert)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -162,6 +171,7 @@ struct srl_sweep {
     unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
     bool order_valid = false;
     unsigned char* d_flags = nullptr;   // capacity
+    unsigned* d_cand_rows = nullptr;    // split form: 32 words per keypoint (k1_scan -> k1_fit)
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
     int* d_status = nullptr;        // capacity, lazily allocated
     // debug buffers, lazily allocated

@@ -202,6 +202,48 @@ def test_fast_kernel_hands_ambiguous_keypoints_to_the_exact_kernel(L, small_worl
     assert _close(g7.HTH, g.HTH) and g7.num_residuals == g.num_residuals
 
 
+@pytest.mark.parametrize("split_lpk", [4, 2])
+def test_split_scan_fit_form_matches_oracle(L, small_world, cfg1_world, split_lpk):
+    """k1_scan (2 or 4 lanes per keypoint, short per-lane lists, merge) + k1_fit: same neighbour lists, same sums, and
+    the same hand-over of uncertified keypoints to the exact kernel."""
+    from sr_livo_b200 import lio
+    prm, oprm = lio.r3live_params(max_num_residuals=BIG), O.r3live_params(max_num_residuals=BIG)
+    L.ctx.set_option("k1_variant", 3)
+    L.ctx.set_option("split_lanes_per_keypoint", split_lpk)
+    try:
+        for world, n in ((small_world, None), (cfg1_world, 20000)):
+            om, sw = _load_world(L, world)
+            raw = sw.raw_xyz if n is None else sw.raw_xyz[:n]
+            L.setKeypoints(raw)
+            o = om.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, oprm, nthreads=8, debug=True)
+            a0 = L.ctx.counter("fast_ambiguous")
+            g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+            a1 = L.ctx.counter("fast_ambiguous")
+            _assert_pass_equal(g, o)
+            assert a1 - a0 <= 0.01 * raw.shape[0]
+            g2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+            g3 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+            assert g2.num_residuals == o.num_residuals and _close(g2.HTH, o.HTH) and _close(g2.HTh, o.HTh)
+            assert np.array_equal(g2.HTH, g3.HTH) and np.array_equal(g2.HTh, g3.HTh)     # run-to-run deterministic
+            assert 0 < g2.num_candidates_scanned <= o.sum_candidates
+            L.ctx.set_option("fast_force_ambiguous_mod", 5)
+            try:
+                g5 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+            finally:
+                L.ctx.set_option("fast_force_ambiguous_mod", 0)
+            _assert_pass_equal(g5, o)
+            assert L.ctx.counter("fast_ambiguous") - a1 >= int((o.num_candidates[::5] >= 20).sum())
+        # ragged tail / tiny sweeps
+        om, sw = _load_world(L, small_world)
+        for n in (1, 7, 33, 1001):
+            L.setKeypoints(sw.raw_xyz[:n])
+            o = om.build_plane_residuals(sw.raw_xyz[:n], sw.q_init, sw.t_init, sw.t_last, oprm, debug=True)
+            _assert_pass_equal(L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True), o)
+    finally:
+        L.ctx.set_option("k1_variant", 0)
+        L.ctx.set_option("split_lanes_per_keypoint", 4)
+
+
 @pytest.mark.parametrize("lpk", [1, 2, 4])
 def test_fast_kernel_lanes_per_keypoint_variants(L, small_world, lpk):
     """k1_fast deals a keypoint's candidates to 1, 2 or 4 lanes and merges their top lists: same answer every way."""
