@@ -150,7 +150,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.force_amb_mod = ctx->force_amb_mod;
         const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
         if (split) {
-            if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)32)) != SRL_OK) return rc;
+            if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
             SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
             ctx->launches += 1;

@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
 constexpr int kScanThreads = 128;
 constexpr unsigned KINF = 0xffffffffu;
 constexpr int kZone0 = 12;     // k1_fit resolves the K-th boundary among slots >= kZone0 (k1_scan flags anything wider)
+constexpr int kRowWords = 24;  // candidate row of a keypoint: NS point ids + header word
 constexpr int kBestMax = 4;    // ... and the nearest neighbour among the first kBestMax slots
 static_assert(NS == kSplitSlots, "srl_internal.h: kSplitSlots must equal NS");
 
@@ -442,7 +443,9 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
     const int warp = threadIdx.x >> 5;
     const int sub = lane % LPK;
     const int kp = threadIdx.x / LPK;
-    const unsigned gmask = ((1u << LPK) - 1u) << (lane & ~(LPK - 1));
+    const int gshift = lane & ~(LPK - 1);          // first lane of my group
+    // (all warp-level primitives below run with the full mask at warp-uniform points: a per-group member mask would make
+    //  the compiler serialise them over the 32 / LPK distinct masks)
     const PassConst& c = A.c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
                     total += (int)cn;
                 }
             }
-            const unsigned present = (__ballot_sync(gmask, e_out != 0u) >> (lane & ~(LPK - 1))) & ((1u << LPK) - 1u);
+            const unsigned present = (__ballot_sync(FULLM, e_out != 0u) >> gshift) & ((1u << LPK) - 1u);
             if (e_out != 0u) {
                 const int pos = n_e + __popc(present & ((1u << sub) - 1u));
                 s_ent[kp][pos] = e_out;
@@ -513,24 +516,27 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
             n_e += __popc(present);
         }
 #pragma unroll
-        for (int d = 1; d < LPK; d <<= 1) total += __shfl_xor_sync(gmask, total, d);
-        __syncwarp(gmask);
+        for (int d = 1; d < LPK; d <<= 1) total += __shfl_xor_sync(FULLM, total, d);
+        __syncwarp();
         const bool full_cand = in_range && total >= c.Kmin;   // else src/optimize.cpp:78 skips the keypoint
 
         // ---- scan: this lane's share of every voxel's candidates through its own NLS-entry sorted list
         unsigned lst[NLS];
 #pragma unroll
         for (int j = 0; j < NLS; ++j) lst[j] = KINF;
-        if (full_cand) {
-            for (int e = 0; e < n_e; ++e) {
-                const unsigned ent = s_ent[kp][e];
-                const int cnt = (int)(ent & 31u);
-                const unsigned lbo = s_lb[kp][e];
-                unsigned tq = lst[Q - 1];
+        int ne_max = full_cand ? n_e : 0;
 #pragma unroll
-                for (int d = 1; d < LPK; d <<= 1) tq = max(tq, __shfl_xor_sync(gmask, tq, d));
-                const float T = key_value(tq);
-                if (__uint_as_float(lbo & ~127u) > T + T * kRel + 3.f * eps_abs) continue;   // voxel cannot matter any more
+        for (int d = 16; d >= 1; d >>= 1) ne_max = max(ne_max, __shfl_xor_sync(FULLM, ne_max, d));
+        for (int e = 0; e < ne_max; ++e) {   // warp-uniform trip count; a group is active while it has voxels left
+            const bool active = full_cand && e < n_e;
+            const unsigned ent = active ? s_ent[kp][e] : 0u;
+            const int cnt = (int)(ent & 31u);
+            const unsigned lbo = active ? s_lb[kp][e] : 0u;
+            unsigned tq = lst[Q - 1];
+#pragma unroll
+            for (int d = 1; d < LPK; d <<= 1) tq = max(tq, __shfl_xor_sync(FULLM, tq, d));
+            const float T = key_value(tq);
+            if (active && !(__uint_as_float(lbo & ~127u) > T + T * kRel + 3.f * eps_abs)) {   // else: the voxel cannot matter any more
                 const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent >> 5) * kBlockFloats);
                 if (sub == 0) scanned += (unsigned)cnt;
                 for (int i = sub; i < cnt; i += LPK) {
@@ -543,6 +549,7 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
                     lst[0] = min(lst[0], key);
                 }
             }
+            __syncwarp();
         }
 
         // ---- merge the lanes' lists (every lane ends up with the group's sorted best 32)
@@ -550,9 +557,8 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
 #pragma unroll
         for (int j = 0; j < 32; ++j) l32[j] = (j < NLS) ? lst[j] : KINF;
         const unsigned own_last = lst[NLS - 1];
-        __syncwarp(gmask);
-        merge_with_partner<NLS>(l32, gmask, 1);
-        if (LPK == 4) merge_with_partner<(2 * NLS < NL ? 2 * NLS : NL)>(l32, gmask, 2);
+        merge_with_partner<NLS>(l32, FULLM, 1);
+        if (LPK == 4) merge_with_partner<(2 * NLS < NL ? 2 * NLS : NL)>(l32, FULLM, 2);
 
         // ---- verdict (k1_fast's) + the lane certificate: what a lane dropped is not below its last tracked key
         //      j0 = leading slots that are certainly among the K nearest (even their upper bound is below the (K+1)-th
@@ -575,14 +581,13 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
             ambiguous = !(key_value(l32[NS]) > lim) || !(key_value(own_last) > lim) ||
                         (m > KF && j0 < kZone0) || b1 > kBestMax || b1 > j0;
         }
-        ambiguous = __any_sync(gmask, ambiguous);
+        ambiguous = ((__ballot_sync(FULLM, ambiguous) >> gshift) & ((1u << LPK) - 1u)) != 0u;
         if (full_cand && A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob
         if (valid) {
-            // one 128-byte row per sorted position: 24 x u32 (block * 20 + index), 24 x u8 offset id, verdict byte
-            unsigned* row = A.cand_rows + (size_t)s * 32;
-            unsigned char* rowb = reinterpret_cast<unsigned char*>(row);
+            // one 96-byte row per sorted position: 23 x u32 (block * 20 + index in block) + header word
+            unsigned* row = A.cand_rows + (size_t)s * kRowWords;
             if (sub == 0) {
-                row[30] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
+                row[NS] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
                 if (ambiguous) { A.flags[k] = 1; if (A.stats) atomicAdd(A.stats + 1, 1ull); }
             }
             if (full_cand && !ambiguous) {
@@ -590,14 +595,12 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
                 for (int j = 0; j < NS; ++j) {
                     if ((j % LPK) == sub && j < m) {
                         const unsigned key = l32[j];
-                        const unsigned e = (key >> 5) & 31u, i = key & 31u;
-                        row[j] = (s_ent[kp][e] >> 5) * (unsigned)kBlockCap + i;
-                        rowb[96 + j] = (unsigned char)(s_lb[kp][e] & 127u);
+                        row[j] = (s_ent[kp][(key >> 5) & 31u] >> 5) * (unsigned)kBlockCap + (key & 31u);
                     }
                 }
             }
         }
-        __syncwarp(gmask);   // the group's shared-memory rows are rewritten by the next group
+        __syncwarp();   // the group's shared-memory rows are rewritten by the next group
     }
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) scanned += __shfl_xor_sync(FULLM, scanned, sft);
@@ -622,10 +625,16 @@ __device__ __forceinline__ u64 exact_d2_bits(const float* blocks, unsigned cp, d
     const double dx = SRL_SUB((double)mp.x, pwx), dy = SRL_SUB((double)mp.y, pwy), dz = SRL_SUB((double)mp.z, pwz);
     return (u64)__double_as_longlong(SRL_ADD(SRL_MUL(dx, dx), SRL_ADD(SRL_MUL(dy, dy), SRL_MUL(dz, dz))));
 }
-// (visit index of the voxel in the reference's loop order) << 5 | index in block: breaks exact distance ties
-__device__ __forceinline__ unsigned visit_id(unsigned cp, unsigned o, int nb, int W) {
-    const int vis = ((c_off_fast[4 * o] + nb) * W + (c_off_fast[4 * o + 1] + nb)) * W + (c_off_fast[4 * o + 2] + nb);
-    return ((unsigned)vis << 5) | (cp % (unsigned)kBlockCap);
+// (visit index of the point's voxel in the reference's loop order) << 5 | index in block: breaks exact distance ties.
+// The voxel comes from the key kept in the block's spare w lanes (srl_device.cuh); only rare paths need it.
+__device__ __forceinline__ unsigned visit_id(const float* blocks, unsigned cp, double pwx, double pwy, double pwz, double size, int nb, int W) {
+    const unsigned blk = cp / (unsigned)kBlockCap;
+    const unsigned* meta = reinterpret_cast<const unsigned*>(blocks + (size_t)blk * kBlockFloats);
+    short vx, vy, vz;
+    unpack_key((unsigned long long)__ldg(meta + kMetaKeyLo) | ((unsigned long long)__ldg(meta + kMetaKeyHi) << 32), vx, vy, vz);
+    const int kx = (int)SRL_DIV(pwx, size), ky = (int)SRL_DIV(pwy, size), kz = (int)SRL_DIV(pwz, size);   // src/optimize.cpp:372-374
+    const int vis = (((int)vx - kx + nb) * W + ((int)vy - ky + nb)) * W + ((int)vz - kz + nb);
+    return ((unsigned)vis << 5) | (cp - blk * (unsigned)kBlockCap);
 }
 
 template <bool DEBUG, int MINB>
@@ -645,22 +654,18 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
         const long long s = A.s_begin + g * 32 + lane;
         const bool valid = s < A.s_end;
         const long long k = valid ? (long long)(A.order ? A.order[s] : (unsigned)s) : 0;
-        unsigned cp[24], visw[6], head = 0;
+        unsigned cp[24];
 #pragma unroll
         for (int q = 0; q < 24; ++q) cp[q] = 0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) visw[q] = 0;
-        if (valid) {   // the keypoint's row, written by k1_scan just before: L2, all 8 loads in flight
-            const uint4* rp = reinterpret_cast<const uint4*>(A.cand_rows + (size_t)s * 32);
+        if (valid) {   // the keypoint's row, written by k1_scan just before: L2, all 6 loads in flight
+            const uint4* rp = reinterpret_cast<const uint4*>(A.cand_rows + (size_t)s * kRowWords);
 #pragma unroll
             for (int q = 0; q < 6; ++q) {
                 const uint4 w = __ldcg(rp + q);
                 cp[4 * q] = w.x; cp[4 * q + 1] = w.y; cp[4 * q + 2] = w.z; cp[4 * q + 3] = w.w;
             }
-            const uint4 w6 = __ldcg(rp + 6), w7 = __ldcg(rp + 7);
-            visw[0] = w6.x; visw[1] = w6.y; visw[2] = w6.z; visw[3] = w6.w; visw[4] = w7.x; visw[5] = w7.y;
-            head = w7.z;
         }
+        const unsigned head = cp[NS];
         const int vd = (int)(head & 255u);
         const bool ambiguous = vd == 255;
         const bool do_fit = vd >= KF && vd <= NS;
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
                     zk[j - kZone0] = 0ull; zi[j - kZone0] = 0u;
                     if (j >= j0 && j < m) {
                         zk[j - kZone0] = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
-                        zi[j - kZone0] = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                        zi[j - kZone0] = visit_id(A.blocks, cp[j], pwx, pwy, pwz, c.size, nb, W);
                     }
                 }
                 for (int drop = m - KF; drop > 0; --drop) {
@@ -721,7 +726,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
                 for (int j = 0; j < kBestMax; ++j) {
                     if (j < b1) {
                         const u64 d = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
-                        const unsigned id = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                        const unsigned id = visit_id(A.blocks, cp[j], pwx, pwy, pwz, c.size, nb, W);
                         if (d < best || (d == best && id < best_id)) { best = d; best_id = id; best_cp = cp[j]; }
                     }
                 }
@@ -765,7 +770,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
                 for (int j = 0; j < NS; ++j) {
                     if (((mask >> j) & 1u) && ns < KF) {
                         dkey[ns] = exact_d2_bits(A.blocks, cp[j], pwx, pwy, pwz);
-                        did[ns] = visit_id(cp[j], (visw[j >> 2] >> (8 * (j & 3))) & 255u, nb, W);
+                        did[ns] = visit_id(A.blocks, cp[j], pwx, pwy, pwz, c.size, nb, W);
                         ++ns;
                     }
                 }

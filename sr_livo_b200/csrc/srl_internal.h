@@ -76,9 +76,9 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     unsigned long long* stats;  // [1] += ambiguous keypoints
     int force_amb_mod;          // test knob: > 0 flags every keypoint whose index is a multiple of it
     // split form (k1_scan -> k1_fit): per sorted position, the NS boundary-inclusive candidates of the keypoint
-    unsigned* cand_rows;        // one 128-byte row per sorted position: 24 x u32 (block * 20 + index in block), 24 x u8
-                                // offset-table id, byte 120 = verdict (0: < K candidates, 1..NS: candidates inside the
-                                // window, 255: ambiguous)
+    unsigned* cand_rows;        // one 96-byte row per sorted position: 23 x u32 (block * 20 + index in block) + header word
+                                // (byte 0: 0 = < K candidates, K..NS = candidates inside the window, 255 = ambiguous;
+                                //  byte 1: slots certainly among the K nearest; byte 2: slots that can be the nearest)
     unsigned long long* scan_count;   // candidates visited by k1_scan, folded into component 30 by k1_fit's last block
 };
 
@@ -171,7 +171,7 @@ struct srl_sweep {
     unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
     bool order_valid = false;
     unsigned char* d_flags = nullptr;   // capacity
-    unsigned* d_cand_rows = nullptr;    // split form: 32 words per keypoint (k1_scan -> k1_fit)
+    unsigned* d_cand_rows = nullptr;    // split form: 24 words per keypoint (k1_scan -> k1_fit)
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)
     int* d_status = nullptr;        // capacity, lazily allocated
     // debug buffers, lazily allocated
