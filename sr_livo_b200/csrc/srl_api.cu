@@ -95,7 +95,7 @@ static void unpack32(const double* o, srl_normal_eq* out, long long n_keypoints)
     out->reserved = 0;
 }
 
-constexpr bool kDefaultSplit = false;   // variant 0 (auto): k1_fast unless the split form measures faster (profiles/README.md)
+constexpr bool kDefaultSplit = true;    // variant 0 (auto): k1_scan + k1_fit (1.27x faster than k1_fast on the 100k-point sweep, profiles/README.md)
 
 static int pass_grid(srl_ctx* ctx, long long n, int K, int nb) {
     const long long n_groups = (n + 31) / 32;
@@ -140,7 +140,6 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
             sw->order_valid = true;
             ctx->launches += 1;
         }
-        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
         FastArgs f;
         std::memset(&f, 0, sizeof(f));
         f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
@@ -149,6 +148,8 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
         const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
+        // k1_scan writes the flag of every keypoint of its range; otherwise (k1_fast, or a shard of the sweep) clear them
+        if (!(split && a.k_begin == 0 && a.k_end == (long long)sw->n)) SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
         if (split) {
             if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;

@@ -257,6 +257,34 @@ __device__ __forceinline__ void select_exact(const float* __restrict__ blocks, c
     nfound = __popc(__ballot_sync(FULL, lane < K && bd < KINF));
 }
 
+// Fused exchange over NVLink peer memory (one warp): publish this rank's 32 sums into every rank's mailbox, wait for the
+// others' sums of the same pass, add all of them in rank order (bitwise identical everywhere).  NaN marks a failed exchange.
+__device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, int lane) {
+    const int par = (int)(cm.seq & 1ull);
+    for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
+    __threadfence_system();
+    __syncwarp();
+    if (lane < cm.world) {
+        volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
+        *f = cm.seq;
+    }
+    __threadfence_system();
+    bool ok = true;
+    if (lane < cm.world) {
+        volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
+        long long spins = 0;
+        while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+    }
+    ok = __all_sync(FULL, ok);
+    __threadfence_system();
+    double sum = 0.0;
+    for (int r = 0; r < cm.world; ++r) {
+        const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
+        sum += *d;
+    }
+    return ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+}
+
 template <int NCH, bool DEBUG, int MINB>
 __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -280,6 +308,16 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     double acc = 0.0;                 // lane i accumulates component i of the 32-double result
     long long scanned = 0;            // warp-uniform: map points whose distance was evaluated
     unsigned fallbacks = 0;           // warp-uniform: keypoints that needed the exact selection
+
+    // fallback launch with nothing flagged in this pass (the usual case): one warp forwards the fast form's sums
+    if (A.only_flagged && A.stats && __ldcg(A.stats + 2) == 0ull) {
+        if (blockIdx.x == 0 && warp == 0) {
+            double tot = A.prev_out32 ? A.prev_out32[lane] : 0.0;
+            if (A.comm.world > 1) tot = comm_exchange(A.comm, tot, lane);
+            A.out32[lane] = tot;
+        }
+        return;
+    }
 
     const long long n = A.k_end - A.k_begin;
     const long long n_groups = (n + 31) / 32;
@@ -507,36 +545,9 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
 #pragma unroll
             for (int w = 0; w < kK1Warps; ++w) tot += s_acc[w][lane];
             if (A.prev_out32) tot += A.prev_out32[lane];   // fallback launch: add k1_fast's sums (fixed order)
-            if (A.comm.world > 1) {
-                // ---- fused exchange over NVLink peer memory: publish this rank's 32 sums into every rank's mailbox, wait
-                //      for the others' sums of the same pass, add all of them in rank order (bitwise identical everywhere)
-                const CommDev& cm = A.comm;
-                const int par = (int)(cm.seq & 1ull);
-                for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
-                __threadfence_system();
-                __syncwarp();
-                if (lane < cm.world) {
-                    volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
-                    *f = cm.seq;
-                }
-                __threadfence_system();
-                bool ok = true;
-                if (lane < cm.world) {
-                    volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
-                    long long spins = 0;
-                    while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
-                }
-                ok = __all_sync(FULL, ok);
-                __threadfence_system();
-                double sum = 0.0;
-                for (int r = 0; r < cm.world; ++r) {
-                    const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
-                    sum += *d;
-                }
-                tot = ok ? sum : __longlong_as_double(0x7ff8000000000000ll);   // NaN marks a failed exchange
-            }
+            if (A.comm.world > 1) tot = comm_exchange(A.comm, tot, lane);
             A.out32[lane] = tot;
-            if (lane == 0) *A.ticket = 0u;
+            if (lane == 0) { *A.ticket = 0u; if (A.only_flagged && A.stats) A.stats[2] = 0ull; }
         }
     }
 }

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
             }
         }
         if (valid && leader && A.status && !ambiguous) A.status[k] = status;
-        if (ambiguous && A.stats) atomicAdd(A.stats + 1, 1ull);
+        if (ambiguous && A.stats) { atomicAdd(A.stats + 1, 1ull); atomicAdd(A.stats + 2, 1ull); }
         __syncwarp();
         acc += transpose_reduce32f(v, lane);
     }
@@ -588,7 +588,8 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
             unsigned* row = A.cand_rows + (size_t)s * kRowWords;
             if (sub == 0) {
                 row[NS] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
-                if (ambiguous) { A.flags[k] = 1; if (A.stats) atomicAdd(A.stats + 1, 1ull); }
+                A.flags[k] = ambiguous ? 1 : 0;   // every keypoint of the range: no separate clear of the flags
+                if (ambiguous && A.stats) { atomicAdd(A.stats + 1, 1ull); atomicAdd(A.stats + 2, 1ull); }
             }
             if (full_cand && !ambiguous) {
 #pragma unroll
@@ -953,7 +954,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream) {
     upload_fast_offsets(device);
     if (g_split_lpk < 0) { const int v = env_int("SRL_SPLIT_LPK", 4); g_split_lpk = (v == 2) ? 2 : 4; }
-    static const int scan_minb = env_int("SRL_SCAN_MINB", 8), fit_minb = env_int("SRL_FIT_MINB", 5);
+    static const int scan_minb = env_int("SRL_SCAN_MINB", 8), fit_minb = env_int("SRL_FIT_MINB", 6);
     const long long kpw = 32 / g_split_lpk;
     const long long n_groups = (n + kpw - 1) / kpw;
     const long long grid_a = std::max<long long>(1, std::min<long long>((n_groups + 3) / 4, 1 << 20));
