@@ -524,19 +524,22 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
         unsigned lst[NLS];
 #pragma unroll
         for (int j = 0; j < NLS; ++j) lst[j] = KINF;
-        int ne_max = full_cand ? n_e : 0;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) ne_max = max(ne_max, __shfl_xor_sync(FULLM, ne_max, d));
-        for (int e = 0; e < ne_max; ++e) {   // warp-uniform trip count; a group is active while it has voxels left
-            const bool active = full_cand && e < n_e;
-            const unsigned ent = active ? s_ent[kp][e] : 0u;
-            const int cnt = (int)(ent & 31u);
-            const unsigned lbo = active ? s_lb[kp][e] : 0u;
+        // Every group walks its own voxel list: per step the group's bound T is refreshed, voxels that cannot matter any
+        // more are stepped over, and the next one is scanned; the warp leaves when no group has a voxel left.
+        int e = full_cand ? 0 : n_e;
+        for (;;) {
             unsigned tq = lst[Q - 1];
 #pragma unroll
             for (int d = 1; d < LPK; d <<= 1) tq = max(tq, __shfl_xor_sync(FULLM, tq, d));
             const float T = key_value(tq);
-            if (active && !(__uint_as_float(lbo & ~127u) > T + T * kRel + 3.f * eps_abs)) {   // else: the voxel cannot matter any more
+            const float Tlim = T + T * kRel + 3.f * eps_abs;
+            unsigned lbo = 0;
+            while (e < n_e && __uint_as_float((lbo = s_lb[kp][e]) & ~127u) > Tlim) ++e;
+            const bool active = e < n_e;
+            if (!__any_sync(FULLM, active)) break;
+            if (active) {
+                const unsigned ent = s_ent[kp][e];
+                const int cnt = (int)(ent & 31u);
                 const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent >> 5) * kBlockFloats);
                 if (sub == 0) scanned += (unsigned)cnt;
                 for (int i = sub; i < cnt; i += LPK) {
@@ -548,6 +551,7 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
                     for (int j = NLS - 1; j >= 1; --j) lst[j] = min(lst[j], max(lst[j - 1], key));   // stages independent of each other
                     lst[0] = min(lst[0], key);
                 }
+                ++e;
             }
             __syncwarp();
         }
