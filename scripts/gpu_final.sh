@@ -11,8 +11,10 @@ echo "== bench b200"; timeout 900 python bench.py > $OUT/bench_b200.json 2> $OUT
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "rc=$?"
-echo "== ncu full k1_fast"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1_fast -s 3 -c 3 -f -o $OUT/k1_fast_full \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_fast.log 2>&1; echo "rc=$?"
+echo "== ncu full k1_scan + k1_fit (the 3 passes of one sweep)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k1_scan|k1_fit" -s 6 -c 6 -f -o $OUT/k1_split_full \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_split.log 2>&1; echo "rc=$?"
+echo "== A/B: previous form of the pass (k1_fast)"
+timeout 300 python bench.py --no-cpu-baseline --steps 20 --k1-variant 1 > $OUT/bench_k1fast.json 2> $OUT/bench_k1fast.err; echo "rc=$?"
 echo "== config-5-sized run on one GPU: 500k-pt spinning sweep, ~50M-pt map, 5 passes"
 timeout 1500 python bench.py --points 500000 --map-extent 1340 --passes 5 --pattern spinning --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_cfg5_1gpu.json 2> $OUT/bench_cfg5_1gpu.err; echo "rc=$?"; cat $OUT/bench_cfg5_1gpu.json; tail -3 $OUT/bench_cfg5_1gpu.err
