@@ -135,11 +135,26 @@ def run_reference(args):
                              "sample": f"whole workload: {args.steps} sweeps x {N_PASSES} passes x {args.points} keypoints, "
                                        f"keypoint ranges over {cores} std::threads"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract goes to the process's real stdout; everything else a library prints to fd 1
+    during the run (e.g. NCCL's version banner) was rerouted to stderr by main()."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -381,7 +396,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         if streaming is not None:
             line["streaming"] = streaming
-        print(json.dumps(line), flush=True)
+        emit(line)
     if D is not None:
         D.close()
     if world > 1:
