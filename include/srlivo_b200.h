@@ -231,6 +231,35 @@ int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sweep, const double q[4]
 int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double size_voxel_subsampling,
                       uint32_t* keypoint_index_out, size_t* n_keypoints);
 
+/* ---- row N3: per-sweep point transforms / undistortion (src/utility.cpp:203-332) -----------------------------------
+ * One thread per point.  Every point buffer may be a host or a device pointer (detected per pointer), so a sweep can
+ * stay in HBM from undistortion through registration to map insertion.  relative_time is point3D::relative_time (ms).
+ * srl_imu_state carries the imuState fields these functions read (include/utility.h: timestamp, quat, trans, vel,
+ * un_acc, un_gyr); states[] is host memory. */
+typedef struct srl_imu_state {
+    double timestamp;
+    double quat[4];   /* x, y, z, w */
+    double trans[3];
+    double vel[3];
+    double un_acc[3];
+    double un_gyr[3];
+} srl_imu_state;
+/* distortFrameByConstant (src/utility.cpp:203-236): imu_point of every point from the pose interpolated (slerp / lerp)
+ * between states[0] and states[n_states-1] */
+int srl_distort_frame_by_constant(srl_ctx* ctx, const double* raw_xyz, const double* relative_time_ms, size_t n,
+                                  const srl_imu_state* states, size_t n_states, double time_frame_begin,
+                                  const double R_imu_lidar[9], const double t_imu_lidar[3], double* imu_xyz);
+/* distortFrameByImu (src/utility.cpp:238-312, "distortion method 1").  The reference walks points and IMU intervals
+ * with one iterator: points are consumed in order, the first point that fits no remaining interval stops the walk.
+ * imu_xyz is in/out (points never reached keep their value); *n_written = number of leading points written.
+ * timestamps must be non-decreasing (SRL_BAD_ARG otherwise). */
+int srl_distort_frame_by_imu(srl_ctx* ctx, const double* raw_xyz, const double* relative_time_ms, size_t n,
+                             const srl_imu_state* states, size_t n_states, double time_frame_begin,
+                             const double R_imu_lidar[9], const double t_imu_lidar[3], double* imu_xyz, int64_t* n_written);
+/* transformAllImuPoint (src/utility.cpp:320-332): raw_point = R_il^T (R(q_end)^-1 imu_point - R(q_end)^-1 t_end) - R_il^T t_il */
+int srl_transform_all_imu_point(srl_ctx* ctx, const double* imu_xyz, size_t n, const srl_imu_state* last_state,
+                                const double R_imu_lidar[9], const double t_imu_lidar[3], double* raw_xyz_out);
+
 /* eskfEstimator::observe (src/eskfEstimator.cpp:219-230) — host math, exported for parity tests */
 int srl_eskf_observe(srl_eskf_state* eskf, const double d_x[17]);
 

@@ -124,6 +124,14 @@ def lib(prefer_tsl: bool = True):
     L.orc_update_iekf.restype = C.c_int32
     L.orc_grid_sampling.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
     L.orc_grid_sampling.restype = C.c_int64
+    L.orc_distort_frame_by_constant.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_distort_frame_by_constant.restype = None
+    L.orc_distort_frame_by_imu.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_distort_frame_by_imu.restype = C.c_int64
+    L.orc_transform_all_imu_point.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_transform_all_imu_point.restype = None
+    L.orc_quat_slerp.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    L.orc_quat_slerp.restype = None
     L.orc_quat_to_rot.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_eig3_sym.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_eskf_observe.argtypes = [C.POINTER(EskfState), C.c_void_p]
@@ -303,6 +311,47 @@ def grid_sampling(xyz, size_voxel_subsampling: float) -> np.ndarray:
     out = np.zeros(xyz.shape[0], np.int32)
     m = lib().orc_grid_sampling(_ptr(xyz), xyz.shape[0], size_voxel_subsampling, _ptr(out))
     return out[:m].copy()
+
+
+def imu_states_array(states) -> np.ndarray:
+    """orc_imu_state[]: rows of 17 doubles (timestamp, quat xyzw, trans, vel, un_acc, un_gyr) from dicts."""
+    a = np.zeros((len(states), 17))
+    for r, s in zip(a, states):
+        r[0] = s["timestamp"]; r[1:5] = s["quat"]; r[5:8] = s["trans"]; r[8:11] = s["vel"]; r[11:14] = s["un_acc"]; r[14:17] = s["un_gyr"]
+    return a
+
+
+def distort_frame_by_constant(raw_xyz, relative_time_ms, states, time_frame_begin, R_il=None, t_il=None) -> np.ndarray:
+    """distortFrameByConstant (src/utility.cpp:203-236)."""
+    raw = _f64(raw_xyz).reshape(-1, 3); rel = _f64(relative_time_ms).reshape(-1); st = imu_states_array(states)
+    R = _f64(np.eye(3) if R_il is None else R_il).reshape(9); t = _f64(np.zeros(3) if t_il is None else t_il)
+    out = np.zeros_like(raw)
+    lib().orc_distort_frame_by_constant(_ptr(raw), _ptr(rel), raw.shape[0], _ptr(st), st.shape[0], float(time_frame_begin), _ptr(R), _ptr(t), _ptr(out))
+    return out
+
+
+def distort_frame_by_imu(raw_xyz, relative_time_ms, states, time_frame_begin, R_il=None, t_il=None, imu_xyz_in=None):
+    """distortFrameByImu (src/utility.cpp:238-312): (imu_xyz, number of leading points the iterator reached)."""
+    raw = _f64(raw_xyz).reshape(-1, 3); rel = _f64(relative_time_ms).reshape(-1); st = imu_states_array(states)
+    R = _f64(np.eye(3) if R_il is None else R_il).reshape(9); t = _f64(np.zeros(3) if t_il is None else t_il)
+    out = np.zeros_like(raw) if imu_xyz_in is None else _f64(imu_xyz_in).reshape(-1, 3).copy()
+    m = lib().orc_distort_frame_by_imu(_ptr(raw), _ptr(rel), raw.shape[0], _ptr(st), st.shape[0], float(time_frame_begin), _ptr(R), _ptr(t), _ptr(out))
+    return out, int(m)
+
+
+def transform_all_imu_point(imu_xyz, last_state, R_il=None, t_il=None) -> np.ndarray:
+    """transformAllImuPoint (src/utility.cpp:320-332)."""
+    imu = _f64(imu_xyz).reshape(-1, 3); st = imu_states_array([last_state])
+    R = _f64(np.eye(3) if R_il is None else R_il).reshape(9); t = _f64(np.zeros(3) if t_il is None else t_il)
+    out = np.zeros_like(imu)
+    lib().orc_transform_all_imu_point(_ptr(imu), imu.shape[0], _ptr(st), _ptr(R), _ptr(t), _ptr(out))
+    return out
+
+
+def quat_slerp(a, t, b) -> np.ndarray:
+    a = _f64(a); b = _f64(b); out = np.zeros(4)
+    lib().orc_quat_slerp(_ptr(a), float(t), _ptr(b), _ptr(out))
+    return out
 
 
 def quat_to_rot(q) -> np.ndarray:

@@ -1166,6 +1166,107 @@ int64_t orc_grid_sampling(const double* xyz, int64_t n, double size_voxel, int32
     return m;
 }
 
+// ---- row N3: per-sweep point transforms / undistortion (src/utility.cpp:203-332) --------------------------------
+namespace {
+// Eigen 3.3.7 QuaternionBase::slerp (Eigen/src/Geometry/Quaternion.h): the dependency is not vendored in the reference;
+// this restates its published algorithm.  The 4-coefficient dot reduces as (x+z)+(y+w) like squaredNorm.
+inline Quat quat_slerp(const Quat& a, double t, const Quat& b) {
+    const double one = 1.0 - std::numeric_limits<double>::epsilon();
+    const double d = (a.x * b.x + a.z * b.z) + (a.y * b.y + a.w * b.w);
+    const double absD = std::fabs(d);
+    double scale0, scale1;
+    if (absD >= one) { scale0 = 1.0 - t; scale1 = t; }
+    else {
+        const double theta = std::acos(absD);
+        const double sinTheta = std::sin(theta);
+        scale0 = std::sin((1.0 - t) * theta) / sinTheta;
+        scale1 = std::sin(t * theta) / sinTheta;
+    }
+    if (d < 0) scale1 = -scale1;
+    return {scale0 * a.x + scale1 * b.x, scale0 * a.y + scale1 * b.y, scale0 * a.z + scale1 * b.z, scale0 * a.w + scale1 * b.w};
+}
+inline Vec3 v3p(const double* p) { return {{p[0], p[1], p[2]}}; }
+inline Mat3 m3p(const double* p) { Mat3 M; std::memcpy(M.m, p, sizeof(M.m)); return M; }
+}  // namespace
+
+// distortFrameByConstant (src/utility.cpp:203-236): pose interpolated between the first and last IMU state of the sweep
+void orc_distort_frame_by_constant(const double* raw_xyz, const double* relative_time, int64_t n, const orc_imu_state* st,
+                                   int64_t n_states, double time_frame_begin, const double R_il[9], const double t_il[3],
+                                   double* imu_xyz) {
+    if (n_states < 1) return;
+    const double time_frame_end = st[n_states - 1].timestamp;
+    const Quat quat_begin = {st[0].quat[0], st[0].quat[1], st[0].quat[2], st[0].quat[3]};
+    const Quat quat_end = {st[n_states - 1].quat[0], st[n_states - 1].quat[1], st[n_states - 1].quat[2], st[n_states - 1].quat[3]};
+    const Vec3 trans_begin = v3p(st[0].trans), trans_end = v3p(st[n_states - 1].trans);
+    const Mat3 R = m3p(R_il);
+    const Vec3 t = v3p(t_il);
+    for (int64_t i = 0; i < n; ++i) {
+        double time_point = time_frame_begin + relative_time[i] / 1000.0;
+        if (std::fabs(time_point - time_frame_begin) < 1e-6) time_point = time_frame_begin + 1e-6;
+        if (std::fabs(time_point - time_frame_end) < 1e-6) time_point = time_frame_end - 1e-6;
+        double alpha_time = (time_point - time_frame_begin) / (time_frame_end - time_frame_begin);
+        if (alpha_time > 1) alpha_time = 1;
+        if (alpha_time < 0) alpha_time = 0;
+        const Quat quat_alpha = quat_slerp(quat_begin, alpha_time, quat_end);
+        const Vec3 trans_alpha = vadd(vscale(trans_begin, 1.0 - alpha_time), vscale(trans_end, alpha_time));
+        const Vec3 p = vadd(matvec(quat_to_rot(quat_alpha), vadd(matvec(R, v3p(raw_xyz + 3 * i)), t)), trans_alpha);
+        imu_xyz[3 * i] = p[0]; imu_xyz[3 * i + 1] = p[1]; imu_xyz[3 * i + 2] = p[2];
+    }
+}
+
+// distortFrameByImu (src/utility.cpp:238-312, "distortion method 1"): one iterator walks the points while the outer loop
+// walks the IMU intervals; a point outside the current interval ends that interval, so points are consumed in order
+// and whatever is left when the intervals run out keeps its old imu_point.  Returns the number of points written.
+int64_t orc_distort_frame_by_imu(const double* raw_xyz, const double* relative_time, int64_t n, const orc_imu_state* st,
+                                 int64_t n_states, double time_frame_begin, const double R_il[9], const double t_il[3],
+                                 double* imu_xyz) {
+    const Mat3 R = m3p(R_il);
+    const Vec3 t = v3p(t_il);
+    int64_t iter = 0;
+    for (int64_t k = 0; k + 1 < n_states; k++) {
+        const double time_imu_begin = st[k].timestamp;
+        const Quat quat_imu = {st[k].quat[0], st[k].quat[1], st[k].quat[2], st[k].quat[3]};
+        const Vec3 trans_imu = v3p(st[k].trans), vel_imu = v3p(st[k].vel);
+        const double time_imu_end = st[k + 1].timestamp;
+        const Vec3 un_acc = v3p(st[k + 1].un_acc), un_gyr = v3p(st[k + 1].un_gyr);
+        while (iter != n) {
+            double time_point = time_frame_begin + relative_time[iter] / 1000.0;
+            if (time_point > time_imu_begin - 1e-6 && time_point < time_imu_end + 1e-6) {
+                if (std::fabs(time_point - time_imu_begin) < 1e-6) time_point = time_imu_begin + 1e-6;
+                if (std::fabs(time_point - time_imu_end) < 1e-6) time_point = time_imu_end - 1e-6;
+                const double dt = time_point - time_imu_begin;
+                const Quat quat_point = quat_normalized(quat_mul(quat_imu, so3ToQuat(vscale(un_gyr, dt))));
+                const Vec3 trans_point = vadd(vadd(trans_imu, vscale(vel_imu, dt)), vscale(vscale(vscale(un_acc, 0.5), dt), dt));
+                const Vec3 p = vadd(matvec(quat_to_rot(quat_point), vadd(matvec(R, v3p(raw_xyz + 3 * iter)), t)), trans_point);
+                imu_xyz[3 * iter] = p[0]; imu_xyz[3 * iter + 1] = p[1]; imu_xyz[3 * iter + 2] = p[2];
+                iter++;
+            } else {
+                break;
+            }
+        }
+    }
+    return iter;
+}
+
+// transformAllImuPoint (src/utility.cpp:320-332): every imu_point into the LiDAR frame at the END of the sweep
+void orc_transform_all_imu_point(const double* imu_xyz, int64_t n, const orc_imu_state* last, const double R_il[9],
+                                 const double t_il[3], double* raw_out) {
+    const Quat quat_end_inv = quat_inverse({last->quat[0], last->quat[1], last->quat[2], last->quat[3]});
+    const Mat3 Rinv = quat_to_rot(quat_end_inv);
+    const Vec3 trans_end_inv = vscale(matvec(Rinv, v3p(last->trans)), -1.0);
+    const Mat3 Rt = transpose(m3p(R_il));
+    const Vec3 off = matvec(Rt, v3p(t_il));
+    for (int64_t i = 0; i < n; ++i) {
+        const Vec3 p = vsub(matvec(Rt, vadd(matvec(Rinv, v3p(imu_xyz + 3 * i)), trans_end_inv)), off);
+        raw_out[3 * i] = p[0]; raw_out[3 * i + 1] = p[1]; raw_out[3 * i + 2] = p[2];
+    }
+}
+
+void orc_quat_slerp(const double a[4], double t, const double b[4], double out[4]) {
+    const Quat q = quat_slerp({a[0], a[1], a[2], a[3]}, t, {b[0], b[1], b[2], b[3]});
+    out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+}
+
 void orc_quat_to_rot(const double q[4], double R[9]) {
     Mat3 M = quat_to_rot({q[0], q[1], q[2], q[3]});
     std::memcpy(R, M.m, sizeof(M.m));

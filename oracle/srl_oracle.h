@@ -120,6 +120,30 @@ int32_t orc_update_iekf(void* map, const double* raw_xyz, int64_t n, orc_eskf_st
  * iteration order of its std::tr1::unordered_map grid). out has capacity n; returns the number of keypoints */
 int64_t orc_grid_sampling(const double* xyz, int64_t n, double size_voxel_subsampling, int32_t* out);
 
+/* row N3 — per-sweep point transforms / undistortion (src/utility.cpp:203-332).  imuState fields the functions read
+ * (include/utility.h imuState: timestamp, quat, trans, vel, un_acc, un_gyr) */
+typedef struct orc_imu_state {
+    double timestamp;
+    double quat[4];   /* x, y, z, w */
+    double trans[3];
+    double vel[3];
+    double un_acc[3];
+    double un_gyr[3];
+} orc_imu_state;
+/* distortFrameByConstant (:203-236); relative_time in ms as point3D::relative_time */
+void orc_distort_frame_by_constant(const double* raw_xyz, const double* relative_time, int64_t n, const orc_imu_state* st,
+                                   int64_t n_states, double time_frame_begin, const double R_il[9], const double t_il[3],
+                                   double* imu_xyz);
+/* distortFrameByImu (:238-312, method 1); imu_xyz is in/out (points the iterator never reaches keep their value);
+ * returns how many leading points were written */
+int64_t orc_distort_frame_by_imu(const double* raw_xyz, const double* relative_time, int64_t n, const orc_imu_state* st,
+                                 int64_t n_states, double time_frame_begin, const double R_il[9], const double t_il[3],
+                                 double* imu_xyz);
+/* transformAllImuPoint (:320-332) */
+void orc_transform_all_imu_point(const double* imu_xyz, int64_t n, const orc_imu_state* last, const double R_il[9],
+                                 const double t_il[3], double* raw_out);
+void orc_quat_slerp(const double a[4], double t, const double b[4], double out[4]);   /* Eigen slerp */
+
 /* small pieces exported for self-checks */
 void orc_quat_to_rot(const double q[4], double R[9]);                 /* Eigen toRotationMatrix */
 void orc_eig3_sym(const double S[9], double evals[3], double evecs[9]); /* SelfAdjointEigenSolver<Matrix3d> */

@@ -58,6 +58,12 @@ class IekfSummary(C.Structure):
                 ("converged", C.c_int32), ("trace", (C.c_double * 24) * 32)]
 
 
+class ImuState(C.Structure):
+    """srl_imu_state: the imuState fields the point transforms read (include/utility.h)."""
+    _fields_ = [("timestamp", C.c_double), ("quat", C.c_double * 4), ("trans", C.c_double * 3), ("vel", C.c_double * 3),
+                ("un_acc", C.c_double * 3), ("un_gyr", C.c_double * 3)]
+
+
 class IekfIter(C.Structure):
     _fields_ = [("predict", EskfState), ("pass_index", C.c_int32), ("max_num_iter", C.c_int32)]
 
@@ -72,6 +78,7 @@ EXPORTS = [
     "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_comm_create", "srl_comm_destroy", "srl_comm_export", "srl_comm_connect",
     "srl_update_iekf_dist", "srl_optimize_host", "srl_sweep_transform_device",
     "srl_grid_sampling", "srl_eskf_observe", "srl_host_plane_fit",
+    "srl_distort_frame_by_constant", "srl_distort_frame_by_imu", "srl_transform_all_imu_point",
 ]
 
 _lib = None
@@ -138,6 +145,9 @@ def lib():
     L.srl_sweep_transform_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.srl_grid_sampling.argtypes = [vp, vp, sz, dbl, vp, C.POINTER(sz)]
     L.srl_eskf_observe.argtypes = [C.POINTER(EskfState), vp]
+    L.srl_distort_frame_by_constant.argtypes = [vp, vp, vp, sz, vp, sz, dbl, vp, vp, vp]
+    L.srl_distort_frame_by_imu.argtypes = [vp, vp, vp, sz, vp, sz, dbl, vp, vp, vp, C.POINTER(i64)]
+    L.srl_transform_all_imu_point.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.srl_host_plane_fit.argtypes = [vp, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

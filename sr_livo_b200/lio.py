@@ -287,6 +287,50 @@ class LioOptimization:
         _check(self.ctx.h, lib().srl_grid_sampling(self.ctx.h, ptr(xyz), xyz.shape[0], size_voxel_subsampling, ptr(out), C.byref(m)))
         return out[:m.value].copy()
 
+    # ---- src/utility.cpp:203-332 (row N3): undistortion and the sweep-end re-expression
+    @staticmethod
+    def _imu_states(states):
+        """states: sequence of dicts / objects with timestamp, quat (x,y,z,w), trans, vel, un_acc, un_gyr."""
+        from .capi import ImuState
+        arr = (ImuState * len(states))()
+        for a, s_ in zip(arr, states):
+            g = (lambda k: s_[k]) if isinstance(s_, dict) else (lambda k: getattr(s_, k))
+            a.timestamp = float(g("timestamp"))
+            for name, m in (("quat", 4), ("trans", 3), ("vel", 3), ("un_acc", 3), ("un_gyr", 3)):
+                v = np.asarray(g(name), np.float64).reshape(m)
+                getattr(a, name)[:] = v.tolist()
+        return arr
+
+    def distortFrameByConstant(self, raw_xyz, relative_time_ms, imu_states, time_frame_begin: float) -> np.ndarray:
+        raw = f64(raw_xyz).reshape(-1, 3)
+        rel = f64(relative_time_ms).reshape(-1)
+        st = self._imu_states(imu_states)
+        out = np.zeros_like(raw)
+        R, t = f64(self.R_imu_lidar).reshape(9), f64(self.t_imu_lidar)
+        _check(self.ctx.h, lib().srl_distort_frame_by_constant(self.ctx.h, ptr(raw), ptr(rel), raw.shape[0], C.cast(st, C.c_void_p),
+                                                               len(imu_states), float(time_frame_begin), ptr(R), ptr(t), ptr(out)))
+        return out
+
+    def distortFrameByImu(self, raw_xyz, relative_time_ms, imu_states, time_frame_begin: float, imu_xyz_in=None):
+        """Returns (imu_xyz, n_written); imu_xyz_in supplies the values kept by points the reference's walk never reaches."""
+        raw = f64(raw_xyz).reshape(-1, 3)
+        rel = f64(relative_time_ms).reshape(-1)
+        st = self._imu_states(imu_states)
+        out = np.zeros_like(raw) if imu_xyz_in is None else f64(imu_xyz_in).reshape(-1, 3).copy()
+        nw = C.c_int64(0)
+        R, t = f64(self.R_imu_lidar).reshape(9), f64(self.t_imu_lidar)
+        _check(self.ctx.h, lib().srl_distort_frame_by_imu(self.ctx.h, ptr(raw), ptr(rel), raw.shape[0], C.cast(st, C.c_void_p),
+                                                          len(imu_states), float(time_frame_begin), ptr(R), ptr(t), ptr(out), C.byref(nw)))
+        return out, int(nw.value)
+
+    def transformAllImuPoint(self, imu_xyz, last_imu_state) -> np.ndarray:
+        imu = f64(imu_xyz).reshape(-1, 3)
+        st = self._imu_states([last_imu_state])
+        out = np.zeros_like(imu)
+        R, t = f64(self.R_imu_lidar).reshape(9), f64(self.t_imu_lidar)
+        _check(self.ctx.h, lib().srl_transform_all_imu_point(self.ctx.h, ptr(imu), imu.shape[0], C.cast(st, C.c_void_p), ptr(R), ptr(t), ptr(out)))
+        return out
+
     def setKeypoints(self, raw_xyz):
         """std::vector<point3D> keypoints (raw_point members), uploaded once per sweep."""
         self.sweep.upload(raw_xyz)

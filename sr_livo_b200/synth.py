@@ -252,3 +252,34 @@ def prior_covariance() -> np.ndarray:
     P[12:15, 12:15] *= 0.0001
     P[15:17, 15:17] *= 0.00001
     return P
+
+
+# ---- synthetic IMU track and point times for the undistortion functions (row N3) ---------------------------------
+def _quat_mul_xyzw(a, b):
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def make_imu_states(n_states=21, t0=100.0, dt=0.005, seed=3):
+    """A smooth synthetic IMU track (200 Hz over a 0.1 s sweep) with every field the functions read."""
+    rng = np.random.default_rng(seed)
+    states = []
+    q = np.array([0.02, -0.01, 0.3, 0.95]); q /= np.linalg.norm(q)
+    p = np.array([1.0, -2.0, 0.5]); v = np.array([2.0, 0.3, -0.1])
+    for k in range(n_states):
+        gyr = rng.normal(0, 0.4, 3); acc = rng.normal(0, 1.5, 3)
+        states.append(dict(timestamp=t0 + k * dt, quat=q.copy(), trans=p.copy(), vel=v.copy(), un_acc=acc, un_gyr=gyr))
+        th = np.linalg.norm(gyr * dt)
+        dq = np.r_[gyr * dt / th * np.sin(th / 2), np.cos(th / 2)] if th > 0 else np.array([0, 0, 0, 1.0])
+        q = _quat_mul_xyzw(q, dq); q /= np.linalg.norm(q)
+        p = p + v * dt + 0.5 * acc * dt * dt; v = v + acc * dt
+    return states
+
+
+def make_sweep_times(n, span_ms=100.0, seed=5):
+    rng = np.random.default_rng(seed)
+    rel = np.sort(rng.uniform(0.0, span_ms, n))
+    rel[0] = 0.0; rel[-1] = span_ms                      # exactly on the sweep's first / last IMU stamp
+    rel[n // 2] = 50.0; rel[n // 3] = 35.0 + 4e-4        # on and within 1e-6 s of interior IMU stamps
+    return np.sort(rel)

@@ -523,6 +523,71 @@ def test_grid_sampling_matches_the_reference_order(L, small_world):
     assert np.allclose(ft, ref["frame_t"], atol=1e-9) and np.allclose(fq, ref["frame_q"], atol=1e-9)
 
 
+def test_undistortion_and_sweep_end_transform_match_the_oracle(L):
+    """Row N3 (src/utility.cpp:203-332): distortFrameByConstant, distortFrameByImu (incl. its one-iterator walk) and
+    transformAllImuPoint, host buffers and device buffers, against the oracle."""
+    import torch
+    import ctypes as C
+    from sr_livo_b200 import capi
+    st = synth.make_imu_states()
+    rng = np.random.default_rng(21)
+    n = 50000
+    raw = rng.normal(0, 30, (n, 3)); rel = synth.make_sweep_times(n)
+    t0 = st[0]["timestamp"]
+    R_il, t_il = L.R_imu_lidar, L.t_imu_lidar
+    tol = dict(rtol=1e-12, atol=1e-10)                       # floating point: north_star allows 1e-5; libm differs in the last ulp
+
+    o_c = O.distort_frame_by_constant(raw, rel, st, t0, R_il, t_il)
+    g_c = L.distortFrameByConstant(raw, rel, st, t0)
+    assert np.allclose(g_c, o_c, **tol) and np.abs(g_c - o_c).max() < 1e-11
+
+    o_i, m_o = O.distort_frame_by_imu(raw, rel, st, t0, R_il, t_il)
+    g_i, m_g = L.distortFrameByImu(raw, rel, st, t0)
+    assert m_g == m_o == n and np.allclose(g_i, o_i, **tol)
+
+    # the walk stops at the first point that fits no remaining interval; the rest keep the caller's values
+    keep = np.full_like(raw, -3.0)
+    for bad_at, val in ((1234, -1.0), (30000, 10.0), (40000, 1e6), (0, -50.0)):
+        rel2 = rel.copy(); rel2[bad_at] = val
+        o2, mo = O.distort_frame_by_imu(raw, rel2, st, t0, R_il, t_il, imu_xyz_in=keep)
+        g2, mg = L.distortFrameByImu(raw, rel2, st, t0, imu_xyz_in=keep)
+        assert mg == mo == bad_at and np.allclose(g2, o2, **tol) and np.all(g2[bad_at:] == -3.0)
+    # unsorted but recoverable: a point one interval back after the walk moved on is NOT recoverable, one on the shared
+    # boundary (within 1e-6 s of an IMU stamp) is
+    ts = np.array([s_["timestamp"] for s_ in st])
+    rel3 = rel.copy(); k = n // 2
+    rel3[k] = (ts[np.searchsorted(ts, t0 + rel[k] / 1000.0) - 1] - t0) * 1000.0 + 5e-4      # just inside the lower boundary's tolerance
+    o3, mo3 = O.distort_frame_by_imu(raw, rel3, st, t0, R_il, t_il, imu_xyz_in=keep)
+    g3, mg3 = L.distortFrameByImu(raw, rel3, st, t0, imu_xyz_in=keep)
+    assert mg3 == mo3 and np.allclose(g3, o3, **tol)
+
+    o_t = O.transform_all_imu_point(o_i, st[-1], R_il, t_il)
+    g_t = L.transformAllImuPoint(g_i, st[-1])
+    assert np.allclose(g_t, o_t, **tol)
+
+    # device buffers in and out: the sweep stays in HBM
+    d_raw = torch.from_numpy(raw).cuda(); d_rel = torch.from_numpy(rel).cuda(); d_out = torch.zeros_like(d_raw); d_back = torch.zeros_like(d_raw)
+    arr = L._imu_states(st)
+    R, t = capi.f64(R_il).reshape(9), capi.f64(t_il)
+    nw = C.c_int64(0)
+    vp = C.c_void_p
+    assert capi.lib().srl_distort_frame_by_imu(L.ctx.h, vp(d_raw.data_ptr()), vp(d_rel.data_ptr()), n, C.cast(arr, vp), len(st), t0,
+                                               capi.ptr(R), capi.ptr(t), vp(d_out.data_ptr()), C.byref(nw)) == 0
+    assert nw.value == n and np.array_equal(d_out.cpu().numpy(), g_i)
+    last = L._imu_states([st[-1]])
+    assert capi.lib().srl_transform_all_imu_point(L.ctx.h, vp(d_out.data_ptr()), n, C.cast(last, vp), capi.ptr(R), capi.ptr(t), vp(d_back.data_ptr())) == 0
+    assert np.array_equal(d_back.cpu().numpy(), g_t)
+    assert capi.lib().srl_distort_frame_by_constant(L.ctx.h, vp(d_raw.data_ptr()), vp(d_rel.data_ptr()), n, C.cast(arr, vp), len(st), t0,
+                                                    capi.ptr(R), capi.ptr(t), vp(d_out.data_ptr())) == 0
+    assert np.array_equal(d_out.cpu().numpy(), g_c)
+
+    # edge cases: empty sweep, a single IMU state, decreasing stamps
+    assert L.distortFrameByImu(raw[:0], rel[:0], st, t0)[1] == 0
+    assert L.distortFrameByImu(raw[:10], rel[:10], st[:1], t0)[1] == 0
+    with pytest.raises(Exception):
+        L.distortFrameByImu(raw[:10], rel[:10], [st[1], st[0]], t0)
+
+
 def test_randomized_parity_many_sweeps_and_poses(L, cfg1_world):
     """A few hundred thousand associations over random sensor poses, sweep patterns and pose errors: every neighbour
     list must equal the oracle's (the FP32 window / guard / fallback logic has to hold on all of them, not on average)."""

@@ -321,3 +321,96 @@ def test_grid_sampling_keeps_the_first_point_of_every_cell(small_world):
     # the order is the hash container's, not the frame's (which is why it has to be reproduced, not re-invented)
     assert not np.array_equal(idx, np.sort(idx))
     assert O.grid_sampling(np.zeros((0, 3)), 1.5).size == 0
+
+
+# ---- row N3: undistortion / point transforms (src/utility.cpp:203-332) -------------------------------------------
+def _np_quat_to_rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _np_quat_mul(a, b):
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+make_imu_states, make_sweep_times = synth.make_imu_states, synth.make_sweep_times
+
+
+def test_slerp_matches_the_closed_form():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        a = rng.normal(size=4); a /= np.linalg.norm(a)
+        b = rng.normal(size=4); b /= np.linalg.norm(b)
+        t = rng.uniform()
+        d = float(a @ b)
+        th = np.arccos(abs(d))
+        s0, s1 = np.sin((1 - t) * th) / np.sin(th), np.sin(t * th) / np.sin(th)
+        ref = s0 * a + (s1 if d >= 0 else -s1) * b
+        assert np.allclose(O.quat_slerp(a, t, b), ref, rtol=0, atol=1e-14)
+    a = np.array([0, 0, 0, 1.0])
+    assert np.allclose(O.quat_slerp(a, 0.3, a), a)                      # |dot| >= 1 - eps: linear branch
+    assert np.allclose(O.quat_slerp(a, 0.3, -a), 0.7 * a + 0.3 * a)     # opposite hemisphere: scale1 flips sign
+
+
+def test_distort_frame_by_constant_against_numpy():
+    st = make_imu_states()
+    rng = np.random.default_rng(9)
+    raw = rng.normal(0, 20, (500, 3)); rel = make_sweep_times(500)
+    R_il = _np_quat_to_rot(np.array([0.01, 0.02, -0.03, 0.9993]) / np.linalg.norm([0.01, 0.02, -0.03, 0.9993])); t_il = np.array([0.05, -0.02, 0.1])
+    got = O.distort_frame_by_constant(raw, rel, st, st[0]["timestamp"], R_il, t_il)
+    t0, t1 = st[0]["timestamp"], st[-1]["timestamp"]
+    for i in range(500):
+        tp = t0 + rel[i] / 1000.0
+        if abs(tp - t0) < 1e-6: tp = t0 + 1e-6
+        if abs(tp - t1) < 1e-6: tp = t1 - 1e-6
+        a = min(max((tp - t0) / (t1 - t0), 0.0), 1.0)
+        q = O.quat_slerp(st[0]["quat"], a, st[-1]["quat"])
+        ref = _np_quat_to_rot(q) @ (R_il @ raw[i] + t_il) + (1 - a) * st[0]["trans"] + a * st[-1]["trans"]
+        assert np.allclose(got[i], ref, rtol=1e-13, atol=1e-12)
+
+
+def test_distort_frame_by_imu_against_numpy_and_its_iterator_semantics():
+    st = make_imu_states()
+    rng = np.random.default_rng(10)
+    raw = rng.normal(0, 20, (400, 3)); rel = make_sweep_times(400)
+    t0 = st[0]["timestamp"]
+    got, m = O.distort_frame_by_imu(raw, rel, st, t0)
+    assert m == 400
+    ts = np.array([s["timestamp"] for s in st])
+    for i in range(400):
+        tp = t0 + rel[i] / 1000.0
+        k = next(k for k in range(len(st) - 1) if tp > ts[k] - 1e-6 and tp < ts[k + 1] + 1e-6)
+        if abs(tp - ts[k]) < 1e-6: tp = ts[k] + 1e-6
+        if abs(tp - ts[k + 1]) < 1e-6: tp = ts[k + 1] - 1e-6
+        dt = tp - ts[k]
+        w = st[k + 1]["un_gyr"] * dt; th = np.linalg.norm(w)
+        dq = np.r_[w / 2, 1.0] if th < 1e-4 else np.r_[w / th * np.sin(th / 2), np.cos(th / 2)]
+        q = _np_quat_mul(st[k]["quat"], dq / np.linalg.norm(dq)); q /= np.linalg.norm(q)
+        ref = _np_quat_to_rot(q) @ raw[i] + st[k]["trans"] + st[k]["vel"] * dt + 0.5 * st[k + 1]["un_acc"] * dt * dt
+        assert np.allclose(got[i], ref, rtol=1e-12, atol=1e-11), i
+    # a point that is earlier than the interval the walk has reached stops it: the rest keep their old values
+    rel2 = rel.copy(); rel2[100] = 1.0
+    keep = np.full_like(raw, 7.0)
+    got2, m2 = O.distort_frame_by_imu(raw, rel2, st, t0, imu_xyz_in=keep)
+    assert m2 == 100 and np.array_equal(got2[:100], got[:100]) and np.all(got2[100:] == 7.0)
+    # a point after the last IMU stamp: same
+    rel3 = rel.copy(); rel3[250:] += 500.0
+    got3, m3 = O.distort_frame_by_imu(raw, rel3, st, t0, imu_xyz_in=keep)
+    assert m3 == 250 and np.all(got3[250:] == 7.0)
+    # fewer than two states: the outer loop never runs
+    assert O.distort_frame_by_imu(raw, rel, st[:1], t0)[1] == 0
+
+
+def test_transform_all_imu_point_inverts_the_end_pose():
+    st = make_imu_states()
+    rng = np.random.default_rng(11)
+    raw = rng.normal(0, 20, (300, 3))
+    R_il = _np_quat_to_rot(np.array([0.0, 0.0, 0.0, 1.0])); t_il = np.array([0.05, -0.02, 0.1])
+    last = st[-1]
+    imu = (_np_quat_to_rot(last["quat"]) @ (R_il @ raw.T + t_il[:, None])).T + last["trans"]   # transformPoint with the end pose
+    back = O.transform_all_imu_point(imu, last, R_il, t_il)
+    assert np.allclose(back, raw, rtol=1e-12, atol=1e-11)
