@@ -1,6 +1,8 @@
 // srl_api.cu — C-ABI glue: context, sweep residency, one ESIKF pass, the iterated update.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -41,6 +43,7 @@ int ensure_pinned(srl_ctx* ctx, size_t bytes) {
 void timing_collect(srl_ctx* ctx) {
     if (!ctx->ev_pending) return;
     float ms = 0.f;
+    cudaEventSynchronize(ctx->ev1);   // the mapped-result path returns before the event behind the last kernel has completed
     if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->k1_ms += ms; ctx->k1_launches += 1; }
     else cudaGetLastError();
     ctx->ev_pending = false;
@@ -116,6 +119,36 @@ static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
     if (*p) return SRL_OK;
     cudaError_t e = cudaMalloc(p, count * sizeof(T));
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(debug/rows)");
+    return SRL_OK;
+}
+
+// Result of a pass through the mapped host buffer: arm_host_result() before the launch, wait_host_result() after it.
+static void arm_host_result(srl_ctx* ctx, K1Args& a) {
+    if (!ctx->mapped_result) { a.host_out = nullptr; a.host_seq = 0; return; }
+    a.host_out = ctx->d_h_out32;
+    a.host_seq = ++ctx->host_seq;
+}
+// Spins on the sequence flag the pass's last kernel writes after its 32 sums; falls back to the stream's status so a
+// failed launch or a device fault is reported instead of spinning forever.
+static int wait_host_result(srl_ctx* ctx, const K1Args& a) {
+    if (!a.host_out) {
+        SRL_CUDA(ctx, cudaMemcpyAsync(ctx->h_out32, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SRL_OK;
+    }
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(ctx->h_out32 + 32);
+    for (unsigned long long spins = 1;; ++spins) {
+        if (*flag == a.host_seq) break;
+        if ((spins & 0x3fffull) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) {   // everything ran: the flag must be there (or the kernel never published)
+                if (*flag == a.host_seq) break;
+                return set_err(ctx, SRL_CUDA_ERROR, "the pass finished without publishing its result");
+            }
+            if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "cudaStreamQuery while waiting for a pass");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
     return SRL_OK;
 }
 
@@ -205,9 +238,12 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
               cudaMalloc(&ctx->d_scan_count, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(ctx->d_scan_count, 0, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMallocHost(&ctx->h_out32, 64 * sizeof(double)) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_out32, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer(&ctx->d_h_out32, ctx->h_out32, 0) == cudaSuccess &&
               cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
     if (!ok) { srl_ctx_destroy(ctx); cudaGetLastError(); return SRL_CUDA_ERROR; }
+    std::memset(ctx->h_out32, 0, 64 * sizeof(double));
+    if (const char* e = getenv("SRL_MAPPED_RESULT")) ctx->mapped_result = atoi(e) != 0;   // A/B switch (bench runs)
     *out = ctx;
     return SRL_OK;
 }
@@ -243,6 +279,7 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
         k1_fast_set_lanes_per_keypoint((int)value);
         return SRL_OK;
     }
+    if (n == "mapped_result") { ctx->mapped_result = value != 0; return SRL_OK; }
     if (n == "split_lanes_per_keypoint") {
         if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");
         k1_split_set_lanes_per_keypoint((int)value);
@@ -431,9 +468,9 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
     if (n <= 0) {
         std::memset(h, 0, 32 * sizeof(double));
     } else if (!cap_mode) {
+        arm_host_result(ctx, a);
         if ((rc = launch_pass(ctx, sw, a, debug)) != SRL_OK) return rc;
-        SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((rc = wait_host_result(ctx, a)) != SRL_OK) return rc;
         if (ctx->timing) timing_collect(ctx);
     } else {
         // ordered cap (src/optimize.cpp:107): process keypoints in order, chunk by chunk, until k* is found
@@ -601,10 +638,10 @@ int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* 
         a.comm.world = comm->world; a.comm.rank = comm->rank; a.comm.seq = ++comm->seq;
         for (int r = 0; r < comm->world; ++r) a.comm.mail[r] = comm->peer[r];
         (void)n;
+        arm_host_result(ctx, a);
         if ((rc = launch_pass(ctx, sw, a, false)) != SRL_OK) return rc;     // also valid for an empty shard
         double* h = ctx->h_out32;
-        SRL_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_out32, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((rc = wait_host_result(ctx, a)) != SRL_OK) return rc;
         if (ctx->timing) timing_collect(ctx);
         if (h[0] != h[0]) return set_err(ctx, SRL_COMM_ERROR, "peer exchange timed out (a rank did not reach this pass)");
         srl_normal_eq ne;

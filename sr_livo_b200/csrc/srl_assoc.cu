@@ -285,6 +285,19 @@ __device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, i
     return ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
 }
 
+// The pass's result straight into mapped pinned host memory (one warp): 32 sums, system fence, sequence flag.  The host
+// spins on the flag (srl_api.cu: wait_host_result) — no D2H copy, no stream synchronize on the critical path.
+__device__ __forceinline__ void publish_to_host(const K1Args& A, double tot, int lane) {
+    if (!A.host_out) return;
+    A.host_out[lane] = tot;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(A.host_out + 32) = A.host_seq;
+        __threadfence_system();
+    }
+}
+
 template <int NCH, bool DEBUG, int MINB>
 __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -315,6 +328,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
             double tot = A.prev_out32 ? A.prev_out32[lane] : 0.0;
             if (A.comm.world > 1) tot = comm_exchange(A.comm, tot, lane);
             A.out32[lane] = tot;
+            publish_to_host(A, tot, lane);
         }
         return;
     }
@@ -548,6 +562,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
             if (A.comm.world > 1) tot = comm_exchange(A.comm, tot, lane);
             A.out32[lane] = tot;
             if (lane == 0) { *A.ticket = 0u; if (A.only_flagged && A.stats) A.stats[2] = 0ull; }
+            publish_to_host(A, tot, lane);
         }
     }
 }

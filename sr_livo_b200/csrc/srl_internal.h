@@ -51,6 +51,9 @@ struct K1Args {
     unsigned long long* stats;   // optional device counters: [0] keypoints that took the exact-selection fallback
     float eps_scale;             // 1 normally; +inf forces the exact selection for every keypoint (tests)
     CommDev comm;                // multi-GPU: the last block exchanges the 32 sums with the peers over NVLink
+    double* host_out;            // optional mapped pinned host buffer: the final 32 sums are also written there, then
+    unsigned long long host_seq; // host_out[32] (as u64) = host_seq after a system fence: the host spins on it instead of
+                                 // a D2H copy + stream synchronize
 };
 
 constexpr int kFastWarps = 4;
@@ -125,7 +128,10 @@ struct srl_ctx {
     int max_grid = 0;
     unsigned int* d_ticket = nullptr;
     double* d_out32 = nullptr;
-    double* h_out32 = nullptr;      // pinned
+    double* h_out32 = nullptr;      // pinned + mapped: [0,32) sums, [32] sequence flag written by the pass's last kernel, [33..64) scratch
+    double* d_h_out32 = nullptr;    // device-side address of h_out32
+    unsigned long long host_seq = 0;
+    bool mapped_result = true;      // option "mapped_result": read a pass's sums through the mapped buffer (default) or by memcpy + sync
     long long* d_k2_state = nullptr;
     unsigned long long* d_stats = nullptr;   // 4 counters
     double* d_fast_out = nullptr;            // k1_fast's 32 sums, added by the exact-fallback launch
