@@ -542,7 +542,22 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
                 const int cnt = (int)(ent & 31u);
                 const float4* bp = reinterpret_cast<const float4*>(A.blocks + (size_t)(ent >> 5) * kBlockFloats);
                 if (sub == 0) scanned += (unsigned)cnt;
-                for (int i = sub; i < cnt; i += LPK) {
+                int i = sub;
+                // two candidates per step while the lane has two left: for a sorted pair (lo, hi) the merged list is
+                // l'[j] = min(l[j], max(l[j-1], lo), max(l[j-2], hi)) — 3 ops per stage for 2 candidates (VIMNMX3)
+                for (; i + LPK < cnt; i += 2 * LPK) {
+                    const float4 ma = __ldg(bp + i), mb = __ldg(bp + i + LPK);
+                    const float ax = (ma.x - ofx) - rfx, ay = (ma.y - ofy) - rfy, az = (ma.z - ofz) - rfz;
+                    const float bx_ = (mb.x - ofx) - rfx, by_ = (mb.y - ofy) - rfy, bz_ = (mb.z - ofz) - rfz;
+                    const unsigned ka = (__float_as_uint(ax * ax + ay * ay + az * az) & ~1023u) | ((unsigned)e << 5) | (unsigned)i;
+                    const unsigned kb = (__float_as_uint(bx_ * bx_ + by_ * by_ + bz_ * bz_) & ~1023u) | ((unsigned)e << 5) | (unsigned)(i + LPK);
+                    const unsigned lo = min(ka, kb), hi = max(ka, kb);
+#pragma unroll
+                    for (int j = NLS - 1; j >= 2; --j) lst[j] = min(min(lst[j], max(lst[j - 1], lo)), max(lst[j - 2], hi));
+                    lst[1] = min(min(lst[1], max(lst[0], lo)), hi);
+                    lst[0] = min(lst[0], lo);
+                }
+                if (i < cnt) {
                     const float4 mp = __ldg(bp + i);
                     const float dx = (mp.x - ofx) - rfx, dy = (mp.y - ofy) - rfy, dz = (mp.z - ofz) - rfz;
                     const float d2f = dx * dx + dy * dy + dz * dz;
@@ -847,23 +862,22 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
 // sweep ordering: Morton code of the LiDAR-frame 1 m cell of every keypoint, stable radix sort -> order[]
 // (a rigid transform keeps neighbours neighbours, so the order is pose independent and computed once per sweep)
 // ---------------------------------------------------------------------------------------------------------
-// 10 bits per axis (1 m cells within +-512 m of the sensor; farther points are clamped, which only costs locality):
-// 30-bit Morton keys -> 4 radix passes
-__device__ __forceinline__ unsigned spread10(unsigned x) {
-    x &= 0x3ffu;
-    x = (x | (x << 16)) & 0x030000ffu;
-    x = (x | (x << 8)) & 0x0300f00fu;
-    x = (x | (x << 4)) & 0x030c30c3u;
-    x = (x | (x << 2)) & 0x09249249u;
+// 8 bits per axis (1 m cells within +-128 m of the sensor; farther points are clamped, which only costs locality):
+// 24-bit Morton keys -> 3 radix passes (the sort of a 100k-point sweep is launch-latency bound: ~11 us per pass)
+__device__ __forceinline__ unsigned spread8(unsigned x) {
+    x &= 0xffu;
+    x = (x | (x << 8)) & 0x00f00fu;
+    x = (x | (x << 4)) & 0x0c30c3u;
+    x = (x | (x << 2)) & 0x249249u;
     return x;
 }
 __global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double cell, unsigned* keys, unsigned* idx) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 512.0, 0.0), 1023.0);
-    const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 512.0, 0.0), 1023.0);
-    const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 512.0, 0.0), 1023.0);
-    keys[i] = spread10((unsigned)fx) | (spread10((unsigned)fy) << 1) | (spread10((unsigned)fz) << 2);
+    const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 128.0, 0.0), 255.0);
+    const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 128.0, 0.0), 255.0);
+    const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 128.0, 0.0), 255.0);
+    keys[i] = spread8((unsigned)fx) | (spread8((unsigned)fy) << 1) | (spread8((unsigned)fz) << 2);
     idx[i] = (unsigned)i;
 }
 
@@ -871,7 +885,7 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
                                 size_t* needed, cudaStream_t stream) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 30, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 24, stream);
     const size_t need = al(n * 4) * 3 + al(tmp);
     if (needed) *needed = need;
     if (!scratch || scratch_bytes < need) return cudaSuccess;
@@ -883,7 +897,7 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
     k_sweep_keys<<<(unsigned)((n + T - 1) / T), T, 0, stream>>>(d_raw, n, 1.0, ka, ia);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return cub::DeviceRadixSort::SortPairs(p, tmp, ka, kb, ia, d_order, (int)n, 0, 30, stream);
+    return cub::DeviceRadixSort::SortPairs(p, tmp, ka, kb, ia, d_order, (int)n, 0, 24, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
