@@ -430,6 +430,20 @@ __device__ __forceinline__ void merge_with_partner(unsigned (&l)[32], unsigned g
     }
 }
 
+// sorts a bitonic 16-sequence held in registers (4 half-cleaner stages)
+__device__ __forceinline__ void sort_bitonic16(unsigned (&x)[16]) {
+#pragma unroll
+    for (int st = 8; st >= 1; st >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if ((j & st) == 0) {
+                const unsigned lo = min(x[j], x[j + st]), hi = max(x[j], x[j + st]);
+                x[j] = lo; x[j + st] = hi;
+            }
+        }
+    }
+}
+
 template <int LPK, int NLS, int MINB>
 __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) {
     static_assert(LPK == 2 || LPK == 4, "lanes per keypoint");
@@ -571,51 +585,140 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
             __syncwarp();
         }
 
-        // ---- merge the lanes' lists (every lane ends up with the group's sorted best 32)
-        unsigned l32[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) l32[j] = (j < NLS) ? lst[j] : KINF;
         const unsigned own_last = lst[NLS - 1];
-        merge_with_partner<NLS>(l32, FULLM, 1);
-        if (LPK == 4) merge_with_partner<(2 * NLS < NL ? 2 * NLS : NL)>(l32, FULLM, 2);
-
-        // ---- verdict (k1_fast's) + the lane certificate: what a lane dropped is not below its last tracked key
-        //      j0 = leading slots that are certainly among the K nearest (even their upper bound is below the (K+1)-th
-        //      key), b1 = leading slots that can be THE nearest; k1_fit computes exact distances only for [j0, m) and [0, b1)
         bool ambiguous = false;
         int m = 0, j0 = 0, b1 = 0;
-        if (full_cand) {
-            const float T = key_value(l32[KF - 1]);
+        if constexpr (LPK == 4) {
+            // ---- merge, result left distributed: the group's sorted best 32 end up as slots 0..15 in lane 0 and 16..31
+            //      in lane 1 (lanes 2, 3 compute along and are ignored).  Level 1, lane pairs: the even lane keeps
+            //      min(a[j], b[15-j]) = the 16 smallest of both lists, the odd lane max(...) = the 16 largest, each a
+            //      bitonic sequence that 4 half-cleaner stages sort.  Level 2, pair against pair: min(P[j], Q[31-j])
+            //      over the 32 slots is bitonic and holds the 32 smallest; its first half-cleaner stage runs across
+            //      lanes 0/1, the other 4 inside each lane.
+            static_assert(NLS <= 16, "per-lane list must fit 16 slots");
+            unsigned x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = (j < NLS) ? lst[j] : KINF;
+            const bool odd = (sub & 1) != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = 15 - j;
+                const unsigned va = x[j], vb = x[r];
+                unsigned ta = KINF, tb = KINF;
+                if (r < NLS) ta = __shfl_xor_sync(FULLM, vb, 1);   // partner's x[15-j] meets my x[j]
+                if (j < NLS) tb = __shfl_xor_sync(FULLM, va, 1);   // partner's x[j] meets my x[15-j]
+                x[j] = odd ? max(va, ta) : min(va, ta);
+                x[r] = odd ? max(vb, tb) : min(vb, tb);
+            }
+            sort_bitonic16(x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = 15 - j;
+                const unsigned va = x[j], vb = x[r];
+                const unsigned ta = __shfl_xor_sync(FULLM, vb, 3), tb = __shfl_xor_sync(FULLM, va, 3);
+                x[j] = min(va, ta);
+                x[r] = min(vb, tb);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const unsigned t = __shfl_xor_sync(FULLM, x[j], 1);
+                x[j] = odd ? max(x[j], t) : min(x[j], t);
+            }
+            sort_bitonic16(x);
+
+            // ---- verdict (k1_fast's) + the lane certificate: what a lane dropped is not below its last tracked key.
+            //      j0 = leading slots that are certainly among the K nearest (even their upper bound is below the (K+1)-th
+            //      key), b1 = leading slots that can be THE nearest; k1_fit computes exact distances only for [j0, m), [0, b1)
+            static_assert(KF - 1 >= 16 && NS < 32, "slots K-1, K and NS live in the odd lane");
+            const unsigned k0 = __shfl_sync(FULLM, x[0], gshift);
+            const unsigned kT = __shfl_sync(FULLM, x[KF - 1 - 16], gshift + 1);
+            const unsigned kK = __shfl_sync(FULLM, x[KF - 16], gshift + 1);
+            const unsigned kC = __shfl_sync(FULLM, x[NS - 16], gshift + 1);
+            const float T = key_value(kT);
             const float lim = T + T * kRel + 2.5f * eps_abs;
-            const float kvK = key_value(l32[KF]);
-            const float v0 = key_value(l32[0]);
+            const float kvK = key_value(kK);
+            const float v0 = key_value(k0);
             const float lim0 = v0 + v0 * kRel + 2.5f * eps_abs;
+            const int n_ns = odd ? NS - 16 : 16, n_kf = odd ? KF - 16 : 16;   // my slots below NS / below K
+            int cm = 0, cb = 0, cj = 0;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                const float kv = key_value(l32[j]);
-                m += (kv <= lim) ? 1 : 0;
-                b1 += (kv <= lim0) ? 1 : 0;
-                if (j < KF) j0 += (kv + kv * kRel + 2.5f * eps_abs < kvK) ? 1 : 0;
+            for (int j = 0; j < 16; ++j) {
+                const float kv = key_value(x[j]);
+                if (j < n_ns) { cm += (kv <= lim) ? 1 : 0; cb += (kv <= lim0) ? 1 : 0; }
+                if (j < n_kf) cj += (kv + kv * kRel + 2.5f * eps_abs < kvK) ? 1 : 0;
             }
-            ambiguous = !(key_value(l32[NS]) > lim) || !(key_value(own_last) > lim) ||
-                        (m > KF && j0 < kZone0) || b1 > kBestMax || b1 > j0;
-        }
-        ambiguous = ((__ballot_sync(FULLM, ambiguous) >> gshift) & ((1u << LPK) - 1u)) != 0u;
-        if (full_cand && A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob
-        if (valid) {
-            // one 96-byte row per sorted position: 23 x u32 (block * 20 + index in block) + header word
-            unsigned* row = A.cand_rows + (size_t)s * kRowWords;
-            if (sub == 0) {
-                row[NS] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
-                A.flags[k] = ambiguous ? 1 : 0;   // every keypoint of the range: no separate clear of the flags
-                if (ambiguous && A.stats) { atomicAdd(A.stats + 1, 1ull); atomicAdd(A.stats + 2, 1ull); }
-            }
-            if (full_cand && !ambiguous) {
+            m = cm + __shfl_xor_sync(FULLM, cm, 1);
+            b1 = cb + __shfl_xor_sync(FULLM, cb, 1);
+            j0 = cj + __shfl_xor_sync(FULLM, cj, 1);
+            if (full_cand)
+                ambiguous = !(key_value(own_last) > lim) ||
+                            (sub < 2 && (!(key_value(kC) > lim) || (m > KF && j0 < kZone0) || b1 > kBestMax || b1 > j0));
+            ambiguous = ((__ballot_sync(FULLM, ambiguous) >> gshift) & ((1u << LPK) - 1u)) != 0u;
+            if (full_cand && A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob
+            if (valid) {
+                // one 96-byte row per sorted position: 23 x u32 (block * 20 + index in block) + header word
+                unsigned* row = A.cand_rows + (size_t)s * kRowWords;
+                if (sub == 0) {
+                    row[NS] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
+                    A.flags[k] = ambiguous ? 1 : 0;   // every keypoint of the range: no separate clear of the flags
+                    if (ambiguous && A.stats) { atomicAdd(A.stats + 1, 1ull); atomicAdd(A.stats + 2, 1ull); }
+                }
+                if (full_cand && !ambiguous && sub < 2) {
+                    unsigned* rw = row + (odd ? 16 : 0);
+                    const int mine = m - (odd ? 16 : 0);   // how many of my slots are inside the window
 #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < n_ns && j < mine) {
+                            const unsigned key = x[j];
+                            rw[j] = (s_ent[kp][(key >> 5) & 31u] >> 5) * (unsigned)kBlockCap + (key & 31u);
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---- merge the lanes' lists (every lane ends up with the group's sorted best 32)
+            unsigned l32[32];
+    #pragma unroll
+            for (int j = 0; j < 32; ++j) l32[j] = (j < NLS) ? lst[j] : KINF;
+            merge_with_partner<NLS>(l32, FULLM, 1);
+            if (LPK == 4) merge_with_partner<(2 * NLS < NL ? 2 * NLS : NL)>(l32, FULLM, 2);
+
+            // ---- verdict (k1_fast's) + the lane certificate: what a lane dropped is not below its last tracked key
+            //      j0 = leading slots that are certainly among the K nearest (even their upper bound is below the (K+1)-th
+            //      key), b1 = leading slots that can be THE nearest; k1_fit computes exact distances only for [j0, m) and [0, b1)
+            if (full_cand) {
+                const float T = key_value(l32[KF - 1]);
+                const float lim = T + T * kRel + 2.5f * eps_abs;
+                const float kvK = key_value(l32[KF]);
+                const float v0 = key_value(l32[0]);
+                const float lim0 = v0 + v0 * kRel + 2.5f * eps_abs;
+    #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    if ((j % LPK) == sub && j < m) {
-                        const unsigned key = l32[j];
-                        row[j] = (s_ent[kp][(key >> 5) & 31u] >> 5) * (unsigned)kBlockCap + (key & 31u);
+                    const float kv = key_value(l32[j]);
+                    m += (kv <= lim) ? 1 : 0;
+                    b1 += (kv <= lim0) ? 1 : 0;
+                    if (j < KF) j0 += (kv + kv * kRel + 2.5f * eps_abs < kvK) ? 1 : 0;
+                }
+                ambiguous = !(key_value(l32[NS]) > lim) || !(key_value(own_last) > lim) ||
+                            (m > KF && j0 < kZone0) || b1 > kBestMax || b1 > j0;
+            }
+            ambiguous = ((__ballot_sync(FULLM, ambiguous) >> gshift) & ((1u << LPK) - 1u)) != 0u;
+            if (full_cand && A.force_amb_mod > 0 && (k % A.force_amb_mod) == 0) ambiguous = true;   // test knob
+            if (valid) {
+                // one 96-byte row per sorted position: 23 x u32 (block * 20 + index in block) + header word
+                unsigned* row = A.cand_rows + (size_t)s * kRowWords;
+                if (sub == 0) {
+                    row[NS] = (full_cand ? (ambiguous ? 255u : (unsigned)m) : 0u) | ((unsigned)j0 << 8) | ((unsigned)b1 << 16);
+                    A.flags[k] = ambiguous ? 1 : 0;   // every keypoint of the range: no separate clear of the flags
+                    if (ambiguous && A.stats) { atomicAdd(A.stats + 1, 1ull); atomicAdd(A.stats + 2, 1ull); }
+                }
+                if (full_cand && !ambiguous) {
+    #pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        if ((j % LPK) == sub && j < m) {
+                            const unsigned key = l32[j];
+                            row[j] = (s_ent[kp][(key >> 5) & 31u] >> 5) * (unsigned)kBlockCap + (key & 31u);
+                        }
                     }
                 }
             }
