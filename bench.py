@@ -389,6 +389,8 @@ def main():
                            "l2": "no flush" if args.no_flush else "256 MB L2 flush between timed steps; 8 distinct sweeps cycled",
                            "map_offered_points": int(n_offered), "map_gen_s": round(t_gen, 2), "map_insert_s": round(t_ins, 2)},
                 "sweeps_per_s": 1e3 / ms_step, "clocks": clk, "gpu_launches": int(launches),
+                "ms_per_step_stats": {"p50": float(np.median(ms_res)), "min": float(ms_res.min()), "max": float(ms_res.max()),
+                                      "note": "this rank's per-step CUDA-event times; ms_per_step is their mean (max over ranks)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,
                         "h2d_bytes_per_step": int(args.points * 24), "d2h_bytes_per_step": int(args.points * 24 + N_PASSES * 256)},
                 "roofline": roofline}

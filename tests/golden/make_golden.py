@@ -61,6 +61,29 @@ def map_insert_fixture():
     print("map_insert.npz:", n1, "+", n2, "points,", k2.shape[0], "voxels")
 
 
+def sweep_prep_fixture():
+    """Rows N2 / N3: gridSampling order and the undistortion / sweep-end transforms on one small sweep."""
+    rng = synth.rng_for(41)
+    n = 2000
+    raw = rng.normal(0, 15, (n, 3))
+    rel = synth.make_sweep_times(n, seed=6)
+    st = synth.make_imu_states(seed=4)
+    R_il = O.quat_to_rot(np.array([0.01, -0.02, 0.015, 0.9996]) / np.linalg.norm([0.01, -0.02, 0.015, 0.9996]))
+    t_il = np.array([0.04, 0.02, -0.03])
+    t0 = st[0]["timestamp"]
+    by_const = O.distort_frame_by_constant(raw, rel, st, t0, R_il, t_il)
+    by_imu, n_imu = O.distort_frame_by_imu(raw, rel, st, t0, R_il, t_il)
+    rel_cut = rel.copy(); rel_cut[1500] = -5.0                       # the iterator walk stops here
+    by_imu_cut, n_cut = O.distort_frame_by_imu(raw, rel_cut, st, t0, R_il, t_il, imu_xyz_in=np.full_like(raw, 9.0))
+    end_frame = O.transform_all_imu_point(by_imu, st[-1], R_il, t_il)
+    keep = O.grid_sampling(by_imu, 0.8)
+    np.savez_compressed(os.path.join(HERE, "sweep_prep.npz"), raw=raw, rel=rel, rel_cut=rel_cut, imu_states=O.imu_states_array(st),
+                        R_il=R_il, t_il=t_il, t0=np.array(t0), by_const=by_const, by_imu=by_imu, n_imu=np.array(n_imu),
+                        by_imu_cut=by_imu_cut, n_cut=np.array(n_cut), end_frame=end_frame, grid_keep=keep, grid_size=np.array(0.8))
+    print("sweep_prep.npz:", n, "points,", len(st), "IMU states,", keep.shape[0], "keypoints after grid sampling, walk cut at", n_cut)
+
+
 if __name__ == "__main__":
     scan_matching_fixture()
     map_insert_fixture()
+    sweep_prep_fixture()
