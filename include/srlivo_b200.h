@@ -150,6 +150,10 @@ int srl_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_vo
 void srl_map_destroy(srl_map* map);
 int srl_map_clear(srl_map* map);
 int srl_map_stats(srl_map* map, int64_t* n_voxels, int64_t* n_points); /* mapSize (src/lioOptimization.cpp:574-581) */
+/* removePointsFarFromLocation (src/lioOptimization.cpp:556-572; the call at :1032 is commented out in the reference, the
+ * function is what bounds the map of a long run): erases every voxel whose FIRST point is farther than `distance` from
+ * `location`; the block pool is compacted and the slot table rebuilt. */
+int srl_map_remove_far(srl_map* map, const double location[3], double distance, int64_t* n_removed);
 /* mirror of a host voxelHashMap: keys n*3, counts n, xyz n*cap*3 (block order = voxelBlock::points order) */
 int srl_map_upload(srl_map* map, const int16_t* keys, const int32_t* counts, const float* xyz, size_t n_voxels);
 int srl_map_download(srl_map* map, int16_t* keys, int32_t* counts, float* xyz, size_t max_voxels, int64_t* n_voxels);

@@ -113,6 +113,8 @@ def lib(prefer_tsl: bool = True):
     L.orc_map_num_points.restype = C.c_int64
     L.orc_map_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_int32]
     L.orc_map_add_points.restype = C.c_int64
+    L.orc_map_remove_far.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.orc_map_remove_far.restype = C.c_int64
     L.orc_map_snapshot.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_map_snapshot.restype = C.c_int64
     L.orc_map_load.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
@@ -203,6 +205,11 @@ class OracleMap:
         xyz = _f64(xyz).reshape(-1, 3)
         return int(lib().orc_map_add_points(self._h, _ptr(xyz), xyz.shape[0], voxel_size, max_num_points_in_voxel,
                                             min_distance_points, min_num_points))
+
+    def remove_far(self, location, distance: float) -> int:
+        """removePointsFarFromLocation (src/lioOptimization.cpp:556-572)."""
+        loc = _f64(location).reshape(3)
+        return int(lib().orc_map_remove_far(self._h, _ptr(loc), float(distance)))
 
     def snapshot(self, cap=20):
         n = self.num_voxels

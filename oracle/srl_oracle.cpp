@@ -865,6 +865,20 @@ int64_t orc_map_add_points(void* map, const double* xyz, int64_t n, double voxel
     return added;
 }
 
+// lioOptimization::removePointsFarFromLocation (src/lioOptimization.cpp:556-572)
+int64_t orc_map_remove_far(void* map_, const double location[3], double distance) {
+    voxelHashMap& map = *static_cast<voxelHashMap*>(map_);
+    std::vector<voxel> voxels_to_erase;
+    const Vec3 loc = {{location[0], location[1], location[2]}};
+    for (auto& pair : map) {
+        const rgbPoint& rgb_point = pair.second.points[0];
+        const Vec3 pt = {{(double)rgb_point.position[0], (double)rgb_point.position[1], (double)rgb_point.position[2]}};
+        if (sqnorm3(vsub(pt, loc)) > (distance * distance)) voxels_to_erase.push_back(pair.first);
+    }
+    for (auto& vox : voxels_to_erase) map.erase(vox);
+    return (int64_t)voxels_to_erase.size();
+}
+
 int64_t orc_map_snapshot(void* map, int32_t cap, int16_t* keys, int32_t* counts, float* xyz) {
     voxelHashMap& m = *static_cast<voxelHashMap*>(map);
     int64_t v = 0;

@@ -91,6 +91,9 @@ int64_t orc_map_add_points(void* map, const double* xyz, int64_t n, double voxel
                            int32_t max_num_points_in_voxel, double min_distance_points,
                            int32_t min_num_points);
 
+/* lioOptimization::removePointsFarFromLocation (src/lioOptimization.cpp:556-572); returns the number of voxels erased */
+int64_t orc_map_remove_far(void* map, const double location[3], double distance);
+
 /* dump in map iteration order; xyz is n_voxels*cap*3 floats (unused tail zero). returns n_voxels */
 int64_t orc_map_snapshot(void* map, int32_t cap, int16_t* keys, int32_t* counts, float* xyz);
 /* test-infra shortcut: fill the map from a snapshot (blocks keep the given point order) */

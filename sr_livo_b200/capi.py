@@ -72,7 +72,7 @@ class IekfIter(C.Structure):
 EXPORTS = [
     "srl_abi_version", "srl_build_info", "srl_icp_params_r3live", "srl_ctx_create", "srl_ctx_destroy",
     "srl_last_error", "srl_ctx_synchronize", "srl_ctx_kernel_launches", "srl_ctx_set_timing", "srl_ctx_pass_time", "srl_ctx_set_option", "srl_ctx_get_counter", "srl_map_create", "srl_map_destroy",
-    "srl_map_clear", "srl_map_stats", "srl_map_upload", "srl_map_download", "srl_map_insert",
+    "srl_map_clear", "srl_map_stats", "srl_map_remove_far", "srl_map_upload", "srl_map_download", "srl_map_insert",
     "srl_map_insert_device", "srl_map_insert_sweep", "srl_sweep_create", "srl_sweep_destroy", "srl_sweep_upload", "srl_sweep_set_device",
     "srl_sweep_set_shard", "srl_build_plane_residuals", "srl_build_plane_residuals_async", "srl_normal_eq_unpack",
     "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_comm_create", "srl_comm_destroy", "srl_comm_export", "srl_comm_connect",
@@ -113,6 +113,7 @@ def lib():
     L.srl_map_destroy.restype = None
     L.srl_map_clear.argtypes = [vp]
     L.srl_map_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.srl_map_remove_far.argtypes = [vp, vp, dbl, C.POINTER(i64)]
     L.srl_map_upload.argtypes = [vp, vp, vp, vp, sz]
     L.srl_map_download.argtypes = [vp, vp, vp, vp, sz, C.POINTER(i64)]
     L.srl_map_insert.argtypes = [vp, vp, sz, dbl, i32, C.POINTER(i64)]

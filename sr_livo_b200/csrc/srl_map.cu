@@ -245,6 +245,87 @@ int srl_map_clear(srl_map* m) {
     return SRL_OK;
 }
 
+// ---- removePointsFarFromLocation (src/lioOptimization.cpp:556-572; row N4): a voxel goes when its FIRST point is farther
+// than `distance` from `location`.  Open addressing has no cheap erase, and the block pool must stay dense (block index
+// = slot payload), so eviction is mark -> compact the pool (stable: surviving blocks keep their relative order) ->
+// rebuild the slot table from the keys kept in the blocks.
+__global__ void k_far_flags(const float* __restrict__ blocks, long long n_voxels, double lx, double ly, double lz, double dist2,
+                            unsigned* __restrict__ keep) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    const float* b = blocks + (size_t)v * kBlockFloats;
+    const unsigned cnt = reinterpret_cast<const unsigned*>(b)[kMetaCount];
+    // rgbPoint::getPosition() widens the stored floats; (pt - location).squaredNorm() reduces as x^2 + (y^2 + z^2)
+    const double dx = __dsub_rn((double)b[0], lx), dy = __dsub_rn((double)b[1], ly), dz = __dsub_rn((double)b[2], lz);
+    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz)));
+    keep[v] = (cnt > 0 && !(d2 > dist2)) ? 1u : 0u;
+}
+__global__ void k_compact_blocks(const float* __restrict__ blocks, long long n_voxels, const unsigned* __restrict__ keep,
+                                 const unsigned* __restrict__ new_index, float* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread
+    const long long v = e / (kBlockFloats / 4);
+    if (v >= n_voxels || !keep[v]) return;
+    const int q = (int)(e % (kBlockFloats / 4));
+    reinterpret_cast<float4*>(out + (size_t)new_index[v] * kBlockFloats)[q] = reinterpret_cast<const float4*>(blocks + (size_t)v * kBlockFloats)[q];
+}
+__global__ void k_rebuild_slots(Slot* slots, unsigned int mask, const float* __restrict__ blocks, long long n_voxels, long long* n_points) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_voxels) return;
+    const unsigned int* meta = reinterpret_cast<const unsigned int*>(blocks + (size_t)v * kBlockFloats);
+    const unsigned long long key = (unsigned long long)meta[kMetaKeyLo] | ((unsigned long long)meta[kMetaKeyHi] << 32);
+    short x, y, z;
+    unpack_key(key, x, y, z);
+    slot_claim(slots, mask, key, x, y, z, (unsigned)v, meta[kMetaCount]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(n_points), (unsigned long long)meta[kMetaCount]);
+}
+
+int srl_map_remove_far(srl_map* m, const double location[3], double distance, int64_t* n_removed) {
+    if (!m || !location) return SRL_BAD_ARG;
+    srl_ctx* ctx = m->ctx;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_removed) *n_removed = 0;
+    const long long nv = (long long)m->n_voxels;
+    if (nv == 0) return SRL_OK;
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (int)nv, ctx->stream);
+    // worst case every block survives: the compacted copy needs a pool-sized scratch
+    const size_t need = 2 * al((size_t)nv * 4) + al(tmp) + al((size_t)nv * kBlockFloats * sizeof(float)) + 256;
+    int rc = ensure_scratch(ctx, need);
+    if (rc != SRL_OK) return rc;
+    char* p = static_cast<char*>(ctx->d_scratch);
+    unsigned* keep = reinterpret_cast<unsigned*>(p); p += al((size_t)nv * 4);
+    unsigned* nidx = reinterpret_cast<unsigned*>(p); p += al((size_t)nv * 4);
+    void* cub_tmp = p; p += al(tmp);
+    float* pool = reinterpret_cast<float*>(p);
+    const int T = 256;
+    k_far_flags<<<(unsigned)((nv + T - 1) / T), T, 0, ctx->stream>>>(m->d_blocks, nv, location[0], location[1], location[2], distance * distance, keep);
+    SRL_CUDA(ctx, cudaGetLastError());
+    SRL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, tmp, keep, nidx, (int)nv, ctx->stream));
+    unsigned last_keep = 0, last_idx = 0;
+    SRL_CUDA(ctx, cudaMemcpyAsync(&last_keep, keep + (nv - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(&last_idx, nidx + (nv - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const long long n_keep = (long long)last_idx + last_keep;
+    ctx->launches += 2;
+    if (n_keep == nv) return SRL_OK;   // nothing to evict
+    const long long n_quads = nv * (kBlockFloats / 4);
+    k_compact_blocks<<<(unsigned)((n_quads + T - 1) / T), T, 0, ctx->stream>>>(m->d_blocks, nv, keep, nidx, pool);
+    SRL_CUDA(ctx, cudaGetLastError());
+    if (n_keep > 0) SRL_CUDA(ctx, cudaMemcpyAsync(m->d_blocks, pool, (size_t)n_keep * kBlockFloats * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    SRL_CUDA(ctx, cudaMemsetAsync(m->d_slots, 0, m->capacity * sizeof(Slot), ctx->stream));
+    SRL_CUDA(ctx, cudaMemsetAsync(m->d_counters, 0, sizeof(long long), ctx->stream));
+    if (n_keep > 0) {
+        k_rebuild_slots<<<(unsigned)((n_keep + T - 1) / T), T, 0, ctx->stream>>>(m->d_slots, (unsigned)(m->capacity - 1), m->d_blocks, n_keep, m->d_counters);
+        SRL_CUDA(ctx, cudaGetLastError());
+    }
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 2;
+    m->n_voxels = n_keep;
+    if (n_removed) *n_removed = nv - n_keep;
+    return SRL_OK;
+}
+
 int srl_map_stats(srl_map* m, int64_t* n_voxels, int64_t* n_points) {
     if (!m) return SRL_BAD_ARG;
     srl_ctx* ctx = m->ctx;

@@ -107,6 +107,13 @@ class VoxelHashMap:
     def clear(self):
         _check(self.ctx.h, lib().srl_map_clear(self.h))
 
+    def remove_far(self, location, distance: float) -> int:
+        """removePointsFarFromLocation (src/lioOptimization.cpp:556-572): number of voxels erased."""
+        loc = f64(location).reshape(3)
+        n = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_remove_far(self.h, ptr(loc), float(distance), C.byref(n)))
+        return int(n.value)
+
     def stats(self):
         nv, npts = C.c_int64(0), C.c_int64(0)
         _check(self.ctx.h, lib().srl_map_stats(self.h, C.byref(nv), C.byref(npts)))
@@ -277,6 +284,10 @@ class LioOptimization:
     # ---- src/lioOptimization.cpp:574-581
     def mapSize(self) -> int:
         return self.voxel_map.stats()[1]
+
+    # ---- src/lioOptimization.cpp:556-572
+    def removePointsFarFromLocation(self, location, distance: float) -> int:
+        return self.voxel_map.remove_far(location, distance)
 
     # ---- src/utility.cpp:188-201, called at src/optimize.cpp:431
     def gridSampling(self, points_world, size_voxel_subsampling: float) -> np.ndarray:

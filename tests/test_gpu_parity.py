@@ -523,6 +523,37 @@ def test_grid_sampling_matches_the_reference_order(L, small_world):
     assert np.allclose(ft, ref["frame_t"], atol=1e-9) and np.allclose(fq, ref["frame_q"], atol=1e-9)
 
 
+def test_remove_points_far_from_location_then_keep_working(L, small_world):
+    """Row N4 (src/lioOptimization.cpp:556-572): eviction by the voxel's first point, pool compaction and slot rebuild;
+    the map must answer queries and take insertions afterwards exactly like the oracle's."""
+    from sr_livo_b200 import lio
+    keys, counts, xyz = small_world["omap"].snapshot()
+    om = O.OracleMap(); om.load(keys, counts, xyz)            # a private copy: this test edits the map
+    L.voxel_map.upload(keys, counts, xyz)
+    sw = small_world["sweep"]
+    loc = np.array([4.0, -3.0, 1.5])
+    nv0, np0 = L.voxel_map.stats()
+    assert L.removePointsFarFromLocation(loc, 1e4) == 0 and L.voxel_map.stats() == (nv0, np0)     # nothing is that far
+    n_g = L.removePointsFarFromLocation(loc, 25.0)
+    n_o = om.remove_far(loc, 25.0)
+    assert n_g == n_o and 0 < n_g < nv0
+    _assert_map_equal(L, om)
+    assert L.mapSize() == om.num_points
+    # queries against the shrunken map
+    prm, oprm = lio.r3live_params(max_num_residuals=BIG), O.r3live_params(max_num_residuals=BIG)
+    L.setKeypoints(sw.raw_xyz)
+    _assert_pass_equal(L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True),
+                       om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, oprm, debug=True))
+    # and insertions: points land in evicted cells again
+    reg = synth.registered_points(sw)
+    assert L.addPointsToMap(reg) == om.add_points(reg)
+    _assert_map_equal(L, om)
+    # evict everything
+    assert L.removePointsFarFromLocation(np.array([1e5, 0.0, 0.0]), 1.0) == om.remove_far(np.array([1e5, 0.0, 0.0]), 1.0)
+    assert L.voxel_map.stats() == (0, 0) and om.num_voxels == 0
+    L.voxel_map.clear()
+
+
 def test_undistortion_and_sweep_end_transform_match_the_oracle(L):
     """Row N3 (src/utility.cpp:203-332): distortFrameByConstant, distortFrameByImu (incl. its one-iterator walk) and
     transformAllImuPoint, host buffers and device buffers, against the oracle."""

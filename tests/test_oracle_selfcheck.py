@@ -414,3 +414,20 @@ def test_transform_all_imu_point_inverts_the_end_pose():
     imu = (_np_quat_to_rot(last["quat"]) @ (R_il @ raw.T + t_il[:, None])).T + last["trans"]   # transformPoint with the end pose
     back = O.transform_all_imu_point(imu, last, R_il, t_il)
     assert np.allclose(back, raw, rtol=1e-12, atol=1e-11)
+
+
+def test_remove_points_far_from_location_by_first_point():
+    pts = synth.sample_map_points(40.0, 40.0, seed=8)
+    om = O.OracleMap(); om.add_points(pts)
+    keys, counts, xyz = om.snapshot()
+    loc = np.array([3.0, -2.0, 1.0]); dist = 12.0
+    first = xyz[:, 0, :].astype(np.float64)
+    d = first - loc
+    far = (d[:, 0] ** 2 + (d[:, 1] ** 2 + d[:, 2] ** 2)) > dist * dist
+    removed = om.remove_far(loc, dist)
+    assert removed == int(far.sum()) and 0 < removed < keys.shape[0]
+    k2, c2, x2 = om.snapshot()
+    left = {tuple(k): (c, x) for k, c, x in zip(k2.tolist(), c2, x2)}
+    want = {tuple(k): (c, x) for k, c, x, f in zip(keys.tolist(), counts, xyz, far) if not f}
+    assert left.keys() == want.keys() and all(left[k][0] == want[k][0] and np.array_equal(left[k][1], want[k][1]) for k in left)
+    assert om.num_points == int(counts[~far].sum())
