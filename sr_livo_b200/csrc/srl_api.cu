@@ -184,7 +184,10 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         // k1_scan writes the flag of every keypoint of its range; otherwise (k1_fast, or a shard of the sweep) clear them
         if (!(split && a.k_begin == 0 && a.k_end == (long long)sw->n)) SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
         if (split) {
-            if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
+            if (!sw->d_cand_rows) {   // k1_fit loads whole rows and uses only the slots k1_scan filled: start from defined memory
+                if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
+                SRL_CUDA(ctx, cudaMemsetAsync(sw->d_cand_rows, 0, (sw->capacity * (size_t)24 + 8) * sizeof(unsigned), ctx->stream));
+            }
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
             SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
             ctx->launches += 1;
