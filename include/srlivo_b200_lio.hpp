@@ -11,9 +11,14 @@
 //   lioOptimization::buildPlaneResiduals  src/optimize.cpp:18       srl::LioBackend::buildPlaneResiduals
 //   lioOptimization::updateIEKF       src/optimize.cpp:133          srl::LioBackend::updateIEKF
 //   lioOptimization::optimize         src/optimize.cpp:428          srl::LioBackend::optimize (keypoints given)
+//   lioOptimization::removePointsFarFromLocation  src/lioOptimization.cpp:556   srl::LioBackend::removePointsFarFromLocation
+//   gridSampling                      src/utility.cpp:188           srl::LioBackend::gridSampling (keypoint indices)
+//   distortFrameByConstant / ByImu    src/utility.cpp:203,238       srl::LioBackend::distortFrameByConstant / distortFrameByImu
+//   transformAllImuPoint              src/utility.cpp:320           srl::LioBackend::transformAllImuPoint
 #pragma once
 
 #include <array>
+#include <cstdint>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -105,6 +110,37 @@ public:
         const int rc = srl_optimize_host(ctx_, map_, sweep_, raw_xyz, n, &eskf, frame_q, frame_t, t_last, R_imu_lidar,
                                          t_imu_lidar, &cur_icp_options, &sm, world_xyz_out);
         return summarise(rc, sm);
+    }
+
+    // src/lioOptimization.cpp:556-572 — voxels whose first point is farther than `distance` from `location` go
+    long long removePointsFarFromLocation(const double location[3], double distance) {
+        int64_t removed = 0;
+        check(srl_map_remove_far(map_, location, distance, &removed), "srl_map_remove_far");
+        return removed;
+    }
+    // src/utility.cpp:188-201 — indices (into the frame) of the keypoints, in the reference's order
+    std::vector<uint32_t> gridSampling(const double* xyz_world, size_t n, double size_voxel_subsampling) {
+        std::vector<uint32_t> keep(n);
+        size_t m = 0;
+        check(srl_grid_sampling(ctx_, xyz_world, n, size_voxel_subsampling, keep.data(), &m), "srl_grid_sampling");
+        keep.resize(m);
+        return keep;
+    }
+    // src/utility.cpp:203-236, :238-312, :320-332 — point buffers may be host or device pointers
+    void distortFrameByConstant(const double* raw_xyz, const double* relative_time_ms, size_t n, const std::vector<srl_imu_state>& imu_states,
+                                double time_frame_begin, double* imu_xyz) {
+        check(srl_distort_frame_by_constant(ctx_, raw_xyz, relative_time_ms, n, imu_states.data(), imu_states.size(), time_frame_begin,
+                                            R_imu_lidar, t_imu_lidar, imu_xyz), "srl_distort_frame_by_constant");
+    }
+    long long distortFrameByImu(const double* raw_xyz, const double* relative_time_ms, size_t n, const std::vector<srl_imu_state>& imu_states,
+                                double time_frame_begin, double* imu_xyz) {
+        int64_t written = 0;
+        check(srl_distort_frame_by_imu(ctx_, raw_xyz, relative_time_ms, n, imu_states.data(), imu_states.size(), time_frame_begin,
+                                       R_imu_lidar, t_imu_lidar, imu_xyz, &written), "srl_distort_frame_by_imu");
+        return written;
+    }
+    void transformAllImuPoint(const double* imu_xyz, size_t n, const srl_imu_state& last_state, double* raw_xyz_out) {
+        check(srl_transform_all_imu_point(ctx_, imu_xyz, n, &last_state, R_imu_lidar, t_imu_lidar, raw_xyz_out), "srl_transform_all_imu_point");
     }
 
 #ifdef SRL_HAVE_EIGEN
