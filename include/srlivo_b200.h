@@ -136,7 +136,9 @@ int srl_ctx_set_timing(srl_ctx* ctx, int enable);
  * "k1_variant" (0 auto; 1: k1_fast, 3: k1_scan + k1_fit, both with the exact fallback where applicable; 2: k1_assoc
  * only), "split_lanes_per_keypoint" (2|4: lanes per keypoint in k1_scan), "k1_min_blocks" (2|3|4) and
  * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_lanes_per_keypoint" (1|2|4:
- * lanes that share one keypoint's candidate scan in k1_fast), "fast_force_ambiguous_mod" (N > 0:
+ * lanes that share one keypoint's candidate scan in k1_fast), "mapped_result" (1 default: a pass's sums
+ * reach the host through a mapped pinned buffer + sequence flag; 0: cudaMemcpyAsync + stream synchronize),
+ * "fast_force_ambiguous_mod" (N > 0:
  * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over).  Counters: "exact_fallbacks"
  * (keypoints whose FP32 selection in k1_assoc was ambiguous and were redone exactly), "fast_ambiguous" (keypoints
  * k1_fast handed to k1_assoc), "kernel_launches". */
@@ -144,7 +146,8 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value);
 int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value);
 int srl_ctx_pass_time(srl_ctx* ctx, double* total_ms, int64_t* launches, int reset);
 
-/* ---- map: voxelHashMap + addPointsToMap (include/cloudMap.h:124-184, src/lioOptimization.cpp:400-446,520-554) */
+/* ---- map: voxelHashMap + addPointsToMap (include/cloudMap.h:124-184, src/lioOptimization.cpp:400-446,520-554)
+ * max_num_points_in_voxel <= 20 (block layout), max_voxels <= 2^25 (32-bit point indices in the kernels) */
 int srl_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_voxel, size_t max_voxels,
                    srl_map** out);
 void srl_map_destroy(srl_map* map);

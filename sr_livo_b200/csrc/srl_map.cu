@@ -211,6 +211,8 @@ int srl_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_vo
     if (!ctx || !out) return SRL_BAD_ARG;
     if (!(voxel_size > 0) || max_num_points_in_voxel < 1 || max_num_points_in_voxel > kBlockCap || max_voxels == 0)
         return set_err(ctx, SRL_BAD_ARG, "srl_map_create: voxel_size>0, 1<=max_num_points_in_voxel<=20, max_voxels>0 required");
+    // the pass kernels address points as 32-bit float indices into the block pool (block * 80 + 4 * i)
+    if (max_voxels > (size_t(1) << 25)) return set_err(ctx, SRL_BAD_ARG, "srl_map_create: max_voxels is limited to 2^25 (33.5 M voxels, 10.7 GB of blocks)");
     SRL_CUDA(ctx, cudaSetDevice(ctx->device));
     srl_map* m = new srl_map();
     m->ctx = ctx; m->voxel_size = voxel_size; m->cap = max_num_points_in_voxel; m->max_voxels = max_voxels;
