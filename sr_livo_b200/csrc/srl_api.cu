@@ -189,6 +189,9 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
                 SRL_CUDA(ctx, cudaMemsetAsync(sw->d_cand_rows, 0, (sw->capacity * (size_t)24 + 8) * sizeof(unsigned), ctx->stream));
             }
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
+            // single GPU: k1_fit publishes the result itself when nothing was flagged, the fallback launch then runs
+            // off the host's critical path (it republishes the same values)
+            if (a.comm.world <= 1) { f.host_out = a.host_out; f.host_seq = a.host_seq; }
             SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
             ctx->launches += 1;
         } else {
@@ -474,7 +477,6 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
         arm_host_result(ctx, a);
         if ((rc = launch_pass(ctx, sw, a, debug)) != SRL_OK) return rc;
         if ((rc = wait_host_result(ctx, a)) != SRL_OK) return rc;
-        if (ctx->timing) timing_collect(ctx);
     } else {
         // ordered cap (src/optimize.cpp:107): process keypoints in order, chunk by chunk, until k* is found
         if ((rc = ensure_buf(ctx, &sw->d_rows, sw->capacity * 8)) != SRL_OK) return rc;
@@ -645,7 +647,6 @@ int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* 
         if ((rc = launch_pass(ctx, sw, a, false)) != SRL_OK) return rc;     // also valid for an empty shard
         double* h = ctx->h_out32;
         if ((rc = wait_host_result(ctx, a)) != SRL_OK) return rc;
-        if (ctx->timing) timing_collect(ctx);
         if (h[0] != h[0]) return set_err(ctx, SRL_COMM_ERROR, "peer exchange timed out (a rank did not reach this pass)");
         srl_normal_eq ne;
         unpack32(h, &ne, (long long)sw->n);

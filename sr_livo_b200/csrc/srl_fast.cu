@@ -957,6 +957,17 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
             if (lane == 30) { tot += (double)__ldcg(A.scan_count); *A.scan_count = 0ull; }   // k1_scan's visit count
             A.out32[lane] = tot;
             if (lane == 0) *A.ticket = 0u;
+            // nothing flagged in this pass (the usual case): these ARE the pass's sums — hand them to the host now; the
+            // fallback launch that follows only forwards them again (same values, same sequence number)
+            if (A.host_out && A.stats && __ldcg(A.stats + 2) == 0ull) {
+                A.host_out[lane] = tot;
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0) {
+                    *reinterpret_cast<volatile unsigned long long*>(A.host_out + 32) = A.host_seq;
+                    __threadfence_system();
+                }
+            }
         }
     }
 }

@@ -83,6 +83,8 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
                                 // (byte 0: 0 = < K candidates, K..NS = candidates inside the window, 255 = ambiguous;
                                 //  byte 1: slots certainly among the K nearest; byte 2: slots that can be the nearest)
     unsigned long long* scan_count;   // candidates visited by k1_scan, folded into component 30 by k1_fit's last block
+    double* host_out;                 // optional (single GPU): mapped host buffer; k1_fit publishes the final sums there
+    unsigned long long host_seq;      // when no keypoint was flagged in this pass (see K1Args::host_out)
 };
 
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
