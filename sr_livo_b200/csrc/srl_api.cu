@@ -38,16 +38,18 @@ int ensure_pinned(srl_ctx* ctx, size_t bytes) {
     return SRL_OK;
 }
 
-// fold a finished k1 event pair into the running totals (call only when the stream is known to have passed ev1,
-// or accept that an unfinished pair is dropped)
-void timing_collect(srl_ctx* ctx) {
-    if (!ctx->ev_pending) return;
+// fold a finished event pair into the running totals.  Pairs alternate between passes and the pair of the PREVIOUS pass is
+// collected when the next one starts: its last kernel (the fallback launch, which on one GPU is off the host's critical
+// path) has long finished by then, so timing never makes the host wait for the device.
+static void timing_collect_pair(srl_ctx* ctx, int i) {
+    if (!ctx->ev_pending[i]) return;
     float ms = 0.f;
-    cudaEventSynchronize(ctx->ev1);   // the mapped-result path returns before the event behind the last kernel has completed
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) { ctx->k1_ms += ms; ctx->k1_launches += 1; }
+    cudaEventSynchronize(ctx->ev1[i]);
+    if (cudaEventElapsedTime(&ms, ctx->ev0[i], ctx->ev1[i]) == cudaSuccess) { ctx->k1_ms += ms; ctx->k1_launches += 1; }
     else cudaGetLastError();
-    ctx->ev_pending = false;
+    ctx->ev_pending[i] = false;
 }
+void timing_collect(srl_ctx* ctx) { timing_collect_pair(ctx, 0); timing_collect_pair(ctx, 1); }
 
 // the per-pass constants of buildPlaneResiduals (src/optimize.cpp:21-28,35,55-61,95)
 void make_pass_const(const srl_frame& f, const srl_icp_params& p, PassConst& c) {
@@ -157,7 +159,11 @@ static int wait_host_result(srl_ctx* ctx, const K1Args& a) {
 static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug) {
     const long long n = a.k_end - a.k_begin;
     const bool fast = !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
-    if (ctx->timing) { timing_collect(ctx); cudaEventRecord(ctx->ev0, ctx->stream); }
+    if (ctx->timing) {
+        ctx->ev_cur ^= 1;
+        timing_collect_pair(ctx, ctx->ev_cur);   // the pair used two passes ago
+        cudaEventRecord(ctx->ev0[ctx->ev_cur], ctx->stream);
+    }
     if (!fast) {
         SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), debug, ctx->device, ctx->stream));
         ctx->launches += 1;
@@ -209,7 +215,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream));
         ctx->launches += 2;
     }
-    if (ctx->timing) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    if (ctx->timing) { cudaEventRecord(ctx->ev1[ctx->ev_cur], ctx->stream); ctx->ev_pending[ctx->ev_cur] = true; }
     return SRL_OK;
 }
 
@@ -262,8 +268,7 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     cudaFree(ctx->d_scratch);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]); if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -330,10 +335,12 @@ int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value) {
 }
 int srl_ctx_set_timing(srl_ctx* ctx, int enable) {
     if (!ctx) return SRL_BAD_ARG;
-    if (enable && !ctx->ev0) {
+    if (enable && !ctx->ev0[0]) {
         SRL_CUDA(ctx, cudaSetDevice(ctx->device));
-        SRL_CUDA(ctx, cudaEventCreate(&ctx->ev0));
-        SRL_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+        for (int i = 0; i < 2; ++i) {
+            SRL_CUDA(ctx, cudaEventCreate(&ctx->ev0[i]));
+            SRL_CUDA(ctx, cudaEventCreate(&ctx->ev1[i]));
+        }
     }
     ctx->timing = enable != 0;
     return SRL_OK;

@@ -121,8 +121,9 @@ struct srl_ctx {
     int64_t launches = 0;
     // optional CUDA-event timing of k1_assoc
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_pending = false;
+    cudaEvent_t ev0[2] = {nullptr, nullptr}, ev1[2] = {nullptr, nullptr};   // two pairs: the pass in flight and the one before
+    bool ev_pending[2] = {false, false};
+    int ev_cur = 0;
     double k1_ms = 0.0;
     int64_t k1_launches = 0;
     // per-pass scratch
