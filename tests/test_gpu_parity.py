@@ -148,8 +148,8 @@ def _close(a, b, rel=1e-12):
 
 @pytest.mark.parametrize("kw", [dict(max_num_residuals=BIG), dict(max_num_residuals=BIG, frame_id=5)])
 def test_exact_selection_path_matches_oracle(L, small_world, kw):
-    """Three ways to the same answer: (a) auto = k1_fast (FP32 packed keys + guards + exact finish) where applicable,
-    (b) k1_assoc only (FP32 selection with error bound, exact fallback), (c) k1_assoc with the exact FP64 selection
+    """Three ways to the same answer: (a) auto = k1_scan + k1_fit (FP32 packed keys + guards + exact finish) where
+    applicable, (b) k1_assoc only (FP32 selection with error bound, exact fallback), (c) k1_assoc with the exact FP64 selection
     forced for every keypoint.  All must equal the oracle: ids bit-exact, floats to rounding."""
     from sr_livo_b200 import lio
     om, sw = _load_world(L, small_world)
@@ -252,13 +252,22 @@ def test_fast_kernel_lanes_per_keypoint_variants(L, small_world, lpk):
     prm = lio.r3live_params(max_num_residuals=BIG)
     L.setKeypoints(sw.raw_xyz[:3001])
     o = om.build_plane_residuals(sw.raw_xyz[:3001], sw.q_init, sw.t_init, sw.t_last, O.r3live_params(max_num_residuals=BIG), debug=True)
+    L.ctx.set_option("k1_variant", 1)                 # k1_fast, the thread-per-keypoint form (not the default any more)
     L.ctx.set_option("fast_lanes_per_keypoint", lpk)
     try:
+        a0 = L.ctx.counter("fast_ambiguous")
         g = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
         g2 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+        L.ctx.set_option("fast_force_ambiguous_mod", 9)          # and its hand-over to the exact kernel
+        g9 = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last, debug=True)
+        a1 = L.ctx.counter("fast_ambiguous")
     finally:
+        L.ctx.set_option("fast_force_ambiguous_mod", 0)
         L.ctx.set_option("fast_lanes_per_keypoint", 1)
+        L.ctx.set_option("k1_variant", 0)
     _assert_pass_equal(g, o)
+    _assert_pass_equal(g9, o)
+    assert a1 - a0 >= int((o.num_candidates[::9] >= 20).sum())
     assert g2.num_residuals == o.num_residuals and _close(g2.HTH, o.HTH)
 
 
