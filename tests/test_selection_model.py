@@ -8,6 +8,9 @@ be bit-exact, so the certificate must never pass a wrong answer.  This file rest
 constants, same formulas) and attacks it with adversarial candidate sets: near ties at the K-th distance, clusters,
 duplicates, FP32 errors at the assumed bound.  It also checks the bound itself on the kernel's FP32 distance formula.
 No GPU, no product code: a model of the math, complementing the GPU parity tests.
+
+Second part: the parallel formulations used by rows N2 / N3 (srl_grid_sampling's dedupe-then-replay, the max-scan form
+of distortFrameByImu's one-iterator walk) against the sequential originals, on random and degenerate inputs.
 """
 import numpy as np
 import pytest
@@ -177,3 +180,71 @@ def test_fp32_distance_error_stays_inside_the_assumed_bound():
             worst = max(worst, float(np.abs(d2f.astype(np.float64) - d2).max()))
         assert worst <= 1e-4 * size * size, (size, worst)
         assert worst <= 0.5e-4 * size * size                                  # in fact with a margin of 2
+
+
+# ---- distortFrameByImu: the parallel formulation of the reference's one-iterator walk (srl_points.cu) ---------------
+def _imu_walk_parallel(tp, ts):
+    """What srl_distort_frame_by_imu computes: f_i / l_i = first / last interval holding point i (the reference's
+    comparisons), n_i = max(f_0..f_i), valid while n_i <= l_i; returns (interval per point, number of points written)."""
+    n, ns = tp.shape[0], ts.shape[0]
+    inside = (tp[:, None] > ts[None, :-1] - 1e-6) & (tp[:, None] < ts[None, 1:] + 1e-6)
+    any_in = inside.any(axis=1)
+    f = np.where(any_in, inside.argmax(axis=1), ns)
+    l = np.where(any_in, ns - 2 - inside[:, ::-1].argmax(axis=1), -1)
+    m = np.maximum.accumulate(f)
+    bad = (m >= ns) | (m > l)
+    v = int(np.argmax(bad)) if bad.any() else n
+    return m, v
+
+
+def _imu_walk_reference(tp, ts):
+    """The loop of src/utility.cpp:238-312 reduced to its control flow."""
+    n, ns = tp.shape[0], ts.shape[0]
+    used = np.full(n, -1)
+    it = 0
+    for k in range(ns - 1):
+        while it != n:
+            if tp[it] > ts[k] - 1e-6 and tp[it] < ts[k + 1] + 1e-6:
+                used[it] = k
+                it += 1
+            else:
+                break
+    return used, it
+
+
+def test_imu_interval_walk_parallel_form_equals_the_iterator():
+    rng = np.random.default_rng(17)
+    for trial in range(600):
+        ns = int(rng.integers(2, 30))
+        ts = 100.0 + np.cumsum(rng.choice([0.005, 0.005, 0.0049, 0.0, 0.01], ns))       # non-decreasing, repeated stamps allowed
+        n = int(rng.integers(1, 200))
+        tp = np.sort(rng.uniform(ts[0] - 0.002, ts[-1] + 0.002, n))
+        mode = trial % 4
+        if mode == 1:        # points exactly on / within the 1e-6 tolerance of IMU stamps
+            j = rng.integers(0, n, min(n, 10))
+            tp[j] = ts[rng.integers(0, ns, j.shape[0])] + rng.choice([0.0, 5e-7, -5e-7, 1e-6, -1e-6], j.shape[0])
+            tp = np.sort(tp)
+        elif mode == 2:      # locally unsorted
+            j = rng.integers(0, n, 3)
+            tp[j] = rng.uniform(ts[0] - 0.002, ts[-1] + 0.002, 3)
+        elif mode == 3:      # everything inside
+            tp = np.sort(rng.uniform(ts[0], ts[-1], n))
+        used, it = _imu_walk_reference(tp, ts)
+        m, v = _imu_walk_parallel(tp, ts)
+        assert v == it, (trial, v, it)
+        assert np.array_equal(m[:v], used[:it]), trial
+
+
+def test_grid_sampling_order_survives_the_dedupe():
+    """srl_grid_sampling keeps the first point of every cell on the GPU and replays only those through the reference's
+    std::tr1::unordered_map: duplicates never change the container's structure, so the iteration order is the same."""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(23)
+    for size, spread, n in ((0.5, 6.0, 20000), (1.5, 40.0, 30000), (0.2, 1.0, 5000)):
+        pts = rng.normal(0, spread, (n, 3))
+        keep_all = O.grid_sampling(pts, size)
+        cells = np.trunc(pts / size).astype(np.int64)          # static_cast<short>(x / size): truncation toward zero
+        _, first = np.unique(cells, axis=0, return_index=True)
+        first = np.sort(first)                                 # first occurrence of every cell, frame order
+        keep_u = O.grid_sampling(pts[first], size)
+        assert np.array_equal(first[keep_u], keep_all)
