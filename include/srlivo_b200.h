@@ -138,7 +138,8 @@ int srl_ctx_set_timing(srl_ctx* ctx, int enable);
  * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_lanes_per_keypoint" (1|2|4:
  * lanes that share one keypoint's candidate scan in k1_fast), "mapped_result" (1 default: a pass's sums
  * reach the host through a mapped pinned buffer + sequence flag; 0: cudaMemcpyAsync + stream synchronize),
- * "fast_force_ambiguous_mod" (N > 0:
+ * "exchange_in_fit" (1 default: on several GPUs k1_fit's last block runs the NVLink exchange itself when the rank
+ * flagged nothing, 0: always in the fallback launch), "fast_force_ambiguous_mod" (N > 0:
  * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over).  Counters: "exact_fallbacks"
  * (keypoints whose FP32 selection in k1_assoc was ambiguous and were redone exactly), "fast_ambiguous" (keypoints
  * k1_fast handed to k1_assoc), "kernel_launches". */

@@ -195,9 +195,10 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
                 SRL_CUDA(ctx, cudaMemsetAsync(sw->d_cand_rows, 0, (sw->capacity * (size_t)24 + 8) * sizeof(unsigned), ctx->stream));
             }
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
-            // single GPU: k1_fit publishes the result itself when nothing was flagged, the fallback launch then runs
-            // off the host's critical path (it republishes the same values)
-            if (a.comm.world <= 1) { f.host_out = a.host_out; f.host_seq = a.host_seq; }
+            // k1_fit publishes the result itself when nothing was flagged (multi-GPU: after running the exchange, option
+            // exchange_in_fit); the fallback launch then runs off the host's critical path and republishes the same values
+            f.comm = a.comm; f.exchange_in_fit = ctx->exchange_in_fit ? 1 : 0;
+            if (a.comm.world <= 1 || ctx->exchange_in_fit) { f.host_out = a.host_out; f.host_seq = a.host_seq; }
             SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
             ctx->launches += 1;
         } else {
@@ -256,6 +257,7 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
     if (!ok) { srl_ctx_destroy(ctx); cudaGetLastError(); return SRL_CUDA_ERROR; }
     std::memset(ctx->h_out32, 0, 64 * sizeof(double));
     if (const char* e = getenv("SRL_MAPPED_RESULT")) ctx->mapped_result = atoi(e) != 0;   // A/B switch (bench runs)
+    if (const char* e = getenv("SRL_EXCHANGE_IN_FIT")) ctx->exchange_in_fit = atoi(e) != 0;
     *out = ctx;
     return SRL_OK;
 }
@@ -291,6 +293,7 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
         return SRL_OK;
     }
     if (n == "mapped_result") { ctx->mapped_result = value != 0; return SRL_OK; }
+    if (n == "exchange_in_fit") { ctx->exchange_in_fit = value != 0; return SRL_OK; }
     if (n == "split_lanes_per_keypoint") {
         if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");
         k1_split_set_lanes_per_keypoint((int)value);

@@ -257,34 +257,6 @@ __device__ __forceinline__ void select_exact(const float* __restrict__ blocks, c
     nfound = __popc(__ballot_sync(FULL, lane < K && bd < KINF));
 }
 
-// Fused exchange over NVLink peer memory (one warp): publish this rank's 32 sums into every rank's mailbox, wait for the
-// others' sums of the same pass, add all of them in rank order (bitwise identical everywhere).  NaN marks a failed exchange.
-__device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, int lane) {
-    const int par = (int)(cm.seq & 1ull);
-    for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
-    __threadfence_system();
-    __syncwarp();
-    if (lane < cm.world) {
-        volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
-        *f = cm.seq;
-    }
-    __threadfence_system();
-    bool ok = true;
-    if (lane < cm.world) {
-        volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
-        long long spins = 0;
-        while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
-    }
-    ok = __all_sync(FULL, ok);
-    __threadfence_system();
-    double sum = 0.0;
-    for (int r = 0; r < cm.world; ++r) {
-        const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
-        sum += *d;
-    }
-    return ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
-}
-
 // The pass's result straight into mapped pinned host memory (one warp): 32 sums, system fence, sequence flag.  The host
 // spins on the flag (srl_api.cu: wait_host_result) — no D2H copy, no stream synchronize on the critical path.
 __device__ __forceinline__ void publish_to_host(const K1Args& A, double tot, int lane) {
@@ -326,7 +298,10 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     if (A.only_flagged && A.stats && __ldcg(A.stats + 2) == 0ull) {
         if (blockIdx.x == 0 && warp == 0) {
             double tot = A.prev_out32 ? A.prev_out32[lane] : 0.0;
-            if (A.comm.world > 1) tot = comm_exchange(A.comm, tot, lane);
+            const bool exchanged = __ldcg(A.stats + 3) != 0ull;   // k1_fit already ran the exchange (and published)
+            __syncwarp();
+            if (A.comm.world > 1 && !exchanged) tot = comm_exchange(A.comm, tot, lane);
+            if (lane == 0 && exchanged) A.stats[3] = 0ull;
             A.out32[lane] = tot;
             publish_to_host(A, tot, lane);
         }

@@ -955,11 +955,19 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
 #pragma unroll
             for (int w = 0; w < kFastWarps; ++w) tot += s_acc[w][lane];
             if (lane == 30) { tot += (double)__ldcg(A.scan_count); *A.scan_count = 0ull; }   // k1_scan's visit count
+            // nothing flagged in this pass on this rank (the usual case): these ARE the rank's sums.  Single GPU: hand them to
+            // the host now; multi-GPU (exchange_in_fit): run the NVLink exchange here.  The fallback launch that follows
+            // then only forwards the totals again (same values, same sequence number).
+            const bool none_flagged = A.stats && __ldcg(A.stats + 2) == 0ull;
+            bool final_here = none_flagged && A.comm.world <= 1;
+            if (none_flagged && A.comm.world > 1 && A.exchange_in_fit) {
+                tot = comm_exchange(A.comm, tot, lane);
+                if (lane == 0) A.stats[3] = 1ull;   // tells the fallback launch not to exchange again
+                final_here = true;
+            }
             A.out32[lane] = tot;
             if (lane == 0) *A.ticket = 0u;
-            // nothing flagged in this pass (the usual case): these ARE the pass's sums — hand them to the host now; the
-            // fallback launch that follows only forwards them again (same values, same sequence number)
-            if (A.host_out && A.stats && __ldcg(A.stats + 2) == 0ull) {
+            if (A.host_out && final_here) {
                 A.host_out[lane] = tot;
                 __threadfence_system();
                 __syncwarp();

@@ -30,6 +30,36 @@ struct CommDev {              // by-value kernel argument; world <= 1 disables t
     Mailbox* mail[kMaxRanks]; // mail[r] = rank r's mailbox as mapped in THIS process (mail[rank] is local memory)
 };
 
+#if defined(__CUDACC__)
+// Fused exchange over NVLink peer memory (one warp): publish this rank's 32 sums into every rank's mailbox, wait for the
+// others' sums of the same pass, add all of them in rank order (bitwise identical everywhere).  NaN marks a failed exchange.
+__device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, int lane) {
+    const int par = (int)(cm.seq & 1ull);
+    for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
+    __threadfence_system();
+    __syncwarp();
+    if (lane < cm.world) {
+        volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
+        *f = cm.seq;
+    }
+    __threadfence_system();
+    bool ok = true;
+    if (lane < cm.world) {
+        volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
+        long long spins = 0;
+        while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    double sum = 0.0;
+    for (int r = 0; r < cm.world; ++r) {
+        const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
+        sum += *d;
+    }
+    return ok ? sum : __longlong_as_double(0x7ff8000000000000ll);
+}
+#endif
+
 struct K1Args {
     PassConst c;
     const Slot* slots;
@@ -83,8 +113,10 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
                                 // (byte 0: 0 = < K candidates, K..NS = candidates inside the window, 255 = ambiguous;
                                 //  byte 1: slots certainly among the K nearest; byte 2: slots that can be the nearest)
     unsigned long long* scan_count;   // candidates visited by k1_scan, folded into component 30 by k1_fit's last block
-    double* host_out;                 // optional (single GPU): mapped host buffer; k1_fit publishes the final sums there
-    unsigned long long host_seq;      // when no keypoint was flagged in this pass (see K1Args::host_out)
+    double* host_out;                 // optional: mapped host buffer; k1_fit publishes the final sums there when no keypoint
+    unsigned long long host_seq;      // was flagged in this pass (see K1Args::host_out)
+    CommDev comm;                     // multi-GPU with exchange_in_fit: k1_fit's last block runs the exchange in that case
+    int exchange_in_fit;
 };
 
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
@@ -134,6 +166,7 @@ struct srl_ctx {
     double* h_out32 = nullptr;      // pinned + mapped: [0,32) sums, [32] sequence flag written by the pass's last kernel, [33..64) scratch
     double* d_h_out32 = nullptr;    // device-side address of h_out32
     unsigned long long host_seq = 0;
+    bool exchange_in_fit = true;    // option "exchange_in_fit" / SRL_EXCHANGE_IN_FIT: multi-GPU, k1_fit runs the exchange when it flagged nothing
     bool mapped_result = true;      // option "mapped_result": read a pass's sums through the mapped buffer (default) or by memcpy + sync
     long long* d_k2_state = nullptr;
     unsigned long long* d_stats = nullptr;   // 4 counters
