@@ -282,6 +282,9 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     ms_res, k1_ms, k1_n, launches = timed(step_resident, True)
+    step_cycles = L.ctx.counter("iekf_step_cycles_avg")
+    loop_on_device = bool(L.ctx.counter("device_loop_active"))
+    stage_cycles = [L.ctx.counter(f"iekf_stage_{i}") for i in range(8)]
     ms_e2e, _, _, _ = timed(step_e2e, False)
     clk = clocks.stop()   # sampled over both timed regions
 
@@ -393,7 +396,10 @@ def main():
                                       "note": "this rank's per-step CUDA-event times; ms_per_step is their mean (max over ranks)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,
                         "h2d_bytes_per_step": int(args.points * 24), "d2h_bytes_per_step": int(args.points * 24 + N_PASSES * 256)},
-                "roofline": roofline}
+                "roofline": roofline,
+                "iekf_step": {"where": "device (persistent ESIKF block, srl_iekf.cu)" if loop_on_device else "host (srl_iekf_step)",
+                              "sm_cycles_sums_to_pose": step_cycles,
+                              "sm_cycles_to_stage": dict(zip(["-", "M", "inverse6", "d_x", "guard", "observe_quat", "observe_g", "post_jac"], stage_cycles))}}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         if streaming is not None:

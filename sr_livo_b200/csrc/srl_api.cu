@@ -116,6 +116,22 @@ static int pass_grid(srl_ctx* ctx, long long n, int K, int nb) {
 
 using namespace srl;
 
+// The device-resident loop needs the persistent ESIKF block and the pass kernels to run at the same time.  Tools that
+// serialise kernels (ncu, CUDA_LAUNCH_BLOCKING=1) make that impossible: probe once per ctx and fall back to the
+// host-driven loop (same kernels, srl_iekf_step on the host) instead of timing out.
+static bool device_loop_usable(srl_ctx* ctx) {
+    if (!ctx->device_loop) return false;
+    if (ctx->concurrent_kernels < 0) {
+        bool ok = false;
+        cudaSetDevice(ctx->device);
+        int* d_probe = reinterpret_cast<int*>(ctx->d_stats + 4);   // two spare words behind the counters
+        if (probe_concurrent_kernels(ctx->loop_stream, ctx->stream, d_probe, &ok) != cudaSuccess) { cudaGetLastError(); ok = false; }
+        ctx->concurrent_kernels = ok ? 1 : 0;
+    }
+    return ctx->concurrent_kernels == 1;
+}
+
+
 template <typename T>
 static int ensure_buf(srl_ctx* ctx, T** p, size_t count) {
     if (*p) return SRL_OK;
@@ -156,10 +172,54 @@ static int wait_host_result(srl_ctx* ctx, const K1Args& a) {
 
 // One pass on the ctx stream.  Fast form (k1_fast + k1_assoc on the flagged keypoints) when the configuration allows
 // it, k1_assoc alone otherwise (nb = 2, K != 20, residual cap, forced exact selection).
-static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug) {
+static bool pass_is_fast(const srl_ctx* ctx, const K1Args& a) {
+    return !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
+}
+// Everything a pass needs besides its kernel launches: buffers, the sweep's Morton order, cleared flags / candidate rows,
+// constant tables and (once per ctx) the kernels themselves.  Idempotent.  The device-resident loop calls it BEFORE it
+// launches the persistent ESIKF block: an allocation, a module load (CUDA loads kernels lazily, and loading waits for
+// running kernels) or a synchronous copy issued while that block spins would deadlock against it.
+static int prepare_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a) {
+    if (!ctx->kernels_preloaded) {
+        SRL_CUDA(ctx, preload_fast_kernels(ctx->device));
+        SRL_CUDA(ctx, preload_assoc_kernels(ctx->device, a.c.K));
+        ctx->kernels_preloaded = true;
+    }
+    if (!pass_is_fast(ctx, a)) return SRL_OK;
+    int rc;
+    if ((rc = ensure_buf(ctx, &sw->d_order, sw->capacity)) != SRL_OK) return rc;
+    if ((rc = ensure_buf(ctx, &sw->d_flags, sw->capacity)) != SRL_OK) return rc;
+    if (!sw->order_valid && sw->n > 0) {
+        size_t need = 0;
+        sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, nullptr, 0, &need, ctx->stream);
+        if ((rc = ensure_scratch(ctx, need)) != SRL_OK) return rc;
+        SRL_CUDA(ctx, sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, ctx->d_scratch, ctx->scratch_bytes, &need, ctx->stream));
+        sw->order_valid = true;
+        ctx->launches += 1;
+    }
+    // k1_scan / k1_fast write the flag of every keypoint of their range in every pass; the fallback launch walks the
+    // flags of the whole sweep, so the keypoints outside this rank's range need zeros once per (upload, shard)
+    if (!sw->flags_clean) {
+        if (sw->n) SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
+        sw->flags_clean = true;
+    }
+    const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
+    if (split && !sw->d_cand_rows) {   // k1_fit loads whole rows and uses only the slots k1_scan filled: start from defined memory
+        if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
+        SRL_CUDA(ctx, cudaMemsetAsync(sw->d_cand_rows, 0, (sw->capacity * (size_t)24 + 8) * sizeof(unsigned), ctx->stream));
+    }
+    return SRL_OK;
+}
+
+static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug, bool own_timing = true) {
     const long long n = a.k_end - a.k_begin;
-    const bool fast = !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
-    if (ctx->timing) {
+    const bool fast = pass_is_fast(ctx, a);
+    const bool timing = ctx->timing && own_timing;
+    {
+        const int rc = prepare_pass(ctx, sw, a);
+        if (rc != SRL_OK) return rc;
+    }
+    if (timing) {
         ctx->ev_cur ^= 1;
         timing_collect_pair(ctx, ctx->ev_cur);   // the pair used two passes ago
         cudaEventRecord(ctx->ev0[ctx->ev_cur], ctx->stream);
@@ -168,17 +228,6 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), debug, ctx->device, ctx->stream));
         ctx->launches += 1;
     } else {
-        int rc;
-        if ((rc = ensure_buf(ctx, &sw->d_order, sw->capacity)) != SRL_OK) return rc;
-        if ((rc = ensure_buf(ctx, &sw->d_flags, sw->capacity)) != SRL_OK) return rc;
-        if (!sw->order_valid) {
-            size_t need = 0;
-            sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, nullptr, 0, &need, ctx->stream);
-            if ((rc = ensure_scratch(ctx, need)) != SRL_OK) return rc;
-            SRL_CUDA(ctx, sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, ctx->d_scratch, ctx->scratch_bytes, &need, ctx->stream));
-            sw->order_valid = true;
-            ctx->launches += 1;
-        }
         FastArgs f;
         std::memset(&f, 0, sizeof(f));
         f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
@@ -186,14 +235,9 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
+        f.dev = a.dev; f.pose_ticket = a.pose_ticket; f.end_ticket = a.end_ticket; f.wait_pose = a.wait_pose;
         const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
-        // k1_scan writes the flag of every keypoint of its range; otherwise (k1_fast, or a shard of the sweep) clear them
-        if (!(split && a.k_begin == 0 && a.k_end == (long long)sw->n)) SRL_CUDA(ctx, cudaMemsetAsync(sw->d_flags, 0, sw->n, ctx->stream));
         if (split) {
-            if (!sw->d_cand_rows) {   // k1_fit loads whole rows and uses only the slots k1_scan filled: start from defined memory
-                if ((rc = ensure_buf(ctx, &sw->d_cand_rows, sw->capacity * (size_t)24 + 8)) != SRL_OK) return rc;
-                SRL_CUDA(ctx, cudaMemsetAsync(sw->d_cand_rows, 0, (sw->capacity * (size_t)24 + 8) * sizeof(unsigned), ctx->stream));
-            }
             f.cand_rows = sw->d_cand_rows; f.scan_count = ctx->d_scan_count;
             // k1_fit publishes the result itself when nothing was flagged (multi-GPU: after running the exchange, option
             // exchange_in_fit); the fallback launch then runs off the host's critical path and republishes the same values
@@ -216,7 +260,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug)
         SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream));
         ctx->launches += 2;
     }
-    if (ctx->timing) { cudaEventRecord(ctx->ev1[ctx->ev_cur], ctx->stream); ctx->ev_pending[ctx->ev_cur] = true; }
+    if (timing) { cudaEventRecord(ctx->ev1[ctx->ev_cur], ctx->stream); ctx->ev_pending[ctx->ev_cur] = true; }
     return SRL_OK;
 }
 
@@ -246,16 +290,23 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
               cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
-              cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_stats, 6 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_fast_out, 32 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_scan_count, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMemset(ctx->d_scan_count, 0, sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->d_stats, 0, 6 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaHostAlloc(&ctx->h_out32, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer(&ctx->d_h_out32, ctx->h_out32, 0) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->loop_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&ctx->d_iekf, sizeof(IekfDev)) == cudaSuccess &&
+              cudaMemset(ctx->d_iekf, 0, sizeof(IekfDev)) == cudaSuccess &&
+              cudaHostAlloc(&ctx->h_iekf, sizeof(IekfHostOut), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer(&ctx->d_h_iekf, ctx->h_iekf, 0) == cudaSuccess &&
               cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)) == cudaSuccess;
     if (!ok) { srl_ctx_destroy(ctx); cudaGetLastError(); return SRL_CUDA_ERROR; }
     std::memset(ctx->h_out32, 0, 64 * sizeof(double));
+    std::memset(ctx->h_iekf, 0, sizeof(IekfHostOut));
+    if (const char* e = getenv("SRL_DEVICE_LOOP")) ctx->device_loop = atoi(e) != 0;
     if (const char* e = getenv("SRL_MAPPED_RESULT")) ctx->mapped_result = atoi(e) != 0;   // A/B switch (bench runs)
     if (const char* e = getenv("SRL_EXCHANGE_IN_FIT")) ctx->exchange_in_fit = atoi(e) != 0;
     *out = ctx;
@@ -266,8 +317,12 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->loop_stream) { cudaStreamSynchronize(ctx->loop_stream); cudaStreamDestroy(ctx->loop_stream); }
     cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out); cudaFree(ctx->d_scan_count);
-    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_iekf);
+    if (ctx->h_iekf) cudaFreeHost(ctx->h_iekf);
+    for (auto& e : ctx->loop_ev0) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->loop_ev1) if (e) cudaEventDestroy(e);
     if (ctx->h_out32) cudaFreeHost(ctx->h_out32);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2; ++i) { if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]); if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]); }
@@ -293,6 +348,7 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
         return SRL_OK;
     }
     if (n == "mapped_result") { ctx->mapped_result = value != 0; return SRL_OK; }
+    if (n == "device_loop") { ctx->device_loop = value != 0; return SRL_OK; }
     if (n == "exchange_in_fit") { ctx->exchange_in_fit = value != 0; return SRL_OK; }
     if (n == "split_lanes_per_keypoint") {
         if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");
@@ -334,6 +390,13 @@ int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value) {
         return SRL_OK;
     }
     if (n == "kernel_launches") { *value = ctx->launches; return SRL_OK; }
+    if (n.rfind("iekf_stage_", 0) == 0 && n.size() == 12 && n[11] >= '0' && n[11] <= '7') { *value = ctx->h_iekf->stage_cycles[n[11] - '0']; return SRL_OK; }
+    if (n == "device_loop_active") { *value = device_loop_usable(ctx) ? 1 : 0; return SRL_OK; }
+    if (n == "iekf_step_cycles_avg") {   // device-resident loop: average SM clock ticks of one ESIKF step (resets on read)
+        *value = ctx->step_cycles_n ? (int64_t)(ctx->step_cycles_sum / (double)ctx->step_cycles_n) : 0;
+        ctx->step_cycles_sum = 0.0; ctx->step_cycles_n = 0;
+        return SRL_OK;
+    }
     return set_err(ctx, SRL_BAD_ARG, "unknown counter " + n);
 }
 int srl_ctx_set_timing(srl_ctx* ctx, int enable) {
@@ -393,7 +456,7 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
         SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, pinned ? raw_xyz : static_cast<const double*>(ctx->h_pinned), n * 3 * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
     return SRL_OK;
 }
 int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
@@ -401,12 +464,12 @@ int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     srl_ctx* ctx = s->ctx;
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false;
+    s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
     return SRL_OK;
 }
 int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
     if (!s || begin > end || end > s->n) return SRL_BAD_ARG;
-    s->shard_begin = begin; s->shard_end = end;
+    s->shard_begin = begin; s->shard_end = end; s->flags_clean = false;
     return SRL_OK;
 }
 
@@ -481,8 +544,10 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
         a.status = sw->d_status;
     }
     double* h = ctx->h_out32;
-    if (n <= 0) {
-        std::memset(h, 0, 32 * sizeof(double));
+    double zero32[32];
+    if (n <= 0) {   // an empty shard sums to zero; the mapped buffer may still be written by the previous pass's fallback launch
+        std::memset(zero32, 0, sizeof(zero32));
+        h = zero32;
     } else if (!cap_mode) {
         arm_host_result(ctx, a);
         if ((rc = launch_pass(ctx, sw, a, debug)) != SRL_OK) return rc;
@@ -541,10 +606,112 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
 }
 
 // ---- iterated update ---------------------------------------------------------------------------------------
+// Row N1: the whole updateIEKF loop enqueued at once.  Pass 0 takes its pose by value; every later pass reads the pose
+// k_iekf_step left in HBM and leaves immediately once the loop has ended on the device.  One host wait at the end, on
+// the sequence flag the finishing step writes into mapped pinned memory after the state, the trace and the summary.
+static int update_iekf_device(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sw, srl_eskf_state* eskf, double frame_q[4],
+                              double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
+                              const srl_icp_params* prm, srl_iekf_summary* summary) {
+    srl_frame fr;
+    std::memcpy(fr.q_cur, frame_q, sizeof(fr.q_cur));
+    std::memcpy(fr.t_cur, frame_t, sizeof(fr.t_cur));
+    std::memcpy(fr.t_last, t_last, sizeof(fr.t_last));
+    std::memcpy(fr.R_il, R_il, sizeof(fr.R_il));
+    std::memcpy(fr.t_il, t_il, sizeof(fr.t_il));
+    K1Args a;
+    int rc = fill_k1_args(ctx, map, sw, &fr, prm, a);
+    if (rc != SRL_OK) return rc;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    srl_iekf_iter it;
+    if ((rc = srl_iekf_begin(eskf, prm, &it)) != SRL_OK) return rc;
+    const int n_pass = it.max_num_iter + 1;                          // i = -1 .. max_iter - 1 (src/optimize.cpp:147)
+    if (n_pass > kLoopMaxPasses) return set_err(ctx, SRL_BAD_ARG, "num_iters_icp > 39 is not supported by the device-resident loop");
+    if (comm) {
+        a.comm.world = comm->world; a.comm.rank = comm->rank; a.comm.seq = comm->d_seq;
+        for (int r = 0; r < comm->world; ++r) a.comm.mail[r] = comm->peer[r];
+    }
+    static_assert(sizeof(IekfLoopArgs) <= 4000, "the loop kernel's arguments must fit the 4 KB kernel parameter space");
+    IekfLoopArgs la;
+    std::memset(&la, 0, sizeof(la));
+    IekfInit& init = la.init;
+    init.eskf = *eskf;
+    std::memcpy(init.frame_q, frame_q, sizeof(init.frame_q));
+    std::memcpy(init.frame_t, frame_t, sizeof(init.frame_t));
+    init.pc0 = a.c;
+    init.laser_cov = prm->laser_point_cov; init.thr_t = prm->threshold_translation_norm; init.thr_r = prm->threshold_orientation_norm;
+    init.max_iter = it.max_num_iter; init.frame_id = prm->frame_id; init.min_neighbors = prm->min_number_neighbors;
+    la.dev = ctx->d_iekf; la.host_out = ctx->d_h_iekf; la.host_seq = ++ctx->iekf_seq;
+    la.base = ctx->loop_base; ctx->loop_base += 64;
+    la.world = comm ? comm->world : 1; la.n_pass = n_pass;
+    const IekfLoopArgs& st = la;
+    if ((rc = prepare_pass(ctx, sw, a)) != SRL_OK) return rc;
+    if (ctx->timing && !ctx->loop_ev0[0])
+        for (int i = 0; i < kLoopMaxPasses; ++i) { SRL_CUDA(ctx, cudaEventCreate(&ctx->loop_ev0[i])); SRL_CUDA(ctx, cudaEventCreate(&ctx->loop_ev1[i])); }
+    // the persistent ESIKF block first (side stream): it is resident before any pass kernel can wait for it
+    SRL_CUDA(ctx, launch_iekf_loop(la, ctx->loop_stream));
+    ctx->launches += 1;
+    for (int p = 0; p < n_pass; ++p) {
+        K1Args ap = a;
+        ap.dev = ctx->d_iekf;
+        ap.pose_ticket = la.base + (unsigned long long)p;
+        ap.end_ticket = la.base + 63ull;
+        ap.wait_pose = p ? 1 : 0;                                    // pass 0: pose by value
+        if (ctx->timing) cudaEventRecord(ctx->loop_ev0[p], ctx->stream);
+        if ((rc = launch_pass(ctx, sw, ap, false, false)) != SRL_OK) return rc;
+        if (ctx->timing) cudaEventRecord(ctx->loop_ev1[p], ctx->stream);
+    }
+    // the one host wait of the sweep
+    volatile unsigned long long* flag = &ctx->h_iekf->seq;
+    for (unsigned long long spins = 1;; ++spins) {
+        if (*flag == st.host_seq) break;
+        if ((spins & 0x3fffull) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->loop_stream);   // the ESIKF block leaves right after publishing
+            if (q == cudaSuccess) {
+                if (*flag == st.host_seq) break;
+                return set_err(ctx, SRL_CUDA_ERROR, "the device-resident updateIEKF loop finished without publishing its result");
+            }
+            if (q != cudaErrorNotReady) return cuda_fail(ctx, q, "cudaStreamQuery while waiting for the updateIEKF loop");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const IekfHostOut* h = ctx->h_iekf;
+    const int passes = h->passes_run;
+    if (ctx->timing) {   // the passes that ran have finished (their events precede the step that published)
+        for (int p = 0; p < passes && p < n_pass; ++p) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->loop_ev0[p], ctx->loop_ev1[p]) == cudaSuccess) { ctx->k1_ms += ms; ctx->k1_launches += 1; }
+            else cudaGetLastError();
+        }
+    }
+    *eskf = h->eskf;
+    std::memcpy(frame_q, h->frame_q, sizeof(h->frame_q));
+    std::memcpy(frame_t, h->frame_t, sizeof(h->frame_t));
+    std::memcpy(ctx->h_out32, h->sums, 32 * sizeof(double));
+    if (summary) {
+        std::memset(summary, 0, sizeof(*summary));
+        summary->success = h->status == SRL_TOO_FEW_RESIDUALS ? 0 : 1;
+        summary->passes_run = passes;
+        summary->num_residuals_used = h->num_residuals_used;
+        summary->converged = h->converged;
+        std::memcpy(summary->trace, h->trace, sizeof(double) * 24 * (size_t)std::min(passes, 32));
+    }
+    for (int p = 0; p < passes && p < kLoopMaxPasses; ++p) { ctx->step_cycles_sum += (double)h->step_cycles[p]; ctx->step_cycles_n += 1; }
+    switch (h->status) {
+        case SRL_OK: return SRL_OK;
+        case SRL_TOO_FEW_RESIDUALS: return set_err(ctx, SRL_TOO_FEW_RESIDUALS, "[Optimization] Error : not enough keypoints selected in ct-icp !");
+        case SRL_NAN_PLANARITY: return set_err(ctx, SRL_NAN_PLANARITY, "NaN planarity (the reference throws at src/optimize.cpp:348)");
+        case SRL_SINGULAR: return set_err(ctx, SRL_SINGULAR, "the 6x6 system of the ESIKF gain is singular (src/optimize.cpp:234,237)");
+        case SRL_COMM_ERROR: return set_err(ctx, SRL_COMM_ERROR, "peer exchange timed out (a rank did not reach this pass)");
+        default: return set_err(ctx, h->status, "device-resident updateIEKF loop failed");
+    }
+}
+
 int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sw, srl_eskf_state* eskf, double frame_q[4], double frame_t[3],
                     const double t_last[3], const double R_il[9], const double t_il[3], const srl_icp_params* prm,
                     srl_iekf_summary* summary) {
     if (!ctx || !eskf || !frame_q || !frame_t || !t_last || !R_il || !t_il || !prm) return SRL_BAD_ARG;
+    if (device_loop_usable(ctx) && map && sw && !((long long)prm->max_num_residuals < (long long)(sw->shard_end - sw->shard_begin)))
+        return update_iekf_device(ctx, nullptr, map, sw, eskf, frame_q, frame_t, t_last, R_il, t_il, prm, summary);
     srl_iekf_iter it;
     int rc = srl_iekf_begin(eskf, prm, &it);
     if (rc != SRL_OK) return rc;
@@ -587,7 +754,9 @@ int srl_comm_create(srl_ctx* ctx, int rank, int world, srl_comm** out) {
     cudaError_t e = cudaMalloc(&c->d_mail, sizeof(Mailbox));
     if (e != cudaSuccess) { delete c; return cuda_fail(ctx, e, "srl_comm_create/cudaMalloc"); }
     e = cudaMemset(c->d_mail, 0, sizeof(Mailbox));
-    if (e != cudaSuccess) { cudaFree(c->d_mail); delete c; return cuda_fail(ctx, e, "srl_comm_create/cudaMemset"); }
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_seq, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->d_seq, 0, sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(c->d_mail); cudaFree(c->d_seq); delete c; return cuda_fail(ctx, e, "srl_comm_create/cudaMemset"); }
     c->peer[rank] = c->d_mail;
     c->connected = (world == 1);
     *out = c;
@@ -598,7 +767,7 @@ void srl_comm_destroy(srl_comm* c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     for (int r = 0; r < c->world; ++r) if (c->opened[r]) cudaIpcCloseMemHandle(c->peer[r]);
-    cudaFree(c->d_mail);
+    cudaFree(c->d_mail); cudaFree(c->d_seq);
     delete c;
 }
 int srl_comm_export(srl_comm* c, void* handle64) {
@@ -632,6 +801,11 @@ int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* 
                          const srl_icp_params* prm, srl_iekf_summary* summary) {
     if (!ctx || !comm || !eskf || !frame_q || !frame_t || !t_last || !R_il || !t_il || !prm) return SRL_BAD_ARG;
     if (comm->ctx != ctx || !comm->connected) return set_err(ctx, SRL_COMM_ERROR, "srl_comm is not connected");
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (map && sw && (long long)prm->max_num_residuals < (long long)sw->n)
+        return set_err(ctx, SRL_BAD_ARG, "the sharded update does not implement the max_num_residuals cap");
+    if (device_loop_usable(ctx) && map && sw)
+        return update_iekf_device(ctx, comm, map, sw, eskf, frame_q, frame_t, t_last, R_il, t_il, prm, summary);
     srl_iekf_iter it;
     int rc = srl_iekf_begin(eskf, prm, &it);
     if (rc != SRL_OK) return rc;
@@ -650,7 +824,7 @@ int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* 
         const long long n = a.k_end - a.k_begin;
         if ((long long)prm->max_num_residuals < (long long)sw->n)
             return set_err(ctx, SRL_BAD_ARG, "the sharded update does not implement the max_num_residuals cap");
-        a.comm.world = comm->world; a.comm.rank = comm->rank; a.comm.seq = ++comm->seq;
+        a.comm.world = comm->world; a.comm.rank = comm->rank; a.comm.seq = comm->d_seq;
         for (int r = 0; r < comm->world; ++r) a.comm.mail[r] = comm->peer[r];
         (void)n;
         arm_host_result(ctx, a);

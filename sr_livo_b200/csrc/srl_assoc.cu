@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const PassConst& c = A.c;
+    __shared__ PassConst s_c;
+    if (!load_pass_const(A.dev, A.wait_pose, A.pose_ticket, A.end_ticket, A.c, s_c)) return;   // device-resident loop already ended: nothing to do
+    const PassConst& c = s_c;
     const int K = c.K;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
@@ -298,12 +300,13 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
     if (A.only_flagged && A.stats && __ldcg(A.stats + 2) == 0ull) {
         if (blockIdx.x == 0 && warp == 0) {
             double tot = A.prev_out32 ? A.prev_out32[lane] : 0.0;
-            const bool exchanged = __ldcg(A.stats + 3) != 0ull;   // k1_fit already ran the exchange (and published)
+            const bool finalised = __ldcg(A.stats + 3) != 0ull;   // k1_fit already finalised the pass (exchange, publication)
             __syncwarp();
-            if (A.comm.world > 1 && !exchanged) tot = comm_exchange(A.comm, tot, lane);
-            if (lane == 0 && exchanged) A.stats[3] = 0ull;
+            if (A.comm.world > 1 && !finalised) tot = comm_exchange(A.comm, tot, lane);
+            if (lane == 0 && finalised) A.stats[3] = 0ull;
             A.out32[lane] = tot;
             publish_to_host(A, tot, lane);
+            if (!finalised) publish_sums_to_loop(A.dev, A.pose_ticket, tot, lane);
         }
         return;
     }
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
             A.out32[lane] = tot;
             if (lane == 0) { *A.ticket = 0u; if (A.only_flagged && A.stats) A.stats[2] = 0ull; }
             publish_to_host(A, tot, lane);
+            publish_sums_to_loop(A.dev, A.pose_ticket, tot, lane);
         }
     }
 }
@@ -705,6 +709,19 @@ cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStr
     if (e != cudaSuccess) return e;
     fn<<<grid, kK1Threads, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t preload_assoc_kernels(int device, int K) {
+    upload_offsets(device);
+    cudaFuncAttributes at;
+    const size_t smem = k1_smem_bytes(K > 0 ? K : 20);
+    for (int nb = 1; nb <= 2; ++nb) {
+        K1Fn fn = pick_k1(nb, false);
+        cudaError_t e = cudaFuncGetAttributes(&at, fn);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 int k1_max_blocks_per_sm(int K, int nb) {

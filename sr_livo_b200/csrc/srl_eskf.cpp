@@ -11,120 +11,11 @@
 #include <cstring>
 
 #include "../../include/srlivo_b200.h"
-#include "srl_math.cuh"
+#include "srl_eskf_math.cuh"
 
 namespace {
 
-constexpr int N = 17;
-constexpr double kTheta = 1e-4;   // THETA_THRESHOLD, include/utility.h:27
-
-template <int R, int C>
-struct Mat {
-    double a[R * C];
-    double& operator()(int r, int c) { return a[r * C + c]; }
-    double operator()(int r, int c) const { return a[r * C + c]; }
-    static Mat zero() { Mat m; std::memset(m.a, 0, sizeof(m.a)); return m; }
-    static Mat identity() { Mat m = zero(); for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = 1.0; return m; }
-};
-template <int R, int K, int C>
-Mat<R, C> operator*(const Mat<R, K>& A, const Mat<K, C>& B) {
-    Mat<R, C> out;
-    for (int r = 0; r < R; ++r)
-        for (int c = 0; c < C; ++c) {
-            double s = 0.0;
-            for (int k = 0; k < K; ++k) s += A(r, k) * B(k, c);
-            out(r, c) = s;
-        }
-    return out;
-}
-template <int R, int C>
-Mat<C, R> tr(const Mat<R, C>& A) {
-    Mat<C, R> t;
-    for (int r = 0; r < R; ++r) for (int c = 0; c < C; ++c) t(c, r) = A(r, c);
-    return t;
-}
-template <int R, int C>
-Mat<R, C> operator+(const Mat<R, C>& A, const Mat<R, C>& B) { Mat<R, C> o; for (int i = 0; i < R * C; ++i) o.a[i] = A.a[i] + B.a[i]; return o; }
-template <int R, int C>
-Mat<R, C> operator-(const Mat<R, C>& A, const Mat<R, C>& B) { Mat<R, C> o; for (int i = 0; i < R * C; ++i) o.a[i] = A.a[i] - B.a[i]; return o; }
-template <int R, int C>
-Mat<R, C> operator*(double s, const Mat<R, C>& A) { Mat<R, C> o; for (int i = 0; i < R * C; ++i) o.a[i] = s * A.a[i]; return o; }
-
-typedef Mat<3, 1> V3;
-typedef Mat<3, 3> M3;
-
-V3 v3(const double* p) { V3 v; v.a[0] = p[0]; v.a[1] = p[1]; v.a[2] = p[2]; return v; }
-double nrm(const V3& v) { return std::sqrt(v.a[0] * v.a[0] + (v.a[1] * v.a[1] + v.a[2] * v.a[2])); }
-V3 unit(const V3& v) { double n2 = v.a[0] * v.a[0] + (v.a[1] * v.a[1] + v.a[2] * v.a[2]); if (n2 > 0) { double n = std::sqrt(n2); V3 o; for (int i = 0; i < 3; ++i) o.a[i] = v.a[i] / n; return o; } return v; }
-M3 hat(const V3& v) { M3 m = M3::zero(); m(0, 1) = -v.a[2]; m(0, 2) = v.a[1]; m(1, 0) = v.a[2]; m(1, 2) = -v.a[0]; m(2, 0) = -v.a[1]; m(2, 1) = v.a[0]; return m; }
-
-struct Q { double x, y, z, w; };
-double qn2(const Q& q) { return (q.x * q.x + q.z * q.z) + (q.y * q.y + q.w * q.w); }
-Q qunit(const Q& q) { double n2 = qn2(q); if (n2 > 0) { double n = std::sqrt(n2); return {q.x / n, q.y / n, q.z / n, q.w / n}; } return q; }
-Q qmul(const Q& a, const Q& b) {
-    return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
-            a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
-}
-Q qinv(const Q& q) { double n2 = qn2(q); if (n2 > 0) return {-q.x / n2, -q.y / n2, -q.z / n2, q.w / n2}; return {0, 0, 0, 0}; }
-M3 qrot(const Q& q) { double qq[4] = {q.x, q.y, q.z, q.w}; M3 R; srl::quat_to_rot(qq, R.a); return R; }
-Q rot2q(const M3& m) {   // Eigen's matrix -> quaternion
-    double q[4];
-    double t = m(0, 0) + m(1, 1) + m(2, 2);
-    if (t > 0) {
-        t = std::sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t;
-        q[0] = (m(2, 1) - m(1, 2)) * t; q[1] = (m(0, 2) - m(2, 0)) * t; q[2] = (m(1, 0) - m(0, 1)) * t;
-    } else {
-        int i = 0;
-        if (m(1, 1) > m(0, 0)) i = 1;
-        if (m(2, 2) > m(i, i)) i = 2;
-        int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0); q[i] = 0.5 * t; t = 0.5 / t;
-        q[3] = (m(k, j) - m(j, k)) * t; q[j] = (m(j, i) + m(i, j)) * t; q[k] = (m(k, i) + m(i, k)) * t;
-    }
-    return {q[0], q[1], q[2], q[3]};
-}
-// numType::rotationToSo3 — normalizeR then acos, not clamped (include/utility.h:267-280)
-V3 log_so3(const M3& Rin) {
-    M3 R = qrot(qunit(rot2q(Rin)));
-    double th = std::acos((R(0, 0) + R(1, 1) + R(2, 2) - 1.0) / 2.0);
-    V3 a; a.a[0] = R(2, 1) - R(1, 2); a.a[1] = R(0, 2) - R(2, 0); a.a[2] = R(1, 0) - R(0, 1);
-    V3 o;
-    if (th < kTheta) for (int i = 0; i < 3; ++i) o.a[i] = a.a[i] / 2.0;
-    else for (int i = 0; i < 3; ++i) o.a[i] = th * a.a[i] / (2.0 * std::sin(th));
-    return o;
-}
-// numType::so3ToRotation (include/utility.h:282-299)
-M3 exp_so3(const V3& w) {
-    double th = nrm(w);
-    if (th < kTheta) { M3 U = hat(w); return M3::identity() + U + 0.5 * (U * U); }
-    M3 U = hat(unit(w));
-    return M3::identity() + std::sin(th) * U + (1.0 - std::cos(th)) * (U * U);
-}
-// numType::so3ToQuat (include/utility.h:301-324)
-Q exp_quat(const V3& w) {
-    double th = nrm(w);
-    if (th < kTheta) return qunit({w.a[0] / 2.0, w.a[1] / 2.0, w.a[2] / 2.0, 1.0});
-    V3 u = unit(w);
-    double s = std::sin(0.5 * th), c = std::cos(0.5 * th);
-    return qunit({u.a[0] * s, u.a[1] * s, u.a[2] * s, c});
-}
-// numType::derivativeS2 (include/utility.h:215-235)
-Mat<3, 2> s2_basis(const V3& gin) {
-    V3 g = unit(gin);
-    Mat<3, 2> B;
-    B(0, 0) = 1.0 - g.a[0] * g.a[0] / (1.0 + g.a[2]);
-    B(0, 1) = -g.a[0] * g.a[1] / (1.0 + g.a[2]);
-    B(1, 0) = B(0, 1);
-    B(1, 1) = 1.0 - g.a[1] * g.a[1] / (1.0 + g.a[2]);
-    B(2, 0) = -g.a[0];
-    B(2, 1) = -g.a[1];
-    return B;
-}
-// AngularDistance(const Vector3d&) (src/utility.cpp:146-153), degrees, acos not clamped
-double angular_distance(const V3& w) {
-    M3 R = exp_so3(w);
-    return std::acos((R(0, 0) + R(1, 1) + R(2, 2) - 1.0) / 2.0) * 180.0 / M_PI;
-}
+using namespace srl::ekf;
 
 // Matrix<double,17,17>::inverse(): LU with partial pivoting
 bool inverse17(const Mat<N, N>& A, Mat<N, N>& out) {
@@ -194,14 +85,9 @@ void srl_icp_params_r3live(srl_icp_params* p) {
 int srl_eskf_observe(srl_eskf_state* s, const double d_x[17]) {
     if (!s || !d_x) return SRL_BAD_ARG;
     for (int i = 0; i < 3; ++i) s->p[i] += d_x[i];
-    Q q = qunit(qmul({s->q[0], s->q[1], s->q[2], s->q[3]}, exp_quat(v3(d_x + 3))));
-    s->q[0] = q.x; s->q[1] = q.y; s->q[2] = q.z; s->q[3] = q.w;
+    observe_quat(s->q, d_x + 3, s->q);
     for (int i = 0; i < 3; ++i) { s->v[i] += d_x[6 + i]; s->ba[i] += d_x[9 + i]; s->bg[i] += d_x[12 + i]; }
-    V3 g = v3(s->g);
-    Mat<3, 2> B = s2_basis(g);
-    Mat<2, 1> dg; dg.a[0] = d_x[15]; dg.a[1] = d_x[16];
-    V3 gn = exp_so3(B * dg) * g;
-    for (int i = 0; i < 3; ++i) s->g[i] = gn.a[i];
+    observe_gravity(s->g, d_x[15], d_x[16], s->g);
     return SRL_OK;
 }
 
@@ -230,29 +116,13 @@ int srl_iekf_step(srl_iekf_iter* it, const srl_normal_eq* ne, const srl_icp_para
         dx[9 + i] = eskf->ba[i] - pr.ba[i];
         dx[12 + i] = eskf->bg[i] - pr.bg[i];
     }
-    Q dq = qmul(qinv({pr.q[0], pr.q[1], pr.q[2], pr.q[3]}), {eskf->q[0], eskf->q[1], eskf->q[2], eskf->q[3]});
-    V3 d_so3 = log_so3(qrot(dq));
+    V3 d_so3; M3 J_so3;
+    boxminus_so3(pr.q, eskf->q, d_so3, J_so3);                                            // :183-186, :213
     for (int i = 0; i < 3; ++i) dx[3 + i] = d_so3.a[i];
-
-    V3 gp = unit(v3(pr.g)), gc = unit(v3(eskf->g));
-    V3 cr; cr.a[0] = gp.a[1] * gc.a[2] - gp.a[2] * gc.a[1]; cr.a[1] = gp.a[2] * gc.a[0] - gp.a[0] * gc.a[2]; cr.a[2] = gp.a[0] * gc.a[1] - gp.a[1] * gc.a[0];
-    double dot = gp.a[0] * gc.a[0] + (gp.a[1] * gc.a[1] + gp.a[2] * gc.a[2]);
-    M3 R_dg;
-    if (std::fabs(1.0 - dot) < 1e-6) R_dg = M3::identity();
-    else {
-        M3 sk = hat(cr);
-        M3 sk2 = sk * sk;
-        const double den = cr.a[0] * cr.a[0] + cr.a[1] * cr.a[1] + cr.a[2] * cr.a[2];
-        R_dg = M3::identity() + sk;
-        for (int e = 0; e < 9; ++e) R_dg.a[e] += sk2.a[e] * (1.0 - dot) / den;   // :197-198
-    }
-    V3 so3_dg = log_so3(R_dg);
-    Mat<3, 2> Bp = s2_basis(v3(pr.g));
-    Mat<2, 1> d_g = tr(Bp) * so3_dg;
+    Mat<2, 1> d_g; Mat<2, 2> J_s2;
+    boxminus_s2(pr.g, eskf->g, d_g, J_s2);                                                // :188-211, :214
     dx[15] = d_g.a[0]; dx[16] = d_g.a[1];
 
-    M3 J_so3 = M3::identity() - 0.5 * hat(d_so3);                                         // :213
-    Mat<2, 2> J_s2 = Mat<2, 2>::identity() + 0.5 * (tr(Bp) * (hat(so3_dg) * Bp));         // :214
     double dx_new[N];
     std::memcpy(dx_new, dx, sizeof(dx));
     { V3 t = J_so3 * d_so3; for (int i = 0; i < 3; ++i) dx_new[3 + i] = t.a[i]; }         // :217
@@ -304,10 +174,7 @@ int srl_iekf_step(srl_iekf_iter* it, const srl_normal_eq* ne, const srl_icp_para
                      angular_distance(dth) < prm->threshold_orientation_norm;             // :265-270
     if (converged || i_pass == it->max_num_iter - 1) {                                    // :272
         Mat<N, N> P_new = P;
-        Mat<3, 2> Bb = s2_basis(g_before);
-        Mat<2, 1> dg2; dg2.a[0] = d_x[15]; dg2.a[1] = d_x[16];
-        J_so3 = M3::identity() - 0.5 * hat(dth);                                          // :278
-        J_s2 = Mat<2, 2>::identity() + 0.5 * (tr(Bb) * (hat(Bb * dg2) * Bb));             // :279
+        posterior_jacobians(d_x + 3, g_before.a, d_x[15], d_x[16], J_so3, J_s2);          // :278-279
         rows_so3(P_new, P, J_so3, N);                                                     // :281-282
         rows_s2(P_new, P, J_s2, N);                                                       // :284-285
         cols_so3(P_new, P, J_so3); cols_so3(P, P, J_so3);                                 // :287-291

@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
     constexpr int KPW = 32 / LPK;                 // keypoints per warp
     const int sub = lane % LPK;                   // this lane's share of every voxel's candidates
     const unsigned gmask = (LPK == 1) ? (1u << lane) : (((1u << LPK) - 1u) << (lane & ~(LPK - 1)));   // lanes of my keypoint
-    const PassConst& c = A.c;
+    __shared__ PassConst s_c;
+    if (!load_pass_const(A.dev, A.wait_pose, A.pose_ticket, A.end_ticket, A.c, s_c)) return;   // device-resident loop already ended: nothing to do
+    const PassConst& c = s_c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
     const int V = W * W * W;
@@ -460,7 +462,9 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
     const int gshift = lane & ~(LPK - 1);          // first lane of my group
     // (all warp-level primitives below run with the full mask at warp-uniform points: a per-group member mask would make
     //  the compiler serialise them over the 32 / LPK distinct masks)
-    const PassConst& c = A.c;
+    __shared__ PassConst s_c;
+    if (!load_pass_const(A.dev, A.wait_pose, A.pose_ticket, A.end_ticket, A.c, s_c)) return;   // device-resident loop already ended: nothing to do
+    const PassConst& c = s_c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
     const int V = W * W * W;
@@ -764,7 +768,9 @@ template <bool DEBUG, int MINB>
 __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const PassConst& c = A.c;
+    __shared__ PassConst s_c;
+    if (!load_pass_const(A.dev, A.wait_pose, A.pose_ticket, A.end_ticket, A.c, s_c)) return;   // device-resident loop already ended: nothing to do
+    const PassConst& c = s_c;
     const int nb = c.nb;
     const int W = 2 * nb + 1;
 
@@ -962,11 +968,12 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
             bool final_here = none_flagged && A.comm.world <= 1;
             if (none_flagged && A.comm.world > 1 && A.exchange_in_fit) {
                 tot = comm_exchange(A.comm, tot, lane);
-                if (lane == 0) A.stats[3] = 1ull;   // tells the fallback launch not to exchange again
                 final_here = true;
             }
+            if (final_here && lane == 0) A.stats[3] = 1ull;   // tells the fallback launch that the pass is already finalised
             A.out32[lane] = tot;
             if (lane == 0) *A.ticket = 0u;
+            if (final_here) publish_sums_to_loop(A.dev, A.pose_ticket, tot, lane);   // device-resident loop: the ESIKF block takes over
             if (A.host_out && final_here) {
                 A.host_out[lane] = tot;
                 __threadfence_system();
@@ -1110,6 +1117,19 @@ cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool d
     else fit = fit_minb == 6 ? k1_fit<false, 6> : (fit_minb == 4 ? k1_fit<false, 4> : k1_fit<false, 5>);
     fit<<<(unsigned)grid_b, kFastThreads, 0, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t preload_fast_kernels(int device) {
+    upload_fast_offsets(device);
+    cudaFuncAttributes at;
+    const FastFn fns[] = {k1_scan<4, 14, 8>, k1_scan<4, 14, 6>, k1_scan<2, 20, 8>, k1_scan<2, 20, 6>,
+                          k1_fit<false, 4>, k1_fit<false, 5>, k1_fit<false, 6>,
+                          pick_fast_mb<false, 1>(), pick_fast_mb<false, 2>(), pick_fast_mb<false, 4>()};
+    for (FastFn fn : fns) {
+        const cudaError_t e = cudaFuncGetAttributes(&at, fn);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 int k1_fast_max_blocks_per_sm() {

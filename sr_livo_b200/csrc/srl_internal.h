@@ -26,28 +26,87 @@ struct Mailbox {
 };
 struct CommDev {              // by-value kernel argument; world <= 1 disables the exchange
     int world, rank;
-    unsigned long long seq;   // sequence number of this pass (>= 1, same on every rank)
+    unsigned long long* seq;  // device counter of the exchanges this rank has run (same on every rank: all ranks run the
+                              // same passes); the exchange of a pass uses *seq + 1 and stores it back.  Kept on the device
+                              // because the device-resident loop skips enqueued passes the host cannot know about.
     Mailbox* mail[kMaxRanks]; // mail[r] = rank r's mailbox as mapped in THIS process (mail[rank] is local memory)
 };
+
+// ---- device-resident updateIEKF loop (srl_iekf.cu, row N1) ------------------------------------------------------
+// One persistent 128-thread block per sweep (k_iekf_loop, on the ctx's side stream) runs the ESIKF algebra of every
+// pass; the pass kernels on the main stream and that block hand data to each other through HBM and three tickets:
+//   alive_seq : the block is resident (the pass kernels may spin on it without starving it)
+//   sums_seq  : ticket + 1 once the sums of the pass with that ticket are in `sums` (written by the pass's last block)
+//   pose_seq  : >= ticket once the constants of the pass with that ticket are in `pc` (written by the ESIKF block); the
+//               block stores a ticket beyond every pass of the sweep when the loop has ended (`done`)
+// ticket = base + pass number; base grows by 64 per sweep, so tickets never repeat and nothing has to be reset.
+constexpr int kLoopMaxPasses = 40;
+struct IekfDev {              // one per ctx, in HBM
+    PassConst pc;             // constants of the NEXT pass: the ESIKF block rewrites Rn, Rq, t after every observe()
+    unsigned long long alive_seq, sums_seq, pose_seq;
+    int done;                 // != 0: the loop has ended (break :309 / return :155); kernels still enqueued leave at once
+    int status;               // srl_status of the loop
+    int pass_index;           // i of the next step, starts at -1 (src/optimize.cpp:147)
+    int max_iter;
+    int passes_run, converged, num_residuals_used, frame_id;
+    int min_neighbors, pad0;
+    double laser_cov, thr_t, thr_r;
+    double sums[32];          // the (all-reduced) sums of the pass in flight
+    srl_eskf_state cur, predict;   // eskf_pro now / the snapshot of :138-143
+    double frame_q[4], frame_t[3]; // p_frame->p_state (:255-256)
+    double trace[32][24];
+    long long step_cycles[kLoopMaxPasses];   // clock64 ticks from "sums seen" to "pose published" per pass (tuning)
+    long long stage_cycles[8];               // ... and to the stages inside the last step
+};
+struct IekfInit {             // by-value argument of the loop kernel (whole argument block < 4 KB)
+    srl_eskf_state eskf;
+    double frame_q[4], frame_t[3];
+    PassConst pc0;            // pass 0 constants (also given by value to pass 0's kernels)
+    double laser_cov, thr_t, thr_r;
+    int max_iter, frame_id, min_neighbors, pad0;
+};
+struct IekfHostOut {          // mapped pinned host memory: what the loop hands back, then the sequence flag
+    srl_eskf_state eskf;
+    double frame_q[4], frame_t[3];
+    double sums[32];          // the last pass's (all-reduced) sums
+    int status, passes_run, num_residuals_used, converged;
+    double trace[32][24];
+    long long step_cycles[kLoopMaxPasses];
+    long long stage_cycles[8];
+    unsigned long long seq;
+};
+struct IekfLoopArgs {
+    IekfDev* dev;
+    IekfHostOut* host_out;    // device-side address of the mapped buffer
+    unsigned long long host_seq;
+    unsigned long long base;  // ticket of this sweep's pass 0
+    int world, n_pass;
+    IekfInit init;
+};
+cudaError_t launch_iekf_loop(const IekfLoopArgs& a, cudaStream_t stream);
+cudaError_t probe_concurrent_kernels(cudaStream_t side, cudaStream_t main_stream, int* d_two_ints, bool* concurrent);
 
 #if defined(__CUDACC__)
 // Fused exchange over NVLink peer memory (one warp): publish this rank's 32 sums into every rank's mailbox, wait for the
 // others' sums of the same pass, add all of them in rank order (bitwise identical everywhere).  NaN marks a failed exchange.
 __device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, int lane) {
-    const int par = (int)(cm.seq & 1ull);
+    const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(cm.seq) + 1ull;
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(cm.seq) = seq;
+    const int par = (int)(seq & 1ull);
     for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
     __threadfence_system();
     __syncwarp();
     if (lane < cm.world) {
         volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
-        *f = cm.seq;
+        *f = seq;
     }
     __threadfence_system();
     bool ok = true;
     if (lane < cm.world) {
         volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
         long long spins = 0;
-        while (*f < cm.seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+        while (*f < seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
     }
     ok = __all_sync(0xffffffffu, ok);
     __threadfence_system();
@@ -84,6 +143,10 @@ struct K1Args {
     double* host_out;            // optional mapped pinned host buffer: the final 32 sums are also written there, then
     unsigned long long host_seq; // host_out[32] (as u64) = host_seq after a system fence: the host spins on it instead of
                                  // a D2H copy + stream synchronize
+    IekfDev* dev;                // device-resident loop: the pass's last block leaves its sums in dev->sums and bumps sums_seq;
+    unsigned long long pose_ticket;   // with wait_pose the kernel first waits for pose_seq >= pose_ticket and takes its constants from
+    unsigned long long end_ticket;   // dev->pc; pose_seq >= end_ticket says the loop has ended: the kernel leaves at once
+    int wait_pose;
 };
 
 constexpr int kFastWarps = 4;
@@ -117,9 +180,55 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     unsigned long long host_seq;      // was flagged in this pass (see K1Args::host_out)
     CommDev comm;                     // multi-GPU with exchange_in_fit: k1_fit's last block runs the exchange in that case
     int exchange_in_fit;
+    IekfDev* dev;                     // device-resident loop (see K1Args::dev)
+    unsigned long long pose_ticket, end_ticket;
+    int wait_pose;
 };
 
+#if defined(__CUDACC__)
+// Every pass kernel reads its constants from shared memory: filled from the by-value argument (host-driven pass, pass 0
+// of the device-resident loop) or from the loop state once the ESIKF block has published them.  Returns false when the
+// loop has already ended (the whole grid leaves).
+__device__ __forceinline__ bool load_pass_const(const IekfDev* dev, int wait_pose, unsigned long long ticket, unsigned long long end_ticket,
+                                                const PassConst& by_value, PassConst& s_c) {
+    constexpr int ND = (int)(sizeof(PassConst) / sizeof(double));
+    static_assert(sizeof(PassConst) % sizeof(double) == 0, "PassConst is copied as doubles");
+    if (dev && wait_pose) {
+        __shared__ int s_go;
+        if (threadIdx.x == 0) {
+            const volatile unsigned long long* ps = &dev->pose_seq;
+            long long spins = 0;
+            unsigned long long v;
+            while ((v = *ps) < ticket) { if (++spins > (1ll << 26)) { v = ~0ull; break; } }   // the ESIKF block died: leave, do not hang
+            __threadfence();
+            s_go = v < end_ticket ? 1 : 0;   // a ticket beyond the sweep's passes = the loop has ended (also a later sweep's)
+        }
+        __syncthreads();
+        if (!s_go) return false;
+        if (threadIdx.x < ND) reinterpret_cast<double*>(&s_c)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(&dev->pc) + threadIdx.x);
+    } else if (threadIdx.x == 0) {
+        s_c = by_value;
+    }
+    __syncthreads();
+    return true;
+}
+// the pass's last block (one warp) hands the final sums to the ESIKF block
+__device__ __forceinline__ void publish_sums_to_loop(IekfDev* dev, unsigned long long ticket, double tot, int lane) {
+    if (!dev) return;
+    dev->sums[lane] = tot;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&dev->sums_seq) = ticket + 1ull;
+        __threadfence();
+    }
+}
+#endif
+
 cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, cudaStream_t stream);
+// load every pass kernel (CUDA loads lazily at first launch, and a load waits for running kernels) and the offset tables
+cudaError_t preload_fast_kernels(int device);
+cudaError_t preload_assoc_kernels(int device, int K);
 constexpr int kSplitSlots = 23;   // = NS of srl_fast.cu: candidate slots k1_scan hands to k1_fit per keypoint
 cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream);
 void k1_split_set_lanes_per_keypoint(int v);
@@ -175,6 +284,19 @@ struct srl_ctx {
     int force_amb_mod = 0;                   // test knob for the k1_fast -> k1_assoc hand-over
     int variant = 0;                         // 0 auto, 1 = k1_fast, 2 = k1_assoc only, 3 = k1_scan + k1_fit (1 and 3 with the exact fallback)
     unsigned long long* d_scan_count = nullptr;
+    // device-resident updateIEKF loop (row N1)
+    bool kernels_preloaded = false;
+    int concurrent_kernels = -1;             // -1 not probed yet; 0: kernels of this process are serialised (profiler): host loop
+    bool device_loop = true;                 // option "device_loop" / SRL_DEVICE_LOOP: 0 = the host-driven loop of round 1
+    srl::IekfDev* d_iekf = nullptr;
+    srl::IekfHostOut* h_iekf = nullptr;      // pinned + mapped
+    srl::IekfHostOut* d_h_iekf = nullptr;    // its device-side address
+    unsigned long long iekf_seq = 0;
+    unsigned long long loop_base = 64;       // ticket of the next sweep's pass 0 (grows by 64 per sweep)
+    cudaStream_t loop_stream = nullptr;      // side stream of the persistent ESIKF block
+    double step_cycles_sum = 0.0;            // counter "iekf_step_cycles_avg": clock ticks from "sums seen" to "pose published"
+    long long step_cycles_n = 0;
+    cudaEvent_t loop_ev0[srl::kLoopMaxPasses] = {nullptr}, loop_ev1[srl::kLoopMaxPasses] = {nullptr};   // timing mode: one pair per enqueued pass
     // generic scratch (map insert)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -197,7 +319,7 @@ struct srl_map {
 struct srl_comm {
     srl_ctx* ctx = nullptr;
     int rank = 0, world = 1;
-    unsigned long long seq = 0;
+    unsigned long long* d_seq = nullptr;            // device counter of the exchanges run (CommDev::seq)
     srl::Mailbox* d_mail = nullptr;                 // this rank's mailbox
     srl::Mailbox* peer[srl::kMaxRanks] = {nullptr}; // mapped peers (peer[rank] == d_mail)
     bool opened[srl::kMaxRanks] = {false};
@@ -212,6 +334,7 @@ struct srl_sweep {
     double* d_raw = nullptr;        // capacity*3
     unsigned* d_order = nullptr;    // capacity: Morton order of the keypoints (lazily computed per upload)
     bool order_valid = false;
+    bool flags_clean = false;       // d_flags holds zeros outside the range the current shard rewrites every pass
     unsigned char* d_flags = nullptr;   // capacity
     unsigned* d_cand_rows = nullptr;    // split form: 24 words per keypoint (k1_scan -> k1_fit)
     double* d_rows = nullptr;       // capacity*8, lazily allocated (cap mode)

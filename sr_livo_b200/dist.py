@@ -133,6 +133,8 @@ class DistributedLio:
                                                        C.byref(prm), C.c_void_p(self.block.data_ptr()))
             if rc != capi.SRL_OK:
                 raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
+            # the pass ran on the ctx stream, the all-reduce and the D2H read run on torch's current stream: order them
+            self.L.ctx.synchronize()
             return self.block
         return fn
 

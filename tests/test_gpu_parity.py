@@ -442,6 +442,39 @@ def test_update_iekf_matches_oracle(L, small_world, kw):
         assert np.linalg.norm(e.p - sw.t_true) < 0.01           # it actually registers the sweep
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(frame_id=5, num_iters_icp=3), dict(threshold_translation_norm=0.0),
+                                dict(threshold_translation_norm=0.0, num_iters_icp=2), dict(num_iters_icp=0)])
+def test_device_resident_loop_equals_host_driven_loop(L, small_world, kw):
+    """Row N1: k_iekf_step on the device (all passes enqueued at once, one host wait) against the round-1 host loop
+    (srl_iekf_step per pass): same passes, same early exit, state to 1e-9 — the two differ only in how the gain is formed
+    (one 6x6 inverse via the Woodbury identity instead of two 17x17 inverses)."""
+    from sr_livo_b200 import lio
+    om, sw = _load_world(L, small_world)
+    n = 1500 if kw.get("frame_id") == 5 else sw.raw_xyz.shape[0]
+    raw = sw.raw_xyz[:n]
+    P = synth.prior_covariance()
+    prm = lio.r3live_params(max_num_residuals=BIG, **kw)
+    out = {}
+    try:
+        for mode in (1, 0):
+            L.ctx.set_option("device_loop", mode)
+            L.setKeypoints(raw)
+            L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), v=np.array([0.3, 0.0, 0.0]),
+                                           ba=np.array([0.01, -0.02, 0.0]), cov=P.copy())
+            launches0 = L.ctx.kernel_launches
+            summ, fq, ft = L.updateIEKF(prm, sw.t_last)
+            out[mode] = (summ, fq, ft, L.eskf_pro, L.ctx.kernel_launches - launches0)
+    finally:
+        L.ctx.set_option("device_loop", 1)
+    (sd, qd, td, ed, _), (sh, qh, th, eh, _) = out[1], out[0]
+    assert (sd.success, sd.passes_run, sd.converged, sd.num_residuals_used) == (sh.success, sh.passes_run, sh.converged, sh.num_residuals_used)
+    assert np.allclose(sd.trace, sh.trace, rtol=1e-7, atol=1e-11)
+    for f in ("p", "q", "v", "ba", "bg", "g"):
+        assert np.allclose(getattr(ed, f), getattr(eh, f), rtol=1e-9, atol=1e-11), f
+    assert np.allclose(ed.cov, eh.cov, rtol=1e-6, atol=1e-13)
+    assert np.allclose(qd, qh, atol=1e-11) and np.allclose(td, th, atol=1e-11)
+
+
 def test_update_iekf_reports_too_few_residuals(L, small_world):
     from sr_livo_b200 import lio
     om, sw = _load_world(L, small_world)
