@@ -213,9 +213,10 @@ def main():
 
     def prepare(i):
         sw = sweeps[i % len(sweeps)]
-        L.sweep.set_device(d_raw[i % len(sweeps)].data_ptr(), sw.raw_xyz.shape[0])
         if world > 1:
-            L.sweep.set_shard(*dist.shard_range(sw.raw_xyz.shape[0], rank, world))
+            D.set_keypoints_device(d_raw[i % len(sweeps)].data_ptr(), sw.raw_xyz.shape[0])   # this rank's range only
+        else:
+            L.sweep.set_device(d_raw[i % len(sweeps)].data_ptr(), sw.raw_xyz.shape[0])
         L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
         return sw
 
@@ -237,17 +238,8 @@ def main():
         L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
         raw_h = raw_host[id(sw)]
         if world > 1:
-            D.set_keypoints(raw_h)                                        # H2D, every rank holds the sweep
-            out = D.updateIEKF(prm, sw.t_last)
-            fr_q, fr_t = out["frame_q"], out["frame_t"]
-            dw = torch.empty((sw.raw_xyz.shape[0], 3), dtype=torch.float64, device=f"cuda:{local}")
-            import ctypes as C
-            from sr_livo_b200 import capi
-            R, ti = capi.f64(L.R_imu_lidar).reshape(9), capi.f64(L.t_imu_lidar)
-            rc = capi.lib().srl_sweep_transform_device(L.ctx.h, L.sweep.h, capi.ptr(fr_q), capi.ptr(fr_t), capi.ptr(R), capi.ptr(ti),
-                                                       C.c_void_p(dw.data_ptr()))
-            assert rc == 0
-            world_out[:] = dw.cpu().numpy()                               # D2H of the registered points
+            out = D.optimize(raw_h, prm, sw.t_last, world_out=world_out)   # srl_optimize_host_dist: all in C, pinned buffers
+            assert out["success"] and out["passes"] == N_PASSES
         else:
             summ, _, _, w = L.optimize(raw_h, prm, sw.t_last, want_world=True, world_out=world_out)
             assert summ.success and summ.passes_run == N_PASSES
@@ -395,7 +387,9 @@ def main():
                 "ms_per_step_stats": {"p50": float(np.median(ms_res)), "min": float(ms_res.min()), "max": float(ms_res.max()),
                                       "note": "this rank's per-step CUDA-event times; ms_per_step is their mean (max over ranks)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,
-                        "h2d_bytes_per_step": int(args.points * 24), "d2h_bytes_per_step": int(args.points * 24 + N_PASSES * 256)},
+                        "h2d_bytes_per_step": int(args.points * 24),
+                        "d2h_bytes_per_step": int(args.points * 24 + (world * 9328 if loop_on_device else world * N_PASSES * 256)),
+                        "entry_point": "srl_optimize_host_dist (C, pinned buffers, this rank's range only)" if world > 1 else "srl_optimize_host"},
                 "roofline": roofline,
                 "iekf_step": {"where": "device (persistent ESIKF block, srl_iekf.cu)" if loop_on_device else "host (srl_iekf_step)",
                               "sm_cycles_sums_to_pose": step_cycles,

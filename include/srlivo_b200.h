@@ -175,7 +175,10 @@ int srl_map_insert_sweep(srl_map* map, srl_sweep* sweep, const double q[4], cons
 /* ---- sweep: the keypoints vector of optimize() (src/optimize.cpp:430) ------------------------ */
 int srl_sweep_create(srl_ctx* ctx, size_t capacity, srl_sweep** out);
 void srl_sweep_destroy(srl_sweep* sweep);
-int srl_sweep_upload(srl_sweep* sweep, const double* raw_xyz, size_t n);        /* host -> HBM (pinned staging) */
+/* host -> HBM.  Pageable memory is staged through a pinned buffer (the call returns when the staging buffer is free
+ * again); pinned memory goes straight to the DMA engine and is read asynchronously: keep it unchanged until the next
+ * synchronising call on the ctx (any pass / update / srl_ctx_synchronize). */
+int srl_sweep_upload(srl_sweep* sweep, const double* raw_xyz, size_t n);
 int srl_sweep_set_device(srl_sweep* sweep, const double* d_raw_xyz, size_t n);  /* device -> device copy */
 /* keypoints [begin, end) are this rank's shard (point-index sharding); default whole sweep */
 int srl_sweep_set_shard(srl_sweep* sweep, size_t begin, size_t end);
@@ -215,6 +218,17 @@ int srl_comm_connect(srl_comm* comm, const void* handles /* world x 64 bytes, ra
 int srl_update_iekf_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],
                          double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
                          const srl_icp_params* prm, srl_iekf_summary* summary);
+
+/* the contiguous keypoint range [begin, end) of `rank` among `world` ranks (boundaries on multiples of 32) */
+void srl_shard_range(size_t n, int rank, int world, size_t* begin, size_t* end);
+/* optimize() on several GPUs with HOST buffers (config 3 end to end): every rank passes the whole sweep's host array; the
+ * rank uploads only its own range of keypoints (srl_shard_range), registers it with the per-pass exchange of
+ * srl_update_iekf_dist (all ranks end with the same state) and writes the re-transformed points of its range
+ * (src/optimize.cpp:441-445) into world_xyz_out[begin*3 .. end*3).  Pinned host memory is copied without staging. */
+int srl_optimize_host_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sweep, const double* raw_xyz, size_t n,
+                           srl_eskf_state* eskf, double frame_q[4], double frame_t[3], const double t_last[3],
+                           const double R_il[9], const double t_il[3], const srl_icp_params* prm, srl_iekf_summary* summary,
+                           double* world_xyz_out, size_t* shard_begin, size_t* shard_end);
 
 /* full loop on one GPU (sweep already resident) */
 int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],

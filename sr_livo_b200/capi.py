@@ -76,7 +76,7 @@ EXPORTS = [
     "srl_map_insert_device", "srl_map_insert_sweep", "srl_sweep_create", "srl_sweep_destroy", "srl_sweep_upload", "srl_sweep_set_device",
     "srl_sweep_set_shard", "srl_build_plane_residuals", "srl_build_plane_residuals_async", "srl_normal_eq_unpack",
     "srl_iekf_begin", "srl_iekf_step", "srl_update_iekf", "srl_comm_create", "srl_comm_destroy", "srl_comm_export", "srl_comm_connect",
-    "srl_update_iekf_dist", "srl_optimize_host", "srl_sweep_transform_device",
+    "srl_update_iekf_dist", "srl_optimize_host", "srl_optimize_host_dist", "srl_shard_range", "srl_sweep_transform_device",
     "srl_grid_sampling", "srl_eskf_observe", "srl_host_plane_fit",
     "srl_distort_frame_by_constant", "srl_distort_frame_by_imu", "srl_transform_all_imu_point",
 ]
@@ -143,6 +143,10 @@ def lib():
                                        C.POINTER(IekfSummary)]
     L.srl_optimize_host.argtypes = [vp, vp, vp, vp, sz, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
                                     C.POINTER(IekfSummary), vp]
+    L.srl_optimize_host_dist.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(EskfState), vp, vp, vp, vp, vp, C.POINTER(IcpParams),
+                                         C.POINTER(IekfSummary), vp, C.POINTER(sz), C.POINTER(sz)]
+    L.srl_shard_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
+    L.srl_shard_range.restype = None
     L.srl_sweep_transform_device.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.srl_grid_sampling.argtypes = [vp, vp, sz, dbl, vp, C.POINTER(sz)]
     L.srl_eskf_observe.argtypes = [C.POINTER(EskfState), vp]
@@ -183,17 +187,21 @@ def ptr(a):
 
 
 def eskf_to_c(p, q, v, ba, bg, g, cov) -> EskfState:
+    """One memmove of the 308 doubles (p3 q4 v3 ba3 bg3 g3 cov289) instead of per-element ctypes stores (~50 us)."""
+    packed = np.empty(19 + NS * NS, np.float64)
+    packed[0:3] = p; packed[3:7] = q; packed[7:10] = v; packed[10:13] = ba; packed[13:16] = bg; packed[16:19] = g
+    packed[19:] = np.asarray(cov, np.float64).reshape(-1)
     s = EskfState()
-    for name, val in (("p", p), ("q", q), ("v", v), ("ba", ba), ("bg", bg), ("g", g)):
-        a = f64(val).reshape(-1)
-        for i in range(a.size):
-            getattr(s, name)[i] = a[i]
-    c = f64(cov).reshape(-1)
-    for i in range(NS * NS):
-        s.cov[i] = c[i]
+    C.memmove(C.addressof(s), packed.ctypes.data, packed.nbytes)
     return s
 
 
 def eskf_from_c(s: EskfState) -> dict:
-    return dict(p=np.array(s.p), q=np.array(s.q), v=np.array(s.v), ba=np.array(s.ba), bg=np.array(s.bg),
-                g=np.array(s.g), cov=np.array(s.cov).reshape(NS, NS))
+    a = np.frombuffer(s, dtype=np.float64, count=19 + NS * NS).copy()
+    return dict(p=a[0:3], q=a[3:7], v=a[7:10], ba=a[10:13], bg=a[13:16], g=a[16:19], cov=a[19:].reshape(NS, NS))
+
+
+def summary_trace(summ: "IekfSummary") -> np.ndarray:
+    """The per-pass trace rows of an srl_iekf_summary as a (passes, 24) array."""
+    n = min(int(summ.passes_run), 32)
+    return np.frombuffer(summ, dtype=np.float64, count=32 * 24, offset=IekfSummary.trace.offset).reshape(32, 24)[:n].copy()

@@ -455,6 +455,9 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
         }
         SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, pinned ? raw_xyz : static_cast<const double*>(ctx->h_pinned), n * 3 * sizeof(double),
                                       cudaMemcpyHostToDevice, ctx->stream));
+        // the staging buffer is shared by every upload of the ctx: it must not be refilled while the DMA still reads it
+        // (pinned caller memory is read asynchronously: the caller keeps it unchanged until the next synchronising call)
+        if (!pinned) SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
     return SRL_OK;
@@ -884,6 +887,43 @@ int srl_optimize_host(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const double* r
         r2 = srl_sweep_transform_device(ctx, sw, frame_q, frame_t, R_il, t_il, static_cast<double*>(ctx->d_scratch));
         if (r2 != SRL_OK) return r2;
         SRL_CUDA(ctx, cudaMemcpyAsync(world_xyz_out, ctx->d_scratch, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SRL_OK;
+}
+
+void srl_shard_range(size_t n, int rank, int world, size_t* begin, size_t* end) {
+    // contiguous keypoint ranges on multiples of 32 (whole warp groups), in rank order
+    const size_t groups = (n + 31) / 32;
+    size_t b = world > 0 ? (groups * (size_t)rank) / (size_t)world * 32 : 0;
+    size_t e = world > 0 ? (groups * (size_t)(rank + 1)) / (size_t)world * 32 : n;
+    if (b > n) b = n;
+    if (e > n) e = n;
+    if (begin) *begin = b;
+    if (end) *end = e;
+}
+
+int srl_optimize_host_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sw, const double* raw_xyz, size_t n,
+                           srl_eskf_state* eskf, double frame_q[4], double frame_t[3], const double t_last[3], const double R_il[9],
+                           const double t_il[3], const srl_icp_params* prm, srl_iekf_summary* summary, double* world_xyz_out,
+                           size_t* shard_begin, size_t* shard_end) {
+    if (!ctx || !comm || !sw || (n && !raw_xyz)) return SRL_BAD_ARG;
+    size_t b = 0, e = 0;
+    srl_shard_range(n, comm->rank, comm->world, &b, &e);
+    if (shard_begin) *shard_begin = b;
+    if (shard_end) *shard_end = e;
+    // this rank's keypoints only: H2D of (e - b) points, the local sweep is sorted and registered as a whole, the 32 sums
+    // of every pass are exchanged inside the pass (srl_update_iekf_dist), so every rank ends with the same state
+    int rc = srl_sweep_upload(sw, raw_xyz + 3 * b, e - b);
+    if (rc != SRL_OK) return rc;
+    rc = srl_update_iekf_dist(ctx, comm, map, sw, eskf, frame_q, frame_t, t_last, R_il, t_il, prm, summary);
+    if (rc != SRL_OK) return rc;
+    if (world_xyz_out && e > b) {                                                // src/optimize.cpp:441-445, this rank's rows
+        int r2 = ensure_scratch(ctx, (e - b) * 3 * sizeof(double));
+        if (r2 != SRL_OK) return r2;
+        r2 = srl_sweep_transform_device(ctx, sw, frame_q, frame_t, R_il, t_il, static_cast<double*>(ctx->d_scratch));
+        if (r2 != SRL_OK) return r2;
+        SRL_CUDA(ctx, cudaMemcpyAsync(world_xyz_out + 3 * b, ctx->d_scratch, (e - b) * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return SRL_OK;

@@ -48,28 +48,25 @@ __device__ __forceinline__ bool inverse6_warp(const double* sM, double* sMinv, i
     int my_k = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        double best = (lane < 6 && !used) ? fabs(row[k]) : -1.0;
-        int who = lane;
-#pragma unroll
-        for (int s = 4; s >= 1; s >>= 1) {
-            const double ob = __shfl_xor_sync(FULLM, best, s);
-            const int ow = __shfl_xor_sync(FULLM, who, s);
-            if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
-        }
-        best = __shfl_sync(FULLM, best, 0);   // lanes 0..7 agree among themselves; lane 0's view is broadcast
-        who = __shfl_sync(FULLM, who, 0);
-        if (!(best > 0.0)) ok = false;
-        const double inv = 1.0 / __shfl_sync(FULLM, row[k], who);
+        // pivot = the unused row with the largest |a[r][k]|, compared on the high word of the magnitude (monotonic for
+        // non-negative doubles; 2^-20 relative resolution is plenty for choosing a pivot): one REDUX + one ballot
+        const unsigned mag = (lane < 6 && !used) ? (unsigned)__double2hiint(fabs(row[k])) : 0u;
+        const unsigned top = __reduce_max_sync(FULLM, mag);
+        const int who = __ffs(__ballot_sync(FULLM, lane < 6 && !used && mag == top)) - 1;
+        const double piv = __shfl_sync(FULLM, row[k], who < 0 ? 0 : who);
+        if (who < 0 || !(fabs(piv) > 0.0)) ok = false;   // also catches NaN
+        const double inv = __drcp_rn(piv);
         if (lane == who) {
 #pragma unroll
             for (int c = 0; c < 12; ++c) row[c] *= inv;
             used = true; my_k = k;
         }
+        const int src = who < 0 ? 0 : who;
         const double f = row[k];
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
             if (c > k) {   // columns <= k of the left half are already unit vectors (or become one now)
-                const double pk = __shfl_sync(FULLM, row[c], who);
+                const double pk = __shfl_sync(FULLM, row[c], src);
                 if (lane != who && lane < 6) row[c] -= f * pk;
             }
         }
@@ -390,11 +387,10 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
             else if (tid >= 32 && tid < 41) D->pc.Rn[tid - 32] = S.Rn[tid - 32];
             else if (tid >= 64 && tid < 73) D->pc.Rq[tid - 64] = S.Rq[tid - 64];
         }
+        if (tid == 0 && done) D->done = 1;
         __threadfence();
         __syncthreads();
         if (tid == 0) {
-            if (done) D->done = 1;
-            __threadfence();
             *reinterpret_cast<volatile unsigned long long*>(&D->pose_seq) = done ? A.base + 63ull : A.base + (unsigned long long)it + 1ull;
             if (it < kLoopMaxPasses) D->step_cycles[it] = clock64() - t0;
             for (int i = 1; i < 8; ++i) D->stage_cycles[i] = S.stamp[i] - S.stamp[0];

@@ -119,10 +119,48 @@ class DistributedLio:
             self.comm = None
 
     def set_keypoints(self, raw_xyz):
-        """Every rank holds the whole sweep (2.4 MB for 100k points); only the shard is processed."""
-        self.L.setKeypoints(raw_xyz)
-        b, e = shard_range(self.L.sweep.n, self.rank, self.world)
-        self.L.sweep.set_shard(b, e)
+        """This rank's contiguous range of the sweep's keypoints becomes its local sweep (uploaded, Morton-ordered and
+        registered as a whole): H2D and ordering shrink with the number of ranks, and the per-pass exchange of the 32 sums
+        makes every rank see the normal equations of the whole sweep."""
+        raw = capi.f64(raw_xyz).reshape(-1, 3)
+        b, e = shard_range(raw.shape[0], self.rank, self.world)
+        self.range = (b, e)
+        self.L.setKeypoints(raw[b:e])
+
+    def set_keypoints_device(self, d_ptr: int, n: int):
+        """Same from a device array of the whole sweep (n x 3 float64): a device-to-device copy of this rank's range."""
+        b, e = shard_range(n, self.rank, self.world)
+        self.range = (b, e)
+        self.L.sweep.set_device(d_ptr + 24 * b, e - b)
+
+    def optimize(self, raw_xyz, prm: IcpParams, t_last, world_out=None, frame_q=None, frame_t=None):
+        """optimize() with HOST buffers on all ranks (srl_optimize_host_dist, all in C): H2D of this rank's range, the
+        sharded iterated update, the final re-transform and D2H of this rank's rows into world_out[b:e]."""
+        from .lio import EskfEstimator
+        if self.comm is None:
+            raise SrlError(capi.SRL_BAD_ARG, "DistributedLio.optimize needs the native exchange (native=True, world > 1)")
+        raw = capi.f64(raw_xyz).reshape(-1, 3)
+        n = raw.shape[0]
+        st = self.L.eskf_pro.to_c()
+        fq = capi.f64(self.L.eskf_pro.q if frame_q is None else frame_q).copy()
+        ft = capi.f64(self.L.eskf_pro.p if frame_t is None else frame_t).copy()
+        tl = capi.f64(t_last)
+        R, ti = capi.f64(self.L.R_imu_lidar).reshape(9), capi.f64(self.L.t_imu_lidar)
+        summ = capi.IekfSummary()
+        b, e = C.c_size_t(0), C.c_size_t(0)
+        rc = lib().srl_optimize_host_dist(self.L.ctx.h, self.comm, self.L.voxel_map.h, self.L.sweep.h, ptr(raw), n, C.byref(st),
+                                          ptr(fq), ptr(ft), ptr(tl), ptr(R), ptr(ti), C.byref(prm), C.byref(summ),
+                                          ptr(world_out) if world_out is not None else None, C.byref(b), C.byref(e))
+        self.range = (b.value, e.value)
+        self.L.sweep.n = e.value - b.value
+        if rc == capi.SRL_NAN_PLANARITY:
+            raise RuntimeError("error")
+        if rc not in (capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS):
+            raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
+        self.L.eskf_pro = EskfEstimator.from_c(st)
+        return dict(success=bool(summ.success) and rc == capi.SRL_OK, passes=summ.passes_run, converged=bool(summ.converged),
+                    num_residuals_used=summ.num_residuals_used, trace=capi.summary_trace(summ), frame_q=fq, frame_t=ft,
+                    range=self.range)
 
     def _pass(self, prm: IcpParams, t_last):
         from .lio import make_frame
@@ -154,7 +192,7 @@ class DistributedLio:
             if rc not in (capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS):
                 raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
             self.L.eskf_pro = EskfEstimator.from_c(st)
-            trace = np.array([list(summ.trace[i]) for i in range(min(summ.passes_run, 32))])
+            trace = capi.summary_trace(summ)
             return dict(success=bool(summ.success) and rc == capi.SRL_OK, passes=summ.passes_run, converged=bool(summ.converged),
                         num_residuals_used=summ.num_residuals_used, trace=trace, frame_q=fq, frame_t=ft)
         out = iekf_loop(self._pass(prm, capi.f64(t_last)), st, fq, ft, prm, self.group)

@@ -383,7 +383,7 @@ class LioOptimization:
             raise RuntimeError("error")
         _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
         self.eskf_pro = EskfEstimator.from_c(st)
-        trace = np.array([list(summ.trace[i]) for i in range(min(summ.passes_run, 32))])
+        trace = capi.summary_trace(summ)
         return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
                                passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft
 
@@ -410,7 +410,7 @@ class LioOptimization:
             raise RuntimeError("error")
         _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
         self.eskf_pro = EskfEstimator.from_c(st)
-        trace = np.array([list(summ.trace[i]) for i in range(min(summ.passes_run, 32))])
+        trace = capi.summary_trace(summ)
         return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
                                passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft, world
 

@@ -754,7 +754,7 @@ for rep in range(3):                                    # several updates in a r
     L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
     # last repetition: rank 1 hands every 7th keypoint to the exact kernel, rank 0 none: the two ranks then finish a pass
     # (and run their side of the exchange) in different kernels
-    L.ctx.set_option("fast_force_ambiguous_mod", 7 if (rep == 2 and rank == 1) else 0)
+    L.ctx.set_option("fast_force_ambiguous_mod", 7 if (rep == 2 and rank == world - 1) else 0)
     out = D.updateIEKF(prm, sw.t_last)
 om = O.OracleMap(); om.add_points(pts)
 ref = om.update_iekf(sw.raw_xyz, O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance()), sw.t_last,
@@ -766,22 +766,35 @@ t = torch.from_numpy(np.concatenate([L.eskf_pro.p, L.eskf_pro.q, L.eskf_pro.cov.
 lst = [torch.zeros_like(t) for _ in range(world)]
 tdist.all_gather(lst, t)
 assert all(torch.equal(lst[0], x) for x in lst)         # every rank ends bit-identical
+# config 3 end to end in C (srl_optimize_host_dist): host buffers in, this rank's rows of the registered sweep out
+L.ctx.set_option("fast_force_ambiguous_mod", 0)
+L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+world_out = np.full_like(sw.raw_xyz, np.nan)
+o2 = D.optimize(sw.raw_xyz, prm, sw.t_last, world_out=world_out)
+b, e = o2["range"]
+assert (b, e) == dist.shard_range(sw.raw_xyz.shape[0], rank, world) and o2["passes"] == ref["passes"]
+assert np.allclose(o2["frame_t"], ref["frame_t"], atol=1e-9) and np.allclose(o2["frame_q"], ref["frame_q"], atol=1e-9)
+expect = sw.raw_xyz @ O.quat_to_rot(o2["frame_q"]).T + o2["frame_t"]
+assert np.allclose(world_out[b:e], expect[b:e], rtol=0, atol=1e-10)
+assert np.isnan(world_out[:b]).all() and np.isnan(world_out[e:]).all()      # only this rank's rows are written
 D.close(); L.close(); tdist.destroy_process_group()
 print("rank", rank, "ok")
 """
 
 
-def test_fused_peer_memory_exchange_two_ranks(tmp_path):
-    """The sharded update with the exchange fused into the pass's last kernel (CUDA IPC mailboxes): two processes
-    (on two GPUs if the box has them, else sharing one GPU), each owning half of the keypoints."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_peer_memory_exchange_ranks(tmp_path, world):
+    """The sharded update with the exchange fused into the pass's last kernel (CUDA IPC mailboxes) and the ESIKF update
+    in each rank's persistent block: `world` processes (one GPU each if the box has them, else sharing GPUs), each owning
+    a contiguous range of the keypoints; then the same end to end from host buffers (srl_optimize_host_dist)."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "dist_worker.py"
     script.write_text(_DIST_WORKER)
     port = 29700 + (os.getpid() % 1000)
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port + world))
         procs.append(subprocess.Popen([sys.executable, str(script), root], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=600)[0] for p in procs]
