@@ -173,7 +173,9 @@ static int wait_host_result(srl_ctx* ctx, const K1Args& a) {
 // One pass on the ctx stream.  Fast form (k1_fast + k1_assoc on the flagged keypoints) when the configuration allows
 // it, k1_assoc alone otherwise (nb = 2, K != 20, residual cap, forced exact selection).
 static bool pass_is_fast(const srl_ctx* ctx, const K1Args& a) {
-    return !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && !a.rows;
+    // (rows = the ordered residual cap: the split form handles it, in keypoint order instead of Morton order)
+    const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
+    return !ctx->force_exact && ctx->variant != 2 && a.c.nb <= 1 && a.c.K == 20 && a.c.Kmin == 20 && (!a.rows || split);
 }
 // Everything a pass needs besides its kernel launches: buffers, the sweep's Morton order, cleared flags / candidate rows,
 // constant tables and (once per ctx) the kernels themselves.  Idempotent.  The device-resident loop calls it BEFORE it
@@ -230,7 +232,9 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
     } else {
         FastArgs f;
         std::memset(&f, 0, sizeof(f));
-        f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw; f.order = sw->d_order;
+        f.c = a.c; f.slots = a.slots; f.mask = a.mask; f.blocks = a.blocks; f.raw = a.raw;
+        f.order = a.rows ? nullptr : sw->d_order;   // the residual cap consumes keypoints in their own order (src/optimize.cpp:68,107)
+        f.rows = a.rows;
         f.s_begin = a.k_begin; f.s_end = a.k_end;   // the shard is a range of SORTED positions in this form
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
@@ -254,7 +258,8 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
             SRL_CUDA(ctx, launch_k1_fast(f, (int)grid, debug, ctx->device, ctx->stream));
         }
         K1Args b = a;   // exact selection for the keypoints k1_fast could not decide; its last block adds k1_fast's sums
-        b.k_begin = 0; b.k_end = (long long)sw->n; b.only_flagged = sw->d_flags; b.prev_out32 = ctx->d_fast_out;
+        b.only_flagged = sw->d_flags; b.prev_out32 = ctx->d_fast_out;
+        if (!a.rows) { b.k_begin = 0; b.k_end = (long long)sw->n; }   // Morton order: the range's keypoints are scattered over the sweep
         // almost always nothing is flagged: a one-block-per-SM grid walks the flags (32 per warp step) and leaves
         const int fb_grid = (int)std::min<long long>(ctx->sm_count, std::max<long long>(1, ((long long)sw->n + 31) / 32));
         SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream));
@@ -590,7 +595,9 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
         }
         SRL_CUDA(ctx, cudaMemcpyAsync(h, d_cap_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        h[30] = scanned; h[31] = nanf;
+        // [31] comes from k2_cap_reduce: NaN planarity counts only where the reference loop got to (k <= k*)
+        (void)nanf;
+        h[30] = scanned;   // candidates scanned in the chunks processed (an upper bound of the reference's count up to k*)
     }
     unpack32(h, out, n);
     if (debug) {

@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(1024, 1) k2_cap_reduce(const double* __restric
     double acc[29];
 #pragma unroll
     for (int i = 0; i < 29; ++i) acc[i] = 0.0;
-    double n_full = 0.0;
+    double n_full = 0.0, n_nan = 0.0;
     for (long long base = k_begin; base < k_end && !s_found; base += 1024) {
         const long long k = base + tid;
         const int st = (k < k_end) ? status[k] : 0;
@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(1024, 1) k2_cap_reduce(const double* __restric
         const long long kstar = s_found ? s_kstar : (long long)0x7fffffffffffffffLL;
         if (k < k_end && k <= kstar) {
             if (st >= 1) n_full += 1.0;
+            if (st >= 1 && rows[8 * k] != rows[8 * k]) n_nan += 1.0;   // NaN planarity -> NaN weight -> NaN Jacobian (the reference throws, :348)
             if (a) {
                 const double* r = rows + 8 * k;
                 int idx = 0;
@@ -621,20 +622,21 @@ __global__ void __launch_bounds__(1024, 1) k2_cap_reduce(const double* __restric
     if (mark_unvisited && s_found)
         for (long long k = s_kstar + 1 + tid; k < k_end; k += 1024) status[k] = -1;
     // fixed-order block reduction of the 30 components
-    double comps[30];
+    double comps[31];
 #pragma unroll
     for (int i = 0; i < 29; ++i) comps[i] = acc[i];
     comps[29] = n_full;
-    for (int i = 0; i < 30; ++i) {
+    comps[30] = n_nan;
+    for (int i = 0; i < 31; ++i) {
         double x = comps[i];
         for (int s = 16; s >= 1; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
         if (lane == 0) s_red[warp][i] = x;
     }
     __syncthreads();
-    if (warp == 0 && lane < 30) {
+    if (warp == 0 && lane < 31) {
         double tot = 0.0;
         for (int w = 0; w < 32; ++w) tot += s_red[w][lane];
-        out32[lane] += tot;   // chunks append
+        out32[lane == 30 ? 31 : lane] += tot;   // chunks append; [31] = NaN-planarity keypoints the reference loop reached
     }
     if (tid == 0) { state[0] = run_acc; state[1] = s_found; state[2] = s_kstar; }
 }

@@ -883,6 +883,12 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
                 v[27] = row.distance * row.distance;                                                          // :104
                 v[28] = 1.0;
             }
+            if (A.rows) {   // per-keypoint rows for the ordered max_num_residuals cap (src/optimize.cpp:107)
+                double* rr = A.rows + 8 * k;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) rr[i] = row.J[i];
+                rr[6] = h; rr[7] = row.distance * row.distance;
+            }
             if (DEBUG) {
                 if (A.dbg_plane) {
                     double* d = A.dbg_plane + 16 * k;

@@ -183,6 +183,7 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     IekfDev* dev;                     // device-resident loop (see K1Args::dev)
     unsigned long long pose_ticket, end_ticket;
     int wait_pose;
+    double* rows;                     // optional n*8 per-keypoint rows (J6, h, d^2) for the ordered residual cap (k2_cap_reduce)
 };
 
 #if defined(__CUDACC__)

@@ -62,11 +62,30 @@ SRL_HD void quat_to_rot(const double* q, double* R) {
 // Input: lower triangle s00 s10 s11 s20 s21 s22.  Output: eigenvalues ascending ev[3] and the unit
 // eigenvector of the smallest one (n0,n1,n2) (sign arbitrary, fixed later by the flip test).
 // ---------------------------------------------------------------------------------------------
+// A FP64 division or square root is a ~35-instruction subroutine on the GPU and the per-keypoint fit is one dependent chain
+// per thread (k1_fit: a single wave of ~21 warps per SM, bound by that chain): on the device reciprocals and reciprocal
+// square roots (MUFU seed + Newton steps, ~1 ulp) followed by multiplies replace them wherever only the 1e-5 relative
+// parity of the plane / residual is at stake.  Association-critical arithmetic (keys, distances that order neighbours)
+// never goes through these.  The host build keeps the textbook operations.
+#if defined(__CUDA_ARCH__)
+SRL_HD double fast_rcp(double x) { return __drcp_rn(x); }
+SRL_HD double fast_rsqrt(double x) { return rsqrt(x); }
+#else
+SRL_HD double fast_rcp(double x) { return 1.0 / x; }
+SRL_HD double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+
 struct Givens { double c, s; };
 SRL_HD Givens make_givens(double p, double q) {
     Givens g;
     if (q == 0.0) { g.c = p < 0.0 ? -1.0 : 1.0; g.s = 0.0; }
     else if (p == 0.0) { g.c = 0.0; g.s = q < 0.0 ? 1.0 : -1.0; }
+#if defined(__CUDA_ARCH__)
+    else {   // both branches below reduce to c = p / r, s = -q / r with r = sqrt(p^2 + q^2); operands are scaled to <= 1
+        const double rinv = fast_rsqrt(p * p + q * q);
+        g.c = p * rinv; g.s = -q * rinv;
+    }
+#else
     else if (fabs(p) > fabs(q)) {
         double t = q / p, u = sqrt(1.0 + t * t);
         if (p < 0.0) u = -u;
@@ -76,6 +95,7 @@ SRL_HD Givens make_givens(double p, double q) {
         if (q < 0.0) u = -u;
         g.s = -1.0 / u; g.c = -t * g.s;
     }
+#endif
     return g;
 }
 
@@ -83,7 +103,11 @@ SRL_HD void eig3_sym(double s00, double s10, double s11, double s20, double s21,
                      double ev[3], double& n0, double& n1, double& n2) {
     double scale = fmax(fmax(fabs(s00), fabs(s10)), fmax(fmax(fabs(s11), fabs(s20)), fmax(fabs(s21), fabs(s22))));
     if (scale == 0.0) scale = 1.0;
+#if defined(__CUDA_ARCH__)
+    { const double is = fast_rcp(scale); s00 *= is; s10 *= is; s11 *= is; s20 *= is; s21 *= is; s22 *= is; }
+#else
     s00 /= scale; s10 /= scale; s11 /= scale; s20 /= scale; s21 /= scale; s22 /= scale;
+#endif
 
     double d0, d1, d2, e0, e1;
     // Q columns: q?0 q?1 q?2
@@ -95,8 +119,14 @@ SRL_HD void eig3_sym(double s00, double s10, double s11, double s20, double s21,
         d1 = s11; d2 = s22; e0 = s10; e1 = s21;
         q11 = 1; q12 = 0; q21 = 0; q22 = 1;
     } else {
+#if defined(__CUDA_ARCH__)
+        const double b2 = s10 * s10 + v1norm2;
+        double invBeta = fast_rsqrt(b2);
+        double beta = b2 * invBeta;
+#else
         double beta = sqrt(s10 * s10 + v1norm2);
         double invBeta = 1.0 / beta;
+#endif
         double m01 = s10 * invBeta, m02 = s20 * invBeta;
         double qq = 2.0 * m01 * s21 + m02 * (s22 - s11);
         d1 = s11 + m02 * qq;
@@ -123,10 +153,17 @@ SRL_HD void eig3_sym(double s00, double s10, double s11, double s20, double s21,
             mu -= fabs(eb);
         } else if (eb != 0.0) {
             double e2 = eb * eb;
+#if defined(__CUDA_ARCH__)
+            double h = sqrt(td * td + e2);                 // scaled operands: no overflow to guard against
+            double den = td + (td > 0.0 ? h : -h);
+            if (e2 == 0.0) mu -= eb / (den / eb);
+            else mu -= e2 * fast_rcp(den);
+#else
             double h = hypot(td, eb);
             double den = td + (td > 0.0 ? h : -h);
             if (e2 == 0.0) mu -= eb / (den / eb);
             else mu -= e2 / den;
+#endif
         }
         double x = ((start == 0) ? d0 : d1) - mu;
         double z = (start == 0) ? e0 : e1;
@@ -172,7 +209,11 @@ SRL_HD void eig3_sym(double s00, double s10, double s11, double s20, double s21,
     double vz = (imin == 0) ? q20 : ((imin == 1) ? q21 : q22);
     ev[0] = lo * scale; ev[1] = mid * scale; ev[2] = hi * scale;
     double nn = vx * vx + (vy * vy + vz * vz);
+#if defined(__CUDA_ARCH__)
+    if (nn > 0.0) { const double rs = fast_rsqrt(nn); vx *= rs; vy *= rs; vz *= rs; }
+#else
     if (nn > 0.0) { double inv = sqrt(nn); vx /= inv; vy /= inv; vz /= inv; }
+#endif
     n0 = vx; n1 = vy; n2 = vz;
 }
 
@@ -222,7 +263,11 @@ SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double 
         nbv.get(j, x, y, z);
         mx += (double)x; my += (double)y; mz += (double)z;
     }
+#if defined(__CUDA_ARCH__)
+    { const double invK = fast_rcp((double)K); mx *= invK; my *= invK; mz *= invK; }
+#else
     mx /= (double)K; my /= (double)K; mz /= (double)K;
+#endif
     // un-normalised scatter, upper triangle (src/optimize.cpp:328-338)
     double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
 #pragma unroll
@@ -235,8 +280,13 @@ SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double 
     }
     double ev[3], nx, ny, nz;
     eig3_sym(c00, c01, c11, c02, c12, c22, ev, nx, ny, nz);
+#if defined(__CUDA_ARCH__)
+    double sigma_2 = sqrt(fabs(ev[1])), sigma_3 = sqrt(fabs(ev[0]));
+    double a2D = (sigma_2 - sigma_3) * fast_rsqrt(fabs(ev[2]));   // (0 - 0) * inf = NaN like the reference's 0 / 0
+#else
     double sigma_1 = sqrt(fabs(ev[2])), sigma_2 = sqrt(fabs(ev[1])), sigma_3 = sqrt(fabs(ev[0]));
     double a2D = (sigma_2 - sigma_3) / sigma_1;           // src/optimize.cpp:343-346
+#endif
     out.a2D = a2D;
     out.nan_planarity = (a2D != a2D) ? 1 : 0;
     double planarity_weight = (c.power == 2.0) ? a2D * a2D : pow(a2D, c.power);   // :47
@@ -245,10 +295,18 @@ SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double 
     // weight (:87-88)
     double ex = n0x - px, ey = n0y - py, ez = n0z - pz;
     double dist0 = sqrt(ex * ex + (ey * ey + ez * ez));
+#if defined(__CUDA_ARCH__)
+    double weight = c.lambda_w * planarity_weight + c.lambda_n * exp(-dist0 * fast_rcp(c.exp_den));
+#else
     double weight = c.lambda_w * planarity_weight + c.lambda_n * exp(-dist0 / c.exp_den);
+#endif
     // plane (:92-96)
     double nn = nx * nx + (ny * ny + nz * nz);
+#if defined(__CUDA_ARCH__)
+    if (nn > 0.0) { const double rs = fast_rsqrt(nn); nx *= rs; ny *= rs; nz *= rs; }
+#else
     if (nn > 0.0) { double s = sqrt(nn); nx /= s; ny /= s; nz /= s; }
+#endif
     double offset = -(nx * n0x + (ny * n0y + nz * n0z));
     double wx = c.Rq[0] * bx + (c.Rq[1] * by + c.Rq[2] * bz) + c.t[0];
     double wy = c.Rq[3] * bx + (c.Rq[4] * by + c.Rq[5] * bz) + c.t[1];
