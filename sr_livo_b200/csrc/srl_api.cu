@@ -172,6 +172,22 @@ static int wait_host_result(srl_ctx* ctx, const K1Args& a) {
 
 // One pass on the ctx stream.  Fast form (k1_fast + k1_assoc on the flagged keypoints) when the configuration allows
 // it, k1_assoc alone otherwise (nb = 2, K != 20, residual cap, forced exact selection).
+// The Morton order of the sweep's keypoints (srl_fast.cu), computed once per upload: eagerly right behind the copy that
+// brings the keypoints to HBM (so it is off the critical path of the first pass), lazily here otherwise.
+static int ensure_order(srl_ctx* ctx, srl_sweep* sw) {
+    int rc;
+    if ((rc = ensure_buf(ctx, &sw->d_order, sw->capacity)) != SRL_OK) return rc;
+    if (!sw->order_valid && sw->n > 0) {
+        size_t need = 0;
+        sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, nullptr, 0, &need, ctx->stream);
+        if ((rc = ensure_scratch(ctx, need)) != SRL_OK) return rc;
+        SRL_CUDA(ctx, sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, ctx->d_scratch, ctx->scratch_bytes, &need, ctx->stream));
+        sw->order_valid = true;
+        ctx->launches += 1;
+    }
+    return SRL_OK;
+}
+
 static bool pass_is_fast(const srl_ctx* ctx, const K1Args& a) {
     // (rows = the ordered residual cap: the split form handles it, in keypoint order instead of Morton order)
     const bool split = ctx->variant == 3 || (ctx->variant == 0 && kDefaultSplit);
@@ -189,16 +205,8 @@ static int prepare_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a) {
     }
     if (!pass_is_fast(ctx, a)) return SRL_OK;
     int rc;
-    if ((rc = ensure_buf(ctx, &sw->d_order, sw->capacity)) != SRL_OK) return rc;
+    if ((rc = ensure_order(ctx, sw)) != SRL_OK) return rc;
     if ((rc = ensure_buf(ctx, &sw->d_flags, sw->capacity)) != SRL_OK) return rc;
-    if (!sw->order_valid && sw->n > 0) {
-        size_t need = 0;
-        sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, nullptr, 0, &need, ctx->stream);
-        if ((rc = ensure_scratch(ctx, need)) != SRL_OK) return rc;
-        SRL_CUDA(ctx, sweep_compute_order(sw->d_raw, (long long)sw->n, sw->d_order, ctx->d_scratch, ctx->scratch_bytes, &need, ctx->stream));
-        sw->order_valid = true;
-        ctx->launches += 1;
-    }
     // k1_scan / k1_fast write the flag of every keypoint of their range in every pass; the fallback launch walks the
     // flags of the whole sweep, so the keypoints outside this rank's range need zeros once per (upload, shard)
     if (!sw->flags_clean) {
@@ -213,7 +221,7 @@ static int prepare_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a) {
     return SRL_OK;
 }
 
-static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug, bool own_timing = true) {
+static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug, bool own_timing = true, bool pdl = false) {
     const long long n = a.k_end - a.k_begin;
     const bool fast = pass_is_fast(ctx, a);
     const bool timing = ctx->timing && own_timing;
@@ -227,7 +235,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
         cudaEventRecord(ctx->ev0[ctx->ev_cur], ctx->stream);
     }
     if (!fast) {
-        SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), debug, ctx->device, ctx->stream));
+        SRL_CUDA(ctx, launch_k1(a, pass_grid(ctx, n, a.c.K, a.c.nb), debug, ctx->device, ctx->stream, pdl));
         ctx->launches += 1;
     } else {
         FastArgs f;
@@ -247,7 +255,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
             // exchange_in_fit); the fallback launch then runs off the host's critical path and republishes the same values
             f.comm = a.comm; f.exchange_in_fit = ctx->exchange_in_fit ? 1 : 0;
             if (a.comm.world <= 1 || ctx->exchange_in_fit) { f.host_out = a.host_out; f.host_seq = a.host_seq; }
-            SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream));
+            SRL_CUDA(ctx, launch_k1_split(f, n, ctx->max_grid, debug, ctx->device, ctx->stream, pdl));
             ctx->launches += 1;
         } else {
             const long long kpw = 32 / k1_fast_lanes_per_keypoint();
@@ -262,7 +270,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
         if (!a.rows) { b.k_begin = 0; b.k_end = (long long)sw->n; }   // Morton order: the range's keypoints are scattered over the sweep
         // almost always nothing is flagged: a one-block-per-SM grid walks the flags (32 per warp step) and leaves
         const int fb_grid = (int)std::min<long long>(ctx->sm_count, std::max<long long>(1, ((long long)sw->n + 31) / 32));
-        SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream));
+        SRL_CUDA(ctx, launch_k1(b, fb_grid, debug, ctx->device, ctx->stream, pdl));
         ctx->launches += 2;
     }
     if (timing) { cudaEventRecord(ctx->ev1[ctx->ev_cur], ctx->stream); ctx->ev_pending[ctx->ev_cur] = true; }
@@ -312,6 +320,7 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
     std::memset(ctx->h_out32, 0, 64 * sizeof(double));
     std::memset(ctx->h_iekf, 0, sizeof(IekfHostOut));
     if (const char* e = getenv("SRL_DEVICE_LOOP")) ctx->device_loop = atoi(e) != 0;
+    if (const char* e = getenv("SRL_PDL")) ctx->pdl = atoi(e) != 0;
     if (const char* e = getenv("SRL_MAPPED_RESULT")) ctx->mapped_result = atoi(e) != 0;   // A/B switch (bench runs)
     if (const char* e = getenv("SRL_EXCHANGE_IN_FIT")) ctx->exchange_in_fit = atoi(e) != 0;
     *out = ctx;
@@ -354,6 +363,8 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     }
     if (n == "mapped_result") { ctx->mapped_result = value != 0; return SRL_OK; }
     if (n == "device_loop") { ctx->device_loop = value != 0; return SRL_OK; }
+    if (n == "eager_order") { ctx->eager_order = value != 0; return SRL_OK; }
+    if (n == "pdl") { ctx->pdl = value != 0; return SRL_OK; }
     if (n == "exchange_in_fit") { ctx->exchange_in_fit = value != 0; return SRL_OK; }
     if (n == "split_lanes_per_keypoint") {
         if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");
@@ -465,7 +476,7 @@ int srl_sweep_upload(srl_sweep* s, const double* raw_xyz, size_t n) {
         if (!pinned) SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
-    return SRL_OK;
+    return ctx->eager_order ? ensure_order(ctx, s) : SRL_OK;
 }
 int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     if (!s || (n && !d_raw_xyz)) return SRL_BAD_ARG;
@@ -473,7 +484,7 @@ int srl_sweep_set_device(srl_sweep* s, const double* d_raw_xyz, size_t n) {
     if (n > s->capacity) return set_err(ctx, SRL_BAD_ARG, "srl_sweep_set_device: n exceeds capacity");
     SRL_CUDA(ctx, cudaMemcpyAsync(s->d_raw, d_raw_xyz, n * 3 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     s->n = n; s->shard_begin = 0; s->shard_end = n; s->order_valid = false; s->flags_clean = false;
-    return SRL_OK;
+    return ctx->eager_order ? ensure_order(ctx, s) : SRL_OK;
 }
 int srl_sweep_set_shard(srl_sweep* s, size_t begin, size_t end) {
     if (!s || begin > end || end > s->n) return SRL_BAD_ARG;
@@ -667,7 +678,7 @@ static int update_iekf_device(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sw
         ap.end_ticket = la.base + 63ull;
         ap.wait_pose = p ? 1 : 0;                                    // pass 0: pose by value
         if (ctx->timing) cudaEventRecord(ctx->loop_ev0[p], ctx->stream);
-        if ((rc = launch_pass(ctx, sw, ap, false, false)) != SRL_OK) return rc;
+        if ((rc = launch_pass(ctx, sw, ap, false, false, ctx->pdl && !ctx->timing)) != SRL_OK) return rc;
         if (ctx->timing) cudaEventRecord(ctx->loop_ev1[p], ctx->stream);
     }
     // the one host wait of the sweep

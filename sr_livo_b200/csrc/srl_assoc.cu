@@ -703,14 +703,13 @@ static K1Fn pick_k1(int nb, bool debug) {
     return debug ? pick_minb<4, true>() : pick_minb<4, false>();
 }
 
-cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream) {
+cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream, bool pdl) {
     upload_offsets(device);
     const size_t smem = k1_smem_bytes(a.c.K);
     K1Fn fn = pick_k1(a.c.nb, debug);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fn<<<grid, kK1Threads, smem, stream>>>(a);
-    return cudaGetLastError();
+    return launch_pass_kernel(fn, a, (unsigned)grid, kK1Threads, smem, stream, pdl);
 }
 
 cudaError_t preload_assoc_kernels(int device, int K) {

@@ -1104,7 +1104,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 
 // k1_scan then k1_fit on the same stream.  SRL_SPLIT_LPK=2|4 (lanes per keypoint), SRL_SCAN_MINB / SRL_FIT_MINB pick
 // the compiled register budgets.
-cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream) {
+cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream, bool pdl) {
     upload_fast_offsets(device);
     if (g_split_lpk < 0) { const int v = env_int("SRL_SPLIT_LPK", 4); g_split_lpk = (v == 2) ? 2 : 4; }
     static const int scan_minb = env_int("SRL_SCAN_MINB", 8), fit_minb = env_int("SRL_FIT_MINB", 6);
@@ -1114,15 +1114,13 @@ cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool d
     FastFn scan;
     if (g_split_lpk == 4) scan = scan_minb == 6 ? k1_scan<4, 14, 6> : k1_scan<4, 14, 8>;
     else scan = scan_minb == 6 ? k1_scan<2, 20, 6> : k1_scan<2, 20, 8>;
-    scan<<<(unsigned)grid_a, kScanThreads, 0, stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pass_kernel(scan, a, (unsigned)grid_a, kScanThreads, 0, stream, pdl);
     if (e != cudaSuccess) return e;
     const long long grid_b = std::max<long long>(1, std::min<long long>(((n + 31) / 32 + kFastWarps - 1) / kFastWarps, max_grid));
     FastFn fit;
     if (debug) fit = k1_fit<true, 4>;
     else fit = fit_minb == 6 ? k1_fit<false, 6> : (fit_minb == 4 ? k1_fit<false, 4> : k1_fit<false, 5>);
-    fit<<<(unsigned)grid_b, kFastThreads, 0, stream>>>(a);
-    return cudaGetLastError();
+    return launch_pass_kernel(fit, a, (unsigned)grid_b, kFastThreads, 0, stream, pdl);
 }
 
 cudaError_t preload_fast_kernels(int device) {

@@ -187,6 +187,12 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
 };
 
 #if defined(__CUDACC__)
+// Programmatic dependent launch (sm_90+): the pass kernels of a sweep are launched with the programmatic-stream-
+// serialization attribute; each lets its successor become resident at once (trigger) and waits for its predecessor's
+// completion and memory flush before touching anything (wait) — stream order with the launch latency hidden.  Both are
+// no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Every pass kernel reads its constants from shared memory: filled from the by-value argument (host-driven pass, pass 0
 // of the device-resident loop) or from the loop state once the ESIKF block has published them.  Returns false when the
 // loop has already ended (the whole grid leaves).
@@ -194,6 +200,8 @@ __device__ __forceinline__ bool load_pass_const(const IekfDev* dev, int wait_pos
                                                 const PassConst& by_value, PassConst& s_c) {
     constexpr int ND = (int)(sizeof(PassConst) / sizeof(double));
     static_assert(sizeof(PassConst) % sizeof(double) == 0, "PassConst is copied as doubles");
+    pdl_trigger();
+    pdl_wait();
     if (dev && wait_pose) {
         __shared__ int s_go;
         if (threadIdx.x == 0) {
@@ -231,7 +239,18 @@ cudaError_t launch_k1_fast(const FastArgs& a, int grid, bool debug, int device, 
 cudaError_t preload_fast_kernels(int device);
 cudaError_t preload_assoc_kernels(int device, int K);
 constexpr int kSplitSlots = 23;   // = NS of srl_fast.cu: candidate slots k1_scan hands to k1_fit per keypoint
-cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream);
+cudaError_t launch_k1_split(const FastArgs& a, long long n, int max_grid, bool debug, int device, cudaStream_t stream, bool pdl);
+// <<<>>> with the programmatic-stream-serialization attribute when pdl is set
+template <typename Args>
+inline cudaError_t launch_pass_kernel(void (*fn)(const Args), const Args& a, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fn, a);
+}
 void k1_split_set_lanes_per_keypoint(int v);
 int k1_fast_max_blocks_per_sm();
 void k1_fast_set_min_blocks(int v);
@@ -243,7 +262,7 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
 size_t k1_smem_bytes(int K);
 int k1_max_blocks_per_sm(int K, int nb);
 void k1_set_min_blocks(int v);
-cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream);
+cudaError_t launch_k1(const K1Args& a, int grid, bool debug, int device, cudaStream_t stream, bool pdl = false);
 cudaError_t launch_k2(const double* rows, int* status, long long k_begin, long long k_end, int cap, long long* state,
                       double* out32, int mark_unvisited, cudaStream_t stream);
 cudaError_t launch_transform(const double* raw, long long n, const PassConst& c, double* out, cudaStream_t stream);
@@ -287,6 +306,8 @@ struct srl_ctx {
     unsigned long long* d_scan_count = nullptr;
     // device-resident updateIEKF loop (row N1)
     bool kernels_preloaded = false;
+    bool pdl = true;                         // option "pdl" / SRL_PDL: programmatic dependent launch of the pass kernels
+    bool eager_order = true;                 // option "eager_order": Morton-order a sweep right behind its upload (default) or at its first pass
     int concurrent_kernels = -1;             // -1 not probed yet; 0: kernels of this process are serialised (profiler): host loop
     bool device_loop = true;                 // option "device_loop" / SRL_DEVICE_LOOP: 0 = the host-driven loop of round 1
     srl::IekfDev* d_iekf = nullptr;

@@ -371,12 +371,13 @@ class LioOptimization:
     # ---- src/optimize.cpp:133-314
     def updateIEKF(self, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None):
         st = self.eskf_pro.to_c()
-        fq = f64(self.eskf_pro.q if frame_q is None else frame_q).copy()
-        ft = f64(self.eskf_pro.p if frame_t is None else frame_t).copy()
+        fq = np.array(self.eskf_pro.q if frame_q is None else frame_q, np.float64)
+        ft = np.array(self.eskf_pro.p if frame_t is None else frame_t, np.float64)
         tl = f64(t_last)
         R = f64(self.R_imu_lidar).reshape(9)
         ti = f64(self.t_imu_lidar)
-        summ = IekfSummary()
+        summ = self._summ if hasattr(self, "_summ") else IekfSummary()   # 6 KB: allocated once, overwritten by every call
+        self._summ = summ
         rc = lib().srl_update_iekf(self.ctx.h, self.voxel_map.h, self.sweep.h, C.byref(st), ptr(fq), ptr(ft), ptr(tl),
                                    ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ))
         if rc == capi.SRL_NAN_PLANARITY:
