@@ -244,6 +244,7 @@ static int launch_pass(srl_ctx* ctx, srl_sweep* sw, const K1Args& a, bool debug,
         f.order = a.rows ? nullptr : sw->d_order;   // the residual cap consumes keypoints in their own order (src/optimize.cpp:68,107)
         f.rows = a.rows;
         f.s_begin = a.k_begin; f.s_end = a.k_end;   // the shard is a range of SORTED positions in this form
+        f.chunk_tickets = ctx->d_chunk_tickets; f.chunk_sums = ctx->d_chunk_sums;
         f.partials = a.partials; f.ticket = a.ticket; f.out32 = ctx->d_fast_out; f.flags = sw->d_flags; f.status = a.status;
         f.dbg_world = a.dbg_world; f.dbg_nbr = a.dbg_nbr; f.dbg_nbr_dist = a.dbg_nbr_dist; f.dbg_plane = a.dbg_plane; f.stats = a.stats;
         f.force_amb_mod = ctx->force_amb_mod;
@@ -301,6 +302,9 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
     ctx->max_grid = 2048;   // rows of the block-partials buffer (>= any grid we launch)
     bool ok = cudaMalloc(&ctx->d_partials, (size_t)ctx->max_grid * 32 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_chunk_tickets, (size_t)(ctx->max_grid / 32 + 1) * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMemset(ctx->d_chunk_tickets, 0, (size_t)(ctx->max_grid / 32 + 1) * sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&ctx->d_chunk_sums, (size_t)(ctx->max_grid / 32 + 1) * 32 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_out32, 64 * sizeof(double)) == cudaSuccess &&
               cudaMalloc(&ctx->d_k2_state, 4 * sizeof(long long)) == cudaSuccess &&
               cudaMalloc(&ctx->d_stats, 6 * sizeof(unsigned long long)) == cudaSuccess &&
@@ -332,7 +336,7 @@ void srl_ctx_destroy(srl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->loop_stream) { cudaStreamSynchronize(ctx->loop_stream); cudaStreamDestroy(ctx->loop_stream); }
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out); cudaFree(ctx->d_scan_count);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_chunk_tickets); cudaFree(ctx->d_chunk_sums); cudaFree(ctx->d_out32); cudaFree(ctx->d_k2_state); cudaFree(ctx->d_stats); cudaFree(ctx->d_fast_out); cudaFree(ctx->d_scan_count);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_iekf);
     if (ctx->h_iekf) cudaFreeHost(ctx->h_iekf);
     for (auto& e : ctx->loop_ev0) if (e) cudaEventDestroy(e);

@@ -51,6 +51,26 @@ __device__ __forceinline__ double transpose_reduce32f(double (&v)[32], int lane)
     return v[0];
 }
 
+// Sum over the 32 lanes of 8 per-lane values w[0..7]: on return every lane holds the total of w[lane & 7].  Three halving
+// steps (4 + 2 + 1 exchanges) leave one value per lane summed over its 8-lane group, two butterflies sum the four groups:
+// 9 exchanges for 8 components, and only 8 values live at a time (the 32-wide transpose needs all 32 in registers).
+__device__ __forceinline__ double reduce8_over_warp(double (&w)[8], int lane) {
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const double send = upper ? w[i] : w[i + s];
+            const double keep = upper ? w[i + s] : w[i];
+            w[i] = keep + __shfl_xor_sync(FULLM, send, s);
+        }
+    }
+    double x = w[0];
+    x += __shfl_xor_sync(FULLM, x, 8);
+    x += __shfl_xor_sync(FULLM, x, 16);
+    return x;
+}
+
 struct SelNb {   // the K selected points: float indices into the block pool (thread-private array)
     const float* blocks;
     const unsigned* pt;
@@ -400,6 +420,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
 // Four times as many, four times shorter warps in the scan; no idle lanes in the fit.
 // =========================================================================================================
 constexpr int kScanThreads = 128;
+constexpr int kChunkBlocks = 32;   // k1_fit's grid reduction: blocks per chunk (a multiple of kFastWarps)
 constexpr unsigned KINF = 0xffffffffu;
 constexpr int kZone0 = 12;     // k1_fit resolves the K-th boundary among slots >= kZone0 (k1_scan flags anything wider)
 constexpr int kRowWords = 24;  // candidate row of a keypoint: NS point ids + header word
@@ -815,9 +836,9 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
             }
         }
 
-        double v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.0;
+        // the keypoint's contribution: J (6), h, d^2 and three flags; the 32 products are formed group by group in the
+        // reduction below so that they never all live in registers
+        double Jr[6] = {0, 0, 0, 0, 0, 0}, hr = 0.0, d2r = 0.0, acc_f = 0.0, full_f = 0.0, nan_f = 0.0;
         int status = 0;
         if (do_fit) {
             // ---- the K-th boundary: slots [0, j0) are in; of the uncertain slots [j0, m) the m - K farthest by exact
@@ -865,23 +886,14 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
             RowNb nbv{A.blocks, cp, mask};
             plane_residual<NS>(nbv, KF, (double)n0.x, (double)n0.y, (double)n0.z, c, pwx, pwy, pwz, bx, by, bz, row);
             status = row.accepted ? 2 : 1;
-            v[29] = 1.0;
-            v[31] = (double)row.nan_planarity;
+            full_f = 1.0;
+            nan_f = (double)row.nan_planarity;
             const double h = row.distance * row.weight;                                                        // :169
             if (row.accepted) {
-                v[0] = row.J[0] * row.J[0]; v[1] = row.J[0] * row.J[1]; v[2] = row.J[0] * row.J[2];
-                v[3] = row.J[0] * row.J[3]; v[4] = row.J[0] * row.J[4]; v[5] = row.J[0] * row.J[5];
-                v[6] = row.J[1] * row.J[1]; v[7] = row.J[1] * row.J[2]; v[8] = row.J[1] * row.J[3];
-                v[9] = row.J[1] * row.J[4]; v[10] = row.J[1] * row.J[5];
-                v[11] = row.J[2] * row.J[2]; v[12] = row.J[2] * row.J[3]; v[13] = row.J[2] * row.J[4];
-                v[14] = row.J[2] * row.J[5];
-                v[15] = row.J[3] * row.J[3]; v[16] = row.J[3] * row.J[4]; v[17] = row.J[3] * row.J[5];
-                v[18] = row.J[4] * row.J[4]; v[19] = row.J[4] * row.J[5];
-                v[20] = row.J[5] * row.J[5];
-                v[21] = row.J[0] * h; v[22] = row.J[1] * h; v[23] = row.J[2] * h;
-                v[24] = row.J[3] * h; v[25] = row.J[4] * h; v[26] = row.J[5] * h;
-                v[27] = row.distance * row.distance;                                                          // :104
-                v[28] = 1.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) Jr[i] = row.J[i];
+                hr = h; d2r = row.distance * row.distance;                                                     // :104
+                acc_f = 1.0;
             }
             if (A.rows) {   // per-keypoint rows for the ordered max_num_residuals cap (src/optimize.cpp:107)
                 double* rr = A.rows + 8 * k;
@@ -930,13 +942,35 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
         }
         if (valid && A.status && !ambiguous) A.status[k] = status;
         __syncwarp();
-        acc += transpose_reduce32f(v, lane);
+        // components 0..20 = upper triangle of J^T J, 21..26 = J^T h, 27 d^2, 28 residuals, 29 full, 30 (scan count), 31 NaN
+        {
+            double w[8];
+            w[0] = Jr[0] * Jr[0]; w[1] = Jr[0] * Jr[1]; w[2] = Jr[0] * Jr[2]; w[3] = Jr[0] * Jr[3];
+            w[4] = Jr[0] * Jr[4]; w[5] = Jr[0] * Jr[5]; w[6] = Jr[1] * Jr[1]; w[7] = Jr[1] * Jr[2];
+            const double t0 = reduce8_over_warp(w, lane);
+            w[0] = Jr[1] * Jr[3]; w[1] = Jr[1] * Jr[4]; w[2] = Jr[1] * Jr[5]; w[3] = Jr[2] * Jr[2];
+            w[4] = Jr[2] * Jr[3]; w[5] = Jr[2] * Jr[4]; w[6] = Jr[2] * Jr[5]; w[7] = Jr[3] * Jr[3];
+            const double t1 = reduce8_over_warp(w, lane);
+            w[0] = Jr[3] * Jr[4]; w[1] = Jr[3] * Jr[5]; w[2] = Jr[4] * Jr[4]; w[3] = Jr[4] * Jr[5];
+            w[4] = Jr[5] * Jr[5]; w[5] = Jr[0] * hr; w[6] = Jr[1] * hr; w[7] = Jr[2] * hr;
+            const double t2 = reduce8_over_warp(w, lane);
+            w[0] = Jr[3] * hr; w[1] = Jr[4] * hr; w[2] = Jr[5] * hr; w[3] = d2r;
+            w[4] = acc_f; w[5] = full_f; w[6] = 0.0; w[7] = nan_f;
+            const double t3 = reduce8_over_warp(w, lane);
+            const int grp = lane >> 3;
+            acc += grp == 0 ? t0 : (grp == 1 ? t1 : (grp == 2 ? t2 : t3));
+        }
     }
 
+    // ---- block sum -> chunk sum (the last block of every 32-block chunk) -> total (the block that closes the last chunk).
+    //      Fixed summation order at every level (run-to-run bitwise deterministic); two short levels instead of one block
+    //      walking all gridDim.x partial rows (for 782 blocks that walk was ~9 us of single-block tail).
     __shared__ double s_acc[kFastWarps][32];
-    __shared__ bool s_last;
+    __shared__ int s_role;
     s_acc[warp][lane] = acc;
     __syncthreads();
+    const unsigned chunk = blockIdx.x / kChunkBlocks, n_chunks = (gridDim.x + kChunkBlocks - 1) / kChunkBlocks;
+    const unsigned in_chunk = min((unsigned)kChunkBlocks, gridDim.x - chunk * kChunkBlocks);
     if (warp == 0) {
         double s = 0.0;
 #pragma unroll
@@ -946,20 +980,46 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(A.ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        const unsigned t = atomicAdd(A.chunk_tickets + chunk, 1u);
+        s_role = (t == in_chunk - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (s_last) {
+    if (!s_role) return;
+    {   // this block closes its chunk: sum the chunk's rows (warp w takes rows w, w + 4, ...: 8 independent loads each)
         __threadfence();
-        double sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fixed-order sum of the block partials, 8 loads in flight per thread
-        int b = warp;
-        for (; b + 7 * kFastWarps < (int)gridDim.x; b += 8 * kFastWarps) {
+        double r[kChunkBlocks / kFastWarps];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) sacc[u] += __ldcg(A.partials + (size_t)(b + u * kFastWarps) * 32 + lane);
+        for (int u = 0; u < kChunkBlocks / kFastWarps; ++u) {
+            const unsigned row = (unsigned)(warp + u * kFastWarps);
+            r[u] = row < in_chunk ? __ldcg(A.partials + (size_t)(chunk * kChunkBlocks + row) * 32 + lane) : 0.0;
         }
-        for (; b < (int)gridDim.x; b += kFastWarps) sacc[0] += __ldcg(A.partials + (size_t)b * 32 + lane);
-        const double s = ((sacc[0] + sacc[1]) + (sacc[2] + sacc[3])) + ((sacc[4] + sacc[5]) + (sacc[6] + sacc[7]));
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < kChunkBlocks / kFastWarps; ++u) s += r[u];
+        __syncthreads();
+        s_acc[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0) {
+            double cs = 0.0;
+#pragma unroll
+            for (int w = 0; w < kFastWarps; ++w) cs += s_acc[w][lane];
+            A.chunk_sums[(size_t)chunk * 32 + lane] = cs;
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            A.chunk_tickets[chunk] = 0u;
+            const unsigned t = atomicAdd(A.ticket, 1u);
+            s_role = (t == n_chunks - 1) ? 2 : 0;
+        }
+        __syncthreads();
+        if (s_role != 2) return;
+    }
+    {   // this block closes the last chunk: the pass's totals
+        __threadfence();
+        double s = 0.0;
+        for (unsigned ch = (unsigned)warp; ch < n_chunks; ch += kFastWarps) s += __ldcg(A.chunk_sums + (size_t)ch * 32 + lane);
+        __syncthreads();
         s_acc[warp][lane] = s;
         __syncthreads();
         if (warp == 0) {

@@ -184,6 +184,8 @@ struct FastArgs {               // k1_fast (srl_fast.cu)
     unsigned long long pose_ticket, end_ticket;
     int wait_pose;
     double* rows;                     // optional n*8 per-keypoint rows (J6, h, d^2) for the ordered residual cap (k2_cap_reduce)
+    unsigned int* chunk_tickets;      // k1_fit's two-level grid reduction: one ticket and one 32-double sum per chunk of 32 blocks
+    double* chunk_sums;
 };
 
 #if defined(__CUDACC__)
@@ -291,6 +293,8 @@ struct srl_ctx {
     double* d_partials = nullptr;   // [max_grid][32]
     int max_grid = 0;
     unsigned int* d_ticket = nullptr;
+    unsigned int* d_chunk_tickets = nullptr;   // [max_grid / 32 + 1], zero between passes
+    double* d_chunk_sums = nullptr;            // [max_grid / 32 + 1][32]
     double* d_out32 = nullptr;
     double* h_out32 = nullptr;      // pinned + mapped: [0,32) sums, [32] sequence flag written by the pass's last kernel, [33..64) scratch
     double* d_h_out32 = nullptr;    // device-side address of h_out32
