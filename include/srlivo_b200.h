@@ -249,7 +249,8 @@ int srl_sweep_transform_device(srl_ctx* ctx, srl_sweep* sweep, const double q[4]
  * src/optimize.cpp:431.  One point per cell of size_voxel_subsampling (the first in frame order), emitted in the
  * reference's order, i.e. the iteration order of its std::tr1::unordered_map<voxel, ...> grid.  The dedupe over the n
  * points runs on the GPU; the order is produced by replaying the unique cells through the same libstdc++ container.
- * xyz_world: host n*3 doubles (point3D::point); keypoint_index_out: capacity n; indices into the frame. */
+ * xyz_world: n*3 doubles (point3D::point) in host memory or already in HBM (detected per pointer; a device frame is not
+ * copied, only the coordinates of the kept points come back for the replay); keypoint_index_out: host, capacity n. */
 int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double size_voxel_subsampling,
                       uint32_t* keypoint_index_out, size_t* n_keypoints);
 
@@ -281,6 +282,43 @@ int srl_distort_frame_by_imu(srl_ctx* ctx, const double* raw_xyz, const double* 
 /* transformAllImuPoint (src/utility.cpp:320-332): raw_point = R_il^T (R(q_end)^-1 imu_point - R(q_end)^-1 t_end) - R_il^T t_il */
 int srl_transform_all_imu_point(srl_ctx* ctx, const double* imu_xyz, size_t n, const srl_imu_state* last_state,
                                 const double R_imu_lidar[9], const double t_imu_lidar[3], double* raw_xyz_out);
+
+/* ---- row N4: the colour map fed by the map update (src/lioOptimization.cpp:448-551, colour branch) and the renderer that
+ * colours its points from a camera frame (src/rgbMapTracker.cpp:181-237 with rgbPoint::updateRgb, src/cloudMap.cpp:59-101).
+ * A colour map = a voxel map (same HBM layout as srl_map; srl_color_map_voxels exposes it for download / stats) whose
+ * points carry (rgb, N_rgb, cov_rgb, observe_distance, last_observe_time), the fine occupancy set hashmap_3d_points
+ * (cells of min_distance_points) that decides which stored points enter rgb_points_vec, and the list of voxels
+ * visited for the first time by the sweeps since the last rendering (voxels_recent_visited). */
+typedef struct srl_color_map srl_color_map;
+typedef struct srl_camera {      /* the state fields cloudFrame::project3dTo2d / if2dPointsAvailable read (include/state.h) */
+    double q_camera_world[4];    /* x, y, z, w */
+    double t_camera_world[3];
+    double t_world_camera[3];
+    double fx, fy, cx, cy;
+    double fov_margin;
+    int32_t cols, rows;          /* image_cols, image_rows */
+} srl_camera;
+int srl_color_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_voxel, size_t max_voxels,
+                         double min_distance_points, srl_color_map** out);
+void srl_color_map_destroy(srl_color_map* cm);
+srl_map* srl_color_map_voxels(srl_color_map* cm);
+int srl_color_map_stats(srl_color_map* cm, int64_t* n_voxels, int64_t* n_points, int64_t* n_rgb_points, int64_t* n_recent,
+                        int64_t* n_new_recent);
+/* the loop of addPointsToMap over the registered frame (:533-542): every add_point_step-th point, sweep order, through
+ * addPointToColorMap (min_num_points = 0).  xyz_world: host or device, n*3 doubles.  to_rendering mirrors the flag of
+ * addPointsToMap (clears voxels_recent_visited_temp first, publishes it to the renderer afterwards). */
+int srl_color_map_add_points(srl_color_map* cm, const double* xyz_world, size_t n, int32_t add_point_step, double time_sweep_end,
+                             double time_last_process, int32_t to_rendering, int64_t* n_stored);
+/* renderPointsInRecentVoxel: every point of every recently visited voxel is projected into the frame (pinhole, scale 1),
+ * tested against the FoV margin, coloured by bilinear interpolation of the BGR8 image (host or device, rows*cols*3,
+ * OpenCV's saturating Vec3b arithmetic) and fused with rgbPoint::updateRgb; *n_rendered = render_point_count. */
+int srl_color_map_render_recent(srl_color_map* cm, const srl_camera* cam, const uint8_t* image_bgr, double obs_time, int64_t* n_rendered);
+/* colour state in the voxel order of srl_map_download(srl_color_map_voxels(cm)): rgb nv*cap*3, n_rgb nv*cap, cov nv*cap*3,
+ * obs_dist nv*cap, last_obs nv*cap, last_visited nv */
+int srl_color_map_download_state(srl_color_map* cm, size_t max_voxels, int16_t* rgb, int16_t* n_rgb, float* cov, double* obs_dist,
+                                 double* last_obs, double* last_visited);
+/* rgb_points_vec as (voxel key x,y,z, index in block) per entry, voxels_recent_visited as voxel keys */
+int srl_color_map_download_lists(srl_color_map* cm, int16_t* rgb_points, int16_t* recent);
 
 /* eskfEstimator::observe (src/eskfEstimator.cpp:219-230) — host math, exported for parity tests */
 int srl_eskf_observe(srl_eskf_state* eskf, const double d_x[17]);

@@ -385,3 +385,65 @@ def mat17_inverse(A):
 
 def voxel_hash(x, y, z) -> int:
     return int(lib().orc_voxel_hash(int(x), int(y), int(z)))
+
+
+class OracleColorMap:
+    """Row N4 oracle: the colour branch of addPointsToMap + renderPointsInRecentVoxel (see srl_oracle.cpp)."""
+
+    def __init__(self, voxel_size=1.0, max_num_points_in_voxel=20, min_distance_points=0.15):
+        L = lib()
+        L.orc_color_create.restype = C.c_void_p
+        L.orc_color_destroy.argtypes = [C.c_void_p]
+        L.orc_color_add_points.restype = C.c_int64
+        L.orc_color_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, C.c_double, C.c_int32,
+                                           C.c_double, C.c_double, C.c_int32]
+        L.orc_color_render.restype = C.c_int64
+        L.orc_color_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double]
+        for f in ("orc_color_num_voxels", "orc_color_num_rgb_points", "orc_color_num_recent", "orc_color_num_new_recent"):
+            getattr(L, f).restype = C.c_int64
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_color_snapshot.restype = C.c_int64
+        L.orc_color_snapshot.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 9
+        L.orc_color_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._h = C.c_void_p(L.orc_color_create())
+        self.voxel_size, self.cap, self.min_dist = voxel_size, max_num_points_in_voxel, min_distance_points
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_color_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add_points(self, xyz, add_point_step=1, time_sweep_end=1.0, time_last_process=0.0, to_rendering=True) -> int:
+        xyz = _f64(xyz).reshape(-1, 3)
+        return int(lib().orc_color_add_points(self._h, _ptr(xyz), xyz.shape[0], self.voxel_size, self.cap, self.min_dist,
+                                              add_point_step, time_sweep_end, time_last_process, 1 if to_rendering else 0))
+
+    def render(self, cam15, image_bgr, obs_time) -> int:
+        cam = _f64(cam15).reshape(15)
+        img = np.ascontiguousarray(image_bgr, np.uint8)
+        return int(lib().orc_color_render(self._h, _ptr(cam), _ptr(img), img.shape[0], img.shape[1], float(obs_time)))
+
+    def counts(self):
+        L = lib()
+        return dict(voxels=int(L.orc_color_num_voxels(self._h)), rgb_points=int(L.orc_color_num_rgb_points(self._h)),
+                    recent=int(L.orc_color_num_recent(self._h)), new_recent=int(L.orc_color_num_new_recent(self._h)))
+
+    def snapshot(self):
+        nv, cap = self.counts()["voxels"], self.cap
+        out = dict(keys=np.zeros((nv, 3), np.int16), counts=np.zeros(nv, np.int32), xyz=np.zeros((nv, cap, 3), np.float32),
+                   rgb=np.zeros((nv, cap, 3), np.int16), n_rgb=np.zeros((nv, cap), np.int16), cov=np.zeros((nv, cap, 3), np.float32),
+                   obs_dist=np.zeros((nv, cap)), last_obs=np.zeros((nv, cap)), last_visited=np.zeros(nv))
+        got = lib().orc_color_snapshot(self._h, cap, *[_ptr(out[k]) for k in ("keys", "counts", "xyz", "rgb", "n_rgb", "cov", "obs_dist",
+                                                                                "last_obs", "last_visited")])
+        assert got == nv
+        return out
+
+    def lists(self):
+        c = self.counts()
+        rgb_points = np.zeros((c["rgb_points"], 4), np.int16)
+        recent = np.zeros((c["recent"], 3), np.int32)
+        lib().orc_color_lists(self._h, _ptr(rgb_points), _ptr(recent))
+        return rgb_points, recent

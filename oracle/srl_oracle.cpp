@@ -59,6 +59,8 @@
 #else
 #include <unordered_map>
 #endif
+#include <array>
+#include <unordered_map>
 
 namespace {
 
@@ -1288,6 +1290,231 @@ void orc_quat_to_rot(const double q[4], double R[9]) {
 void orc_eig3_sym(const double S[9], double evals[3], double evecs[9]) { eig3_sym(S, evals, evecs); }
 void orc_eskf_observe(orc_eskf_state* s, const double dx[17]) { eskf_observe(s, dx); }
 int32_t orc_mat17_inverse(const double* A, double* Ainv) { return mat_inverse(A, Ainv, NS) ? 1 : 0; }
+// ======================================================================================
+// Row N4: the colour map (vision side of the map update).  Restates
+//   lioOptimization::addPointToColorMap           src/lioOptimization.cpp:448-518
+//   its driver loop in addPointsToMap             src/lioOptimization.cpp:520-551 (colour branch only)
+//   rgbMapTracker::renderPointsInRecentVoxel /
+//   threadRenderPointsInVoxel                     src/rgbMapTracker.cpp:181-237 (sequential: the reference's
+//                                                 cv::parallel_for_ + mutex leaves the per-point result unchanged
+//                                                 as long as a voxel appears once in the list; duplicates are
+//                                                 applied here in list order)
+//   cloudFrame::project3dTo2d / if2dPointsAvailable / getRgb / getSubPixel   src/lioOptimization.cpp:49-190
+//   rgbPoint::updateRgb                           src/cloudMap.cpp:59-101
+// Third-party arithmetic absent from /root/reference: OpenCV's cv::Vec3b operators (double * Vec3b and
+// Vec3b + Vec3b saturate every element to uchar with cvRound = round-half-to-even) — restated from
+// OpenCV 4's matx.hpp / saturate.hpp; PARITY UNPINNED like the rest of the oracle.
+// ======================================================================================
+struct voxelId { int kx, ky, kz; };   // include/cloudMap.h:88-95
+struct ColorMap {
+    voxelHashMap map;                                                                    // color_voxel_map
+    std::unordered_map<long, std::unordered_map<long, std::unordered_map<long, int>>> hash3d;   // hashmap_3d_points (value: index into rgb_points)
+    std::vector<std::array<short, 4>> rgb_points;                                        // rgb_points_vec as (voxel key, index in block)
+    std::vector<voxelId> recent_temp;                                                    // voxels_recent_visited_temp
+    std::vector<voxelId> recent;                                                         // map_tracker->voxels_recent_visited
+    long number_of_new_visited_voxel = 0;
+};
+
+static int hash3d_exist(ColorMap& cm, long x, long y, long z) {      // Hash_map_3d::if_exist (include/utility.h:105-119)
+    auto a = cm.hash3d.find(x);
+    if (a == cm.hash3d.end()) return 0;
+    auto b = a->second.find(y);
+    if (b == a->second.end()) return 0;
+    return b->second.find(z) == b->second.end() ? 0 : 1;
+}
+
+// lioOptimization::addPointToColorMap (src/lioOptimization.cpp:448-518); returns 1 if the point was stored in a voxel
+static int addPointToColorMap(ColorMap& cm, rgbPoint& point, double voxel_size, int max_num_points_in_voxel,
+                              double min_distance_points, int min_num_points, double time_sweep_end, double time_last_process) {
+    bool add_point = true;
+    int stored = 0;
+    int point_map_kx = static_cast<short>(point.getPosition()[0] / min_distance_points);
+    int point_map_ky = static_cast<short>(point.getPosition()[1] / min_distance_points);
+    int point_map_kz = static_cast<short>(point.getPosition()[2] / min_distance_points);
+    int kx = static_cast<short>(point.getPosition()[0] / voxel_size);
+    int ky = static_cast<short>(point.getPosition()[1] / voxel_size);
+    int kz = static_cast<short>(point.getPosition()[2] / voxel_size);
+    if (hash3d_exist(cm, point_map_kx, point_map_ky, point_map_kz)) add_point = false;
+    auto search = cm.map.find(voxel(kx, ky, kz));
+    if (search != cm.map.end()) {
+        voxelBlock& voxel_block = MAP_VALUE(search);
+        if (!voxel_block.IsFull()) {
+            if (min_num_points <= 0 || voxel_block.NumPoints() >= min_num_points) {
+                voxel_block.AddPoint(point);
+                stored = 1;
+                if (add_point) {
+                    point.point_index = (int)cm.rgb_points.size();
+                    cm.rgb_points.push_back({{(short)kx, (short)ky, (short)kz, (short)(voxel_block.NumPoints() - 1)}});
+                    cm.hash3d[point_map_kx][point_map_ky][point_map_kz] = point.point_index;
+                }
+            }
+        }
+        if (std::fabs(time_sweep_end - time_last_process) > 1e-5 && std::fabs(voxel_block.last_visited_time - time_sweep_end) > 1e-5) {
+            voxel_block.last_visited_time = time_sweep_end;
+            cm.recent_temp.push_back({kx, ky, kz});
+        }
+    } else {
+        if (min_num_points <= 0) {
+            voxelBlock voxel_block(max_num_points_in_voxel);
+            voxel_block.AddPoint(point);
+            cm.map[voxel(kx, ky, kz)] = std::move(voxel_block);
+            stored = 1;
+            if (add_point) {
+                point.point_index = (int)cm.rgb_points.size();
+                cm.rgb_points.push_back({{(short)kx, (short)ky, (short)kz, 0}});
+                cm.hash3d[point_map_kx][point_map_ky][point_map_kz] = point.point_index;
+            }
+            voxelBlock& vb = cm.map[voxel(kx, ky, kz)];
+            if (std::fabs(time_sweep_end - time_last_process) > 1e-5 && std::fabs(vb.last_visited_time - time_sweep_end) > 1e-5) {
+                vb.last_visited_time = time_sweep_end;
+                cm.recent_temp.push_back({kx, ky, kz});
+            }
+        }
+    }
+    return stored;
+}
+
+static inline unsigned char sat_u8(double v) {       // cv::saturate_cast<uchar>(double): cvRound (lrint, half to even) then clamp
+    long r = std::lrint(v);
+    return (unsigned char)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+static inline unsigned char sat_add_u8(unsigned char a, unsigned char b) { int r = (int)a + (int)b; return (unsigned char)(r > 255 ? 255 : r); }
+
+// rgbPoint::updateRgb (src/cloudMap.cpp:59-101)
+static int updateRgb(rgbPoint& p, const double rgb_[3], double observe_distance_, const double observe_sigma_[3], double observe_time_) {
+    const double process_noise_sigma = 0.1;
+    if (p.observe_distance != 0 && (observe_distance_ > p.observe_distance * 1.2)) return 0;
+    if (p.N_rgb == 0) {
+        p.last_observe_time = observe_time_;
+        p.observe_distance = observe_distance_;
+        for (int i = 0; i < 3; i++) {
+            p.rgb[0] = (short)std::round(rgb_[0]);
+            p.rgb[1] = (short)std::round(rgb_[1]);
+            p.rgb[2] = (short)std::round(rgb_[2]);
+            for (int a = 0; a < 3; ++a) p.cov_rgb[a] = (float)observe_sigma_[a];
+        }
+        p.N_rgb = 1;
+        return 0;
+    }
+    for (int i = 0; i < 3; i++) {
+        p.cov_rgb[i] = (float)(p.cov_rgb[i] + process_noise_sigma * (observe_time_ - p.last_observe_time));   // float(float + double)
+        double old_sigma = p.cov_rgb[i];
+        p.cov_rgb[i] = (float)std::sqrt(1.0 / (1.0 / (p.cov_rgb[i] * p.cov_rgb[i]) + 1.0 / (observe_sigma_[i] * observe_sigma_[i])));
+        p.rgb[i] = (short)(p.cov_rgb[i] * p.cov_rgb[i] * (p.rgb[i] / (old_sigma * old_sigma) + rgb_[i] / (observe_sigma_[i] * observe_sigma_[i])));
+    }
+    if (observe_distance_ < p.observe_distance) p.observe_distance = observe_distance_;
+    p.last_observe_time = observe_time_;
+    p.N_rgb++;
+    return 1;
+}
+
 uint64_t orc_voxel_hash(int16_t x, int16_t y, int16_t z) { return (uint64_t)voxel_hash()(voxel(x, y, z)); }
+
+
+// ---- colour map C API ---------------------------------------------------------------------------------
+void* orc_color_create(void) { return new ColorMap(); }
+void orc_color_destroy(void* cm) { delete static_cast<ColorMap*>(cm); }
+
+// the colour branch of lioOptimization::addPointsToMap (src/lioOptimization.cpp:520-551)
+int64_t orc_color_add_points(void* cm_, const double* xyz, int64_t n, double voxel_size, int32_t max_num_points_in_voxel,
+                             double min_distance_points, int32_t add_point_step, double time_sweep_end, double time_last_process,
+                             int32_t to_rendering) {
+    ColorMap& cm = *static_cast<ColorMap*>(cm_);
+    if (to_rendering) { cm.recent_temp.clear(); std::vector<voxelId>().swap(cm.recent_temp); }
+    int number_of_voxels_before_add = (int)cm.recent_temp.size();
+    int64_t stored = 0;
+    int point_idx = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        rgbPoint rgb_point({{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}});
+        if (point_idx % add_point_step == 0)
+            stored += addPointToColorMap(cm, rgb_point, voxel_size, max_num_points_in_voxel, min_distance_points, 0, time_sweep_end, time_last_process);
+        point_idx++;
+    }
+    if (to_rendering) {
+        cm.recent = cm.recent_temp;
+        cm.number_of_new_visited_voxel = (long)cm.recent.size() - number_of_voxels_before_add;
+    }
+    return stored;
+}
+
+// rgbMapTracker::renderPointsInRecentVoxel (src/rgbMapTracker.cpp:181-237) over map_tracker->voxels_recent_visited.
+// cam: q_camera_world (x,y,z,w), t_camera_world, t_world_camera, fx, fy, cx, cy, fov_margin  (17 doubles); image BGR u8.
+int64_t orc_color_render(void* cm_, const double* cam, const uint8_t* image, int32_t rows, int32_t cols, double obs_time) {
+    ColorMap& cm = *static_cast<ColorMap*>(cm_);
+    const Mat3 R = quat_to_rot({cam[0], cam[1], cam[2], cam[3]});
+    const Vec3 t_cw = {{cam[4], cam[5], cam[6]}}, t_wc = {{cam[7], cam[8], cam[9]}};
+    const double fx = cam[10], fy = cam[11], cx = cam[12], cy = cam[13], fov_margin = cam[14];
+    const double image_obs_cov = 15;
+    const double sigma[3] = {image_obs_cov, image_obs_cov, image_obs_cov};
+    int64_t render_point_count = 0;
+    auto pix = [&](int r, int c, int ch) -> unsigned char { return image[((size_t)r * cols + c) * 3 + ch]; };
+    for (const voxelId& id : cm.recent) {
+        voxelBlock& voxel_block = cm.map[voxel((short)id.kx, (short)id.ky, (short)id.kz)];
+        for (int point_index = 0; point_index < voxel_block.NumPoints(); point_index++) {
+            rgbPoint& point = voxel_block.points[(size_t)point_index];
+            const Vec3 point_world = point.getPosition();
+            // project3dTo2d (src/lioOptimization.cpp:132-152), scale 1
+            const Vec3 pc = vadd(matvec(R, point_world), t_cw);
+            if (pc[2] < 0.001) continue;
+            double u = (pc[0] * fx / pc[2] + cx) * 1.0;
+            double v = (pc[1] * fy / pc[2] + cy) * 1.0;
+            // if2dPointsAvailable (:49-60)
+            if (!((u / 1.0 >= (fov_margin * cols + 1)) && (std::ceil(u / 1.0) < ((1 - fov_margin) * cols)) &&
+                  (v / 1.0 >= (fov_margin * rows + 1)) && (std::ceil(v / 1.0) < ((1 - fov_margin) * rows)))) continue;
+            const double point_camera_norm = norm3(vsub(point_world, t_wc));
+            // getSubPixel<cv::Vec3b>(rgb_image, v, u, 0) (:71-98): four saturated products, three saturated sums
+            const int floor_row = (int)std::floor(v), floor_col = (int)std::floor(u);
+            const double frac_row = v - floor_row, frac_col = u - floor_col;
+            const int ceil_row = floor_row + 1, ceil_col = floor_col + 1;
+            double color[3];
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned char a = sat_u8(pix(floor_row, floor_col, ch) * ((1.0 - frac_row) * (1.0 - frac_col)));
+                const unsigned char b = sat_u8(pix(ceil_row, floor_col, ch) * (frac_row * (1.0 - frac_col)));
+                const unsigned char c = sat_u8(pix(floor_row, ceil_col, ch) * ((1.0 - frac_row) * frac_col));
+                const unsigned char d = sat_u8(pix(ceil_row, ceil_col, ch) * (frac_row * frac_col));
+                color[ch] = (double)sat_add_u8(sat_add_u8(sat_add_u8(a, b), c), d);
+            }
+            if (updateRgb(point, color, point_camera_norm, sigma, obs_time)) render_point_count++;
+        }
+    }
+    return render_point_count;
+}
+
+int64_t orc_color_num_voxels(void* cm) { return (int64_t) static_cast<ColorMap*>(cm)->map.size(); }
+int64_t orc_color_num_rgb_points(void* cm) { return (int64_t) static_cast<ColorMap*>(cm)->rgb_points.size(); }
+int64_t orc_color_num_recent(void* cm) { return (int64_t) static_cast<ColorMap*>(cm)->recent.size(); }
+int64_t orc_color_num_new_recent(void* cm) { return (int64_t) static_cast<ColorMap*>(cm)->number_of_new_visited_voxel; }
+// voxel contents in container order: keys nv*3, counts nv, xyz nv*cap*3, rgb nv*cap*3, n_rgb nv*cap, cov nv*cap*3,
+// obs_dist nv*cap, last_obs nv*cap, last_visited nv
+int64_t orc_color_snapshot(void* cm_, int32_t cap, int16_t* keys, int32_t* counts, float* xyz, int16_t* rgb, int16_t* n_rgb,
+                           float* cov, double* obs_dist, double* last_obs, double* last_visited) {
+    ColorMap& cm = *static_cast<ColorMap*>(cm_);
+    int64_t v = 0;
+    for (auto& it : cm.map) {
+        keys[3 * v] = it.first.x; keys[3 * v + 1] = it.first.y; keys[3 * v + 2] = it.first.z;
+        const int c = std::min<int>(it.second.NumPoints(), cap);
+        counts[v] = c;
+        last_visited[v] = it.second.last_visited_time;
+        for (int i = 0; i < cap; ++i) {
+            const size_t e = (size_t)v * cap + i;
+            const rgbPoint* p = i < c ? &it.second.points[(size_t)i] : nullptr;
+            for (int a = 0; a < 3; ++a) {
+                xyz[e * 3 + a] = p ? p->position[a] : 0.f;
+                rgb[e * 3 + a] = p ? p->rgb[a] : (short)0;
+                cov[e * 3 + a] = (p && p->N_rgb > 0) ? p->cov_rgb[a] : 0.f;   // cov_rgb is uninitialised before the first observation
+            }
+            n_rgb[e] = p ? p->N_rgb : (short)0;
+            obs_dist[e] = p ? p->observe_distance : 0.0;
+            last_obs[e] = p ? p->last_observe_time : 0.0;
+        }
+        ++v;
+    }
+    return v;
+}
+void orc_color_lists(void* cm_, int16_t* rgb_points /* n*4 */, int32_t* recent /* m*3 */) {
+    ColorMap& cm = *static_cast<ColorMap*>(cm_);
+    for (size_t i = 0; i < cm.rgb_points.size(); ++i) for (int a = 0; a < 4; ++a) rgb_points[4 * i + a] = cm.rgb_points[i][(size_t)a];
+    for (size_t i = 0; i < cm.recent.size(); ++i) { recent[3 * i] = cm.recent[i].kx; recent[3 * i + 1] = cm.recent[i].ky; recent[3 * i + 2] = cm.recent[i].kz; }
+}
 
 }  // extern "C"

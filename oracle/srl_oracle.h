@@ -154,6 +154,21 @@ void orc_eskf_observe(orc_eskf_state* s, const double dx[17]);        /* src/esk
 int32_t orc_mat17_inverse(const double* A, double* Ainv);             /* PartialPivLU inverse */
 uint64_t orc_voxel_hash(int16_t x, int16_t y, int16_t z);             /* include/cloudMap.h:173-184 */
 
+/* ---- row N4: colour map (src/lioOptimization.cpp:448-551 colour branch, src/rgbMapTracker.cpp:181-237, src/cloudMap.cpp:59-101) */
+void* orc_color_create(void);
+void orc_color_destroy(void* cm);
+int64_t orc_color_add_points(void* cm, const double* xyz, int64_t n, double voxel_size, int32_t max_num_points_in_voxel,
+                             double min_distance_points, int32_t add_point_step, double time_sweep_end, double time_last_process,
+                             int32_t to_rendering);
+int64_t orc_color_render(void* cm, const double* cam15, const uint8_t* image_bgr, int32_t rows, int32_t cols, double obs_time);
+int64_t orc_color_num_voxels(void* cm);
+int64_t orc_color_num_rgb_points(void* cm);
+int64_t orc_color_num_recent(void* cm);
+int64_t orc_color_num_new_recent(void* cm);
+int64_t orc_color_snapshot(void* cm, int32_t cap, int16_t* keys, int32_t* counts, float* xyz, int16_t* rgb, int16_t* n_rgb,
+                           float* cov, double* obs_dist, double* last_obs, double* last_visited);
+void orc_color_lists(void* cm, int16_t* rgb_points, int32_t* recent);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,13 @@ class ImuState(C.Structure):
                 ("un_acc", C.c_double * 3), ("un_gyr", C.c_double * 3)]
 
 
+class Camera(C.Structure):
+    """srl_camera: the state fields cloudFrame::project3dTo2d / if2dPointsAvailable read (include/state.h)."""
+    _fields_ = [("q_camera_world", C.c_double * 4), ("t_camera_world", C.c_double * 3), ("t_world_camera", C.c_double * 3),
+                ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("fov_margin", C.c_double),
+                ("cols", C.c_int32), ("rows", C.c_int32)]
+
+
 class IekfIter(C.Structure):
     _fields_ = [("predict", EskfState), ("pass_index", C.c_int32), ("max_num_iter", C.c_int32)]
 
@@ -79,6 +86,8 @@ EXPORTS = [
     "srl_update_iekf_dist", "srl_optimize_host", "srl_optimize_host_dist", "srl_shard_range", "srl_sweep_transform_device",
     "srl_grid_sampling", "srl_eskf_observe", "srl_host_plane_fit",
     "srl_distort_frame_by_constant", "srl_distort_frame_by_imu", "srl_transform_all_imu_point",
+    "srl_color_map_create", "srl_color_map_destroy", "srl_color_map_voxels", "srl_color_map_stats", "srl_color_map_add_points",
+    "srl_color_map_render_recent", "srl_color_map_download_state", "srl_color_map_download_lists",
 ]
 
 _lib = None
@@ -154,6 +163,16 @@ def lib():
     L.srl_distort_frame_by_imu.argtypes = [vp, vp, vp, sz, vp, sz, dbl, vp, vp, vp, C.POINTER(i64)]
     L.srl_transform_all_imu_point.argtypes = [vp, vp, sz, vp, vp, vp, vp]
     L.srl_host_plane_fit.argtypes = [vp, i32, vp, vp, vp]
+    L.srl_color_map_create.argtypes = [vp, dbl, i32, sz, dbl, C.POINTER(vp)]
+    L.srl_color_map_destroy.argtypes = [vp]
+    L.srl_color_map_destroy.restype = None
+    L.srl_color_map_voxels.argtypes = [vp]
+    L.srl_color_map_voxels.restype = vp
+    L.srl_color_map_stats.argtypes = [vp] + [C.POINTER(i64)] * 5
+    L.srl_color_map_add_points.argtypes = [vp, vp, sz, i32, dbl, dbl, i32, C.POINTER(i64)]
+    L.srl_color_map_render_recent.argtypes = [vp, C.POINTER(Camera), vp, dbl, C.POINTER(i64)]
+    L.srl_color_map_download_state.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
+    L.srl_color_map_download_lists.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("srl_abi_version",):

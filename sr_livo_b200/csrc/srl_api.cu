@@ -63,6 +63,7 @@ void make_pass_const(const srl_frame& f, const srl_icp_params& p, PassConst& c) 
     for (int i = 0; i < 3; ++i) { c.t[i] = f.t_cur[i]; c.t_last[i] = f.t_last[i]; c.t_il[i] = f.t_il[i]; }
     for (int i = 0; i < 9; ++i) c.R_il[i] = f.R_il[i];
     c.size = p.size_voxel_map;
+    { int e = 0; c.inv_size = std::frexp(c.size, &e) == 0.5 ? 1.0 / c.size : 0.0; c.pad_ = 0.0; }   // exact reciprocal only for 2^k
     double lw = std::fabs(p.weight_alpha), ln = std::fabs(p.weight_neighborhood);
     const double sum = lw + ln;
     c.lambda_w = lw / sum; c.lambda_n = ln / sum;

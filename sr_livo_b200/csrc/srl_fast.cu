@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) 
             bx = SRL_ADD(tx, c.t_il[0]); by = SRL_ADD(ty, c.t_il[1]); bz = SRL_ADD(tz, c.t_il[2]);      // src/optimize.cpp:83
             matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);
             pwx = SRL_ADD(tx, c.t[0]); pwy = SRL_ADD(ty, c.t[1]); pwz = SRL_ADD(tz, c.t[2]);            // :38
-            const double qx = SRL_DIV(pwx, c.size), qy = SRL_DIV(pwy, c.size), qz = SRL_DIV(pwz, c.size);   // :372-374
+            const double qx = voxel_quotient(pwx, c), qy = voxel_quotient(pwy, c), qz = voxel_quotient(pwz, c);   // :372-374
             in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;
             if (in_range) {
                 kx = (int)qx; ky = (int)qy; kz = (int)qz;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) 
             const double bx = SRL_ADD(tx, c.t_il[0]), by = SRL_ADD(ty, c.t_il[1]), bz = SRL_ADD(tz, c.t_il[2]);   // src/optimize.cpp:83
             matvec3_exact(c.Rn, bx, by, bz, tx, ty, tz);
             const double pwx = SRL_ADD(tx, c.t[0]), pwy = SRL_ADD(ty, c.t[1]), pwz = SRL_ADD(tz, c.t[2]);         // :38
-            const double qx = SRL_DIV(pwx, c.size), qy = SRL_DIV(pwy, c.size), qz = SRL_DIV(pwz, c.size);        // :372-374
+            const double qx = voxel_quotient(pwx, c), qy = voxel_quotient(pwy, c), qz = voxel_quotient(pwz, c);        // :372-374
             in_range = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0;
             if (in_range) {
                 kx = (int)qx; ky = (int)qy; kz = (int)qz;

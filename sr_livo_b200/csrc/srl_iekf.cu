@@ -223,7 +223,7 @@ __device__ __noinline__ void iekf_post(IekfShared& S, bool dry) {
         const double* q = S.q_new;
         const double n2 = (q[0] * q[0] + q[2] * q[2]) + (q[1] * q[1] + q[3] * q[3]);
         double qn[4] = {q[0], q[1], q[2], q[3]};
-        if (n2 > 0.0) { const double n = sqrt(n2); for (int i = 0; i < 4; ++i) qn[i] = q[i] / n; }
+        if (n2 > 0.0) { const double rn = rsqrt(n2); for (int i = 0; i < 4; ++i) qn[i] = q[i] * rn; }   // (q_new is already unit to 1 ulp)
         quat_to_rot(qn, S.Rn);
         quat_to_rot(q, S.Rq);
     } else if (warp == 2 && lane == 0) {

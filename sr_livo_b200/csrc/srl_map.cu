@@ -199,6 +199,239 @@ __global__ void k_first_in_cell(const unsigned long long* __restrict__ keys_sort
     is_first[idx_sorted[j]] = (k != kInvalidKey && (j == 0 || keys_sorted[j - 1] != k)) ? 1 : 0;
 }
 
+// ---- N4: colour map (src/lioOptimization.cpp:448-551 colour branch; src/rgbMapTracker.cpp:181-237; src/cloudMap.cpp:59-101) ----
+// The colour map is a second voxel map (same slot table / block pool) whose points carry a colour estimate, plus
+//   * a fine occupancy set (cells of min_distance_points, the reference's Hash_map_3d hashmap_3d_points) that decides
+//     which stored points also enter rgb_points_vec, and
+//   * the list of voxels first visited by the current sweep(s) (voxels_recent_visited_temp), which the renderer walks.
+// addPointToColorMap is sequential in the reference; the same (sort by voxel, replay per voxel in sweep order) scheme as K3
+// reproduces it: a voxel accepts the first (cap - count) offered points, a fine cell is claimed by the first ACCEPTED
+// point of the sweep that falls into it, and both lists are emitted in sweep order.
+struct ColorPoint {            // colour state of one stored point (rgbPoint minus position), index = block * cap + i
+    short rgb[3]; short n_rgb;
+    float cov[3]; float pad;
+    double obs_dist, last_obs;
+};
+constexpr unsigned kNoIndex = 0xffffffffu;
+
+// selected points (every step-th of the frame): voxel key + fine key from the float-rounded position (getPosition())
+__global__ void k_color_keys(const double* __restrict__ xyz, long long m, int step, double size, double fine, unsigned long long* vkeys,
+                             unsigned long long* fkeys, unsigned int* idx, float* fxyz) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const long long i = j * step;
+    const float fx = __double2float_rn(xyz[3 * i]), fy = __double2float_rn(xyz[3 * i + 1]), fz = __double2float_rn(xyz[3 * i + 2]);
+    fxyz[3 * j] = fx; fxyz[3 * j + 1] = fy; fxyz[3 * j + 2] = fz;
+    const double qx = __ddiv_rn((double)fx, size), qy = __ddiv_rn((double)fy, size), qz = __ddiv_rn((double)fz, size);
+    const double gx = __ddiv_rn((double)fx, fine), gy = __ddiv_rn((double)fy, fine), gz = __ddiv_rn((double)fz, fine);
+    const bool ok = fabs(qx) < 32765.0 && fabs(qy) < 32765.0 && fabs(qz) < 32765.0 && fabs(gx) < 32765.0 && fabs(gy) < 32765.0 && fabs(gz) < 32765.0;
+    vkeys[j] = ok ? pack_key((int)qx, (int)qy, (int)qz) : kInvalidKey;
+    fkeys[j] = ok ? pack_key((int)gx, (int)gy, (int)gz) : kInvalidKey;
+    idx[j] = (unsigned int)j;
+}
+
+// one thread per touched voxel: append the first (cap - count) offered points in sweep order, note the visit
+__global__ void k_color_seg_process(Slot* slots, float* blocks, ColorPoint* cpts, double* last_visited,
+                                    const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idx,
+                                    const float* __restrict__ fxyz, const unsigned int* __restrict__ seg_start, const int* n_seg_p,
+                                    const int* __restrict__ seg_slot, const unsigned int* __restrict__ is_new, long long m, int cap,
+                                    double t_end, double t_last_process, unsigned int* accept_id, unsigned int* seg_first,
+                                    long long* n_points) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_seg_p) return;
+    seg_first[s] = kNoIndex;
+    const int slot = seg_slot[s];
+    if (slot < 0) return;
+    const unsigned int blk = slots[slot].block;
+    int count = (int)slots[slot].count;
+    float* bp = blocks + (size_t)blk * kBlockFloats;
+    const long long start = seg_start[s];
+    const unsigned long long key = keys[start];
+    if (is_new[s]) last_visited[blk] = 0.0;                       // voxelBlock::last_visited_time = 0.0 (include/cloudMap.h:153)
+    int added = 0;
+    for (long long j = start; j < m && keys[j] == key && count < cap; ++j) {
+        const unsigned int i = idx[j];
+        bp[4 * count] = fxyz[3 * (size_t)i]; bp[4 * count + 1] = fxyz[3 * (size_t)i + 1]; bp[4 * count + 2] = fxyz[3 * (size_t)i + 2];
+        ColorPoint cp;                                            // rgbPoint::reset() (src/cloudMap.cpp:12-19)
+        cp.rgb[0] = cp.rgb[1] = cp.rgb[2] = 0; cp.n_rgb = 0; cp.cov[0] = cp.cov[1] = cp.cov[2] = 0.f; cp.pad = 0.f; cp.obs_dist = 0.0; cp.last_obs = 0.0;
+        cpts[(size_t)blk * kBlockCap + count] = cp;
+        accept_id[i] = blk * (unsigned)kBlockCap + (unsigned)count;
+        ++count; ++added;
+    }
+    if (added) {
+        slots[slot].count = (unsigned int)count;
+        reinterpret_cast<unsigned int*>(bp)[kMetaCount] = (unsigned int)count;
+        atomicAdd(reinterpret_cast<unsigned long long*>(n_points), (unsigned long long)added);
+    }
+    // :486-490 / :509-513: once per voxel and sweep end time, whether or not a point was stored
+    if (fabs(t_end - t_last_process) > 1e-5 && fabs(last_visited[blk] - t_end) > 1e-5) {
+        last_visited[blk] = t_end;
+        seg_first[s] = idx[start];                                // the sweep position of the voxel's first offered point
+    }
+}
+__global__ void k_color_seg_keys(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ seg_start, const int* n_seg_p,
+                                 unsigned long long* seg_key) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < *n_seg_p) seg_key[s] = keys[seg_start[s]];
+}
+// after sorting the visited voxels by the sweep position of their first point: append them to the recent list
+__global__ void k_color_append_recent(const unsigned int* __restrict__ first_sorted, const unsigned long long* __restrict__ key_sorted,
+                                      int n_seg, unsigned long long* recent, long long* counters, long long capacity) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_seg || first_sorted[t] == kNoIndex) return;
+    const long long base = counters[1];
+    if (base + t < capacity) recent[base + t] = key_sorted[t];
+    if (t + 1 == n_seg || first_sorted[t + 1] == kNoIndex) counters[3] = t + 1;   // how many were appended (applied by the host)
+}
+// accepted points only keep their fine key
+__global__ void k_color_mask_fine(unsigned long long* fkeys, const unsigned int* __restrict__ accept_id, long long m) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < m && accept_id[j] == kNoIndex) fkeys[j] = kInvalidKey;
+}
+// heads of the fine-cell runs (= the first accepted point of the sweep in that cell) whose cell is still free win
+__global__ void k_color_fine_winners(const Slot* fine, unsigned int fmask, const unsigned long long* __restrict__ fk_sorted,
+                                     const unsigned int* __restrict__ idx_sorted, long long m, unsigned int* winner) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const unsigned long long k = fk_sorted[j];
+    if (k == kInvalidKey || (j > 0 && fk_sorted[j - 1] == k)) return;
+    short x, y, z;
+    unpack_key(k, x, y, z);
+    if (slot_find_rw(fine, fmask, k, x, y, z) < 0) winner[idx_sorted[j]] = 1u;
+}
+__global__ void k_color_emit_rgb(Slot* fine, unsigned int fmask, const unsigned long long* __restrict__ fkeys_by_idx,
+                                 const unsigned int* __restrict__ winner, const unsigned int* __restrict__ rank,
+                                 const unsigned int* __restrict__ accept_id, long long m, unsigned int* rgb_points, long long* counters,
+                                 long long capacity) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m || !winner[j]) return;
+    const long long pos = counters[0] + rank[j];
+    if (pos < capacity) rgb_points[pos] = accept_id[j];            // point.point_index = rgb_points_vec.size() (:478, :503)
+    const unsigned long long k = fkeys_by_idx[j];
+    short x, y, z;
+    unpack_key(k, x, y, z);
+    slot_claim(fine, fmask, k, x, y, z, (unsigned)pos, 1u);       // hashmap_3d_points.insert (:481, :506)
+    if (j + 1 == m || true) { /* the count is finalised by the host from rank/winner of the last element */ }
+}
+
+struct CamConst { double R[9], t_cw[3], t_wc[3], fx, fy, cx, cy, fov; int cols, rows; };
+__device__ __forceinline__ unsigned char sat_u8(double v) {       // cv::saturate_cast<uchar>(double): cvRound (half to even), clamp
+    const long long r = __double2ll_rn(v);
+    return (unsigned char)(r < 0 ? 0 : (r > 255 ? 255 : r));
+}
+__device__ __forceinline__ unsigned char sat_add_u8(unsigned char a, unsigned char b) { const int r = (int)a + (int)b; return (unsigned char)(r > 255 ? 255 : r); }
+// one warp per distinct recent voxel, a lane per stored point; a voxel listed `mult` times is rendered `mult` times in a row
+__global__ void __launch_bounds__(256) k_color_render(const Slot* slots, unsigned int mask, const float* __restrict__ blocks, ColorPoint* cpts,
+                                                       const unsigned long long* __restrict__ uniq_keys, const int* __restrict__ mult,
+                                                       const int* n_uniq_p, CamConst c, const unsigned char* __restrict__ img, double obs_time,
+                                                       unsigned long long* n_rendered) {
+    const int lane = threadIdx.x & 31;
+    const int u_i = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (u_i >= *n_uniq_p) return;
+    const unsigned long long key = uniq_keys[u_i];
+    short kx, ky, kz;
+    unpack_key(key, kx, ky, kz);
+    const int slot = slot_find_rw(slots, mask, key, kx, ky, kz);
+    if (slot < 0) return;
+    const unsigned blk = slots[slot].block;
+    const int count = (int)slots[slot].count;
+    if (lane >= count) return;
+    const float* bp = blocks + (size_t)blk * kBlockFloats + 4 * lane;
+    const double px = (double)bp[0], py = (double)bp[1], pz = (double)bp[2];
+    // project3dTo2d (src/lioOptimization.cpp:132-152), scale 1: products and sums rounded one by one like the host code
+    double cxm, cym, czm;
+    matvec3_exact(c.R, px, py, pz, cxm, cym, czm);
+    const double pcx = __dadd_rn(cxm, c.t_cw[0]), pcy = __dadd_rn(cym, c.t_cw[1]), pcz = __dadd_rn(czm, c.t_cw[2]);
+    if (pcz < 0.001) return;
+    const double u = __dadd_rn(__ddiv_rn(__dmul_rn(pcx, c.fx), pcz), c.cx);
+    const double v = __dadd_rn(__ddiv_rn(__dmul_rn(pcy, c.fy), pcz), c.cy);
+    // if2dPointsAvailable (:49-60)
+    if (!((u >= __dadd_rn(__dmul_rn(c.fov, (double)c.cols), 1.0)) && (ceil(u) < __dmul_rn(__dsub_rn(1.0, c.fov), (double)c.cols)) &&
+          (v >= __dadd_rn(__dmul_rn(c.fov, (double)c.rows), 1.0)) && (ceil(v) < __dmul_rn(__dsub_rn(1.0, c.fov), (double)c.rows)))) return;
+    const double dx = __dsub_rn(px, c.t_wc[0]), dy = __dsub_rn(py, c.t_wc[1]), dz = __dsub_rn(pz, c.t_wc[2]);
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz))));
+    // getSubPixel<cv::Vec3b> (:71-98): four saturated products, three saturated sums per channel
+    const int fr = (int)floor(v), fc = (int)floor(u);
+    const double frac_r = __dsub_rn(v, (double)fr), frac_c = __dsub_rn(u, (double)fc);
+    const double w00 = __dmul_rn(__dsub_rn(1.0, frac_r), __dsub_rn(1.0, frac_c)), w10 = __dmul_rn(frac_r, __dsub_rn(1.0, frac_c));
+    const double w01 = __dmul_rn(__dsub_rn(1.0, frac_r), frac_c), w11 = __dmul_rn(frac_r, frac_c);
+    double color[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const unsigned char a = sat_u8(__dmul_rn((double)img[((size_t)fr * c.cols + fc) * 3 + ch], w00));
+        const unsigned char b = sat_u8(__dmul_rn((double)img[((size_t)(fr + 1) * c.cols + fc) * 3 + ch], w10));
+        const unsigned char cc = sat_u8(__dmul_rn((double)img[((size_t)fr * c.cols + fc + 1) * 3 + ch], w01));
+        const unsigned char d = sat_u8(__dmul_rn((double)img[((size_t)(fr + 1) * c.cols + fc + 1) * 3 + ch], w11));
+        color[ch] = (double)sat_add_u8(sat_add_u8(sat_add_u8(a, b), cc), d);
+    }
+    // rgbPoint::updateRgb (src/cloudMap.cpp:59-101), mixed float / double arithmetic as written there
+    ColorPoint cp = cpts[(size_t)blk * kBlockCap + lane];
+    const double sigma = 15.0, process_noise_sigma = 0.1;
+    unsigned rendered = 0;
+    const int reps = mult[u_i];
+    for (int rep = 0; rep < reps; ++rep) {
+        if (cp.obs_dist != 0 && (dist > __dmul_rn(cp.obs_dist, 1.2))) continue;
+        if (cp.n_rgb == 0) {
+            cp.last_obs = obs_time; cp.obs_dist = dist;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { cp.rgb[i] = (short)round(color[i]); cp.cov[i] = (float)sigma; }
+            cp.n_rgb = 1;
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            cp.cov[i] = __double2float_rn(__dadd_rn((double)cp.cov[i], __dmul_rn(process_noise_sigma, __dsub_rn(obs_time, cp.last_obs))));
+            const double old_sigma = (double)cp.cov[i];
+            const double c2 = (double)__fmul_rn(cp.cov[i], cp.cov[i]);
+            cp.cov[i] = __double2float_rn(__dsqrt_rn(__ddiv_rn(1.0, __dadd_rn(__ddiv_rn(1.0, c2), __ddiv_rn(1.0, __dmul_rn(sigma, sigma))))));
+            const double n2 = (double)__fmul_rn(cp.cov[i], cp.cov[i]);
+            const double mix = __dadd_rn(__ddiv_rn((double)cp.rgb[i], __dmul_rn(old_sigma, old_sigma)), __ddiv_rn(color[i], __dmul_rn(sigma, sigma)));
+            cp.rgb[i] = (short)(int)__dmul_rn(n2, mix);           // double -> short truncates
+        }
+        if (dist < cp.obs_dist) cp.obs_dist = dist;
+        cp.last_obs = obs_time;
+        cp.n_rgb = (short)(cp.n_rgb + 1);
+        ++rendered;
+    }
+    cpts[(size_t)blk * kBlockCap + lane] = cp;
+    if (rendered) atomicAdd(n_rendered, (unsigned long long)rendered);
+}
+// colour state + last visited time in the block order of srl_map_download
+__global__ void k_color_download(const ColorPoint* __restrict__ cpts, const float* __restrict__ blocks, const double* __restrict__ last_visited,
+                                 long long n_voxels, int cap, short* rgb, short* n_rgb, float* cov, double* obs_dist, double* last_obs,
+                                 double* visited) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_voxels * cap) return;
+    const long long v = e / cap;
+    const int i = (int)(e % cap);
+    const int cnt = (int)reinterpret_cast<const unsigned int*>(blocks + (size_t)v * kBlockFloats)[kMetaCount];
+    const bool on = i < cnt;
+    const ColorPoint cp = cpts[(size_t)v * kBlockCap + i];
+    for (int a = 0; a < 3; ++a) { rgb[3 * e + a] = on ? cp.rgb[a] : (short)0; cov[3 * e + a] = (on && cp.n_rgb > 0) ? cp.cov[a] : 0.f; }
+    n_rgb[e] = on ? cp.n_rgb : (short)0;
+    obs_dist[e] = on ? cp.obs_dist : 0.0;
+    last_obs[e] = on ? cp.last_obs : 0.0;
+    if (i == 0) visited[v] = last_visited[v];
+}
+// rgb_points_vec entries as (voxel key, index in block)
+__global__ void k_color_rgb_ids(const unsigned int* __restrict__ rgb_points, long long n, const float* __restrict__ blocks, int cap, short* out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const unsigned id = rgb_points[t];
+    const unsigned blk = id / (unsigned)kBlockCap;
+    const unsigned int* meta = reinterpret_cast<const unsigned int*>(blocks + (size_t)blk * kBlockFloats);
+    short x, y, z;
+    unpack_key((unsigned long long)meta[kMetaKeyLo] | ((unsigned long long)meta[kMetaKeyHi] << 32), x, y, z);
+    out[4 * t] = x; out[4 * t + 1] = y; out[4 * t + 2] = z; out[4 * t + 3] = (short)(id - blk * (unsigned)kBlockCap);
+}
+
+__global__ void k_gather_points(const double* __restrict__ xyz, const unsigned int* __restrict__ sel, int m, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const size_t i = sel[j];
+    out[3 * j] = xyz[3 * i]; out[3 * j + 1] = xyz[3 * i + 1]; out[3 * j + 2] = xyz[3 * i + 2];
+}
+
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 }  // namespace srl
@@ -510,7 +743,12 @@ int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double si
     if (rc != SRL_OK) return rc;
     char* p = static_cast<char*>(ctx->d_scratch);
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
-    double* d_xyz = reinterpret_cast<double*>(take(n * 24));
+    // the frame may already be in HBM (e.g. the output of srl_distort_frame_* / srl_sweep_transform_device): no H2D then
+    cudaPointerAttributes attr;
+    const bool on_device = cudaPointerGetAttributes(&attr, xyz_world) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    if (!on_device) cudaGetLastError();
+    double* d_stage = reinterpret_cast<double*>(take(n * 24));
+    const double* d_xyz = on_device ? xyz_world : d_stage;
     unsigned long long* ka = reinterpret_cast<unsigned long long*>(take(n * 8));
     unsigned long long* kb = reinterpret_cast<unsigned long long*>(take(n * 8));
     unsigned int* ia = reinterpret_cast<unsigned int*>(take(n * 4));
@@ -519,7 +757,7 @@ int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double si
     unsigned char* is_first = reinterpret_cast<unsigned char*>(take(n));
     int* d_count = reinterpret_cast<int*>(take(256));
     void* d_tmp = take(tmp_bytes);
-    SRL_CUDA(ctx, cudaMemcpyAsync(d_xyz, xyz_world, n * 24, cudaMemcpyHostToDevice, st));
+    if (!on_device) SRL_CUDA(ctx, cudaMemcpyAsync(d_stage, xyz_world, n * 24, cudaMemcpyHostToDevice, st));
     const int T = 256;
     const unsigned gb = (unsigned)((n + T - 1) / T);
     k_cell_keys<<<gb, T, 0, st>>>(d_xyz, (long long)n, size, ka, ia);
@@ -535,21 +773,353 @@ int srl_grid_sampling(srl_ctx* ctx, const double* xyz_world, size_t n, double si
     SRL_CUDA(ctx, cudaStreamSynchronize(st));
     std::vector<unsigned int> first((size_t)m);
     if (m) SRL_CUDA(ctx, cudaMemcpy(first.data(), sel, (size_t)m * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    std::vector<double> first_xyz;                       // device input: the coordinates of those points come back, not the frame
+    if (on_device && m) {
+        k_gather_points<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_xyz, sel, m, d_stage);
+        SRL_CUDA(ctx, cudaGetLastError());
+        first_xyz.resize((size_t)m * 3);
+        SRL_CUDA(ctx, cudaMemcpyAsync(first_xyz.data(), d_stage, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
+        SRL_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     // `first` = the frame indices that open a new cell, in frame order: exactly the sequence of node insertions the
     // reference's grid sees (later points of a cell only push_back into an existing node).  Replaying it through the same
     // libstdc++ container gives the reference's iteration order (src/utility.cpp:180-187).
     std::tr1::unordered_map<CellKey, unsigned int, CellHash> grid;
     for (int j = 0; j < m; ++j) {
         const unsigned int i = first[(size_t)j];
+        const double* pt = on_device ? &first_xyz[3 * (size_t)j] : &xyz_world[3 * (size_t)i];
         CellKey k;
-        k.x = static_cast<short>(xyz_world[3 * (size_t)i] / size);
-        k.y = static_cast<short>(xyz_world[3 * (size_t)i + 1] / size);
-        k.z = static_cast<short>(xyz_world[3 * (size_t)i + 2] / size);
+        k.x = static_cast<short>(pt[0] / size);
+        k.y = static_cast<short>(pt[1] / size);
+        k.z = static_cast<short>(pt[2] / size);
         grid[k] = i;
     }
     size_t w = 0;
     for (std::tr1::unordered_map<CellKey, unsigned int, CellHash>::const_iterator it = grid.begin(); it != grid.end(); ++it) out[w++] = it->second;
     *n_out = w;
+    return SRL_OK;
+}
+
+
+// ---- N4: colour map host side ---------------------------------------------------------------------------------------
+struct srl_color_map {
+    srl_ctx* ctx = nullptr;
+    srl_map* vox = nullptr;                 // color_voxel_map (include/lioOptimization.h:275)
+    double min_dist = 0.15;
+    srl::ColorPoint* d_cpts = nullptr;      // max_voxels * 20
+    double* d_last_visited = nullptr;       // max_voxels
+    srl::Slot* d_fine = nullptr;            // hashmap_3d_points as an occupancy set: key = fine cell, block = index into rgb_points
+    size_t fine_capacity = 0;
+    unsigned int* d_rgb_points = nullptr;   // rgb_points_vec: point ids (block * 20 + index)
+    size_t max_rgb_points = 0;
+    unsigned long long* d_recent_temp = nullptr;   // voxels_recent_visited_temp (packed keys)
+    unsigned long long* d_recent = nullptr;        // map_tracker->voxels_recent_visited
+    size_t recent_capacity = 0;
+    long long* d_counters = nullptr;        // [0] rgb points, [1] recent_temp size, [2] scratch, [3] scratch
+    int64_t n_rgb_points = 0, n_recent_temp = 0, n_recent = 0, n_new_recent = 0;
+};
+
+int srl_color_map_create(srl_ctx* ctx, double voxel_size, int32_t max_num_points_in_voxel, size_t max_voxels, double min_distance_points,
+                         srl_color_map** out) {
+    if (!ctx || !out || !(min_distance_points > 0)) return SRL_BAD_ARG;
+    *out = nullptr;
+    srl_color_map* cm = new srl_color_map();
+    cm->ctx = ctx; cm->min_dist = min_distance_points;
+    int rc = srl_map_create(ctx, voxel_size, max_num_points_in_voxel, max_voxels, &cm->vox);
+    if (rc != SRL_OK) { delete cm; return rc; }
+    cm->max_rgb_points = max_voxels * (size_t)kBlockCap;
+    cm->recent_capacity = 4 * max_voxels + 1024;
+    size_t cap = 1024;
+    while (cap < 2 * cm->max_rgb_points) cap <<= 1;
+    cm->fine_capacity = cap;
+    cudaError_t e;
+    if ((e = cudaMalloc(&cm->d_cpts, max_voxels * kBlockCap * sizeof(ColorPoint))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_last_visited, max_voxels * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_fine, cap * sizeof(Slot))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_rgb_points, cm->max_rgb_points * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_recent_temp, cm->recent_capacity * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_recent, cm->recent_capacity * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&cm->d_counters, 8 * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMemsetAsync(cm->d_fine, 0, cap * sizeof(Slot), ctx->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(cm->d_cpts, 0, max_voxels * kBlockCap * sizeof(ColorPoint), ctx->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(cm->d_last_visited, 0, max_voxels * sizeof(double), ctx->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(cm->d_counters, 0, 8 * sizeof(long long), ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) {
+        srl_color_map_destroy(cm);
+        return cuda_fail(ctx, e, "srl_color_map_create");
+    }
+    *out = cm;
+    return SRL_OK;
+}
+
+void srl_color_map_destroy(srl_color_map* cm) {
+    if (!cm) return;
+    if (cm->vox) srl_map_destroy(cm->vox);
+    cudaFree(cm->d_cpts); cudaFree(cm->d_last_visited); cudaFree(cm->d_fine); cudaFree(cm->d_rgb_points);
+    cudaFree(cm->d_recent_temp); cudaFree(cm->d_recent); cudaFree(cm->d_counters);
+    delete cm;
+}
+
+srl_map* srl_color_map_voxels(srl_color_map* cm) { return cm ? cm->vox : nullptr; }
+
+int srl_color_map_stats(srl_color_map* cm, int64_t* n_voxels, int64_t* n_points, int64_t* n_rgb_points, int64_t* n_recent, int64_t* n_new_recent) {
+    if (!cm) return SRL_BAD_ARG;
+    int rc = srl_map_stats(cm->vox, n_voxels, n_points);
+    if (n_rgb_points) *n_rgb_points = cm->n_rgb_points;
+    if (n_recent) *n_recent = cm->n_recent;
+    if (n_new_recent) *n_new_recent = cm->n_new_recent;
+    return rc;
+}
+
+int srl_color_map_add_points(srl_color_map* cm, const double* xyz_world, size_t n, int32_t add_point_step, double time_sweep_end,
+                             double time_last_process, int32_t to_rendering, int64_t* n_stored) {
+    if (!cm || (n && !xyz_world) || add_point_step < 1) return SRL_BAD_ARG;
+    srl_ctx* ctx = cm->ctx;
+    srl_map* m = cm->vox;
+    cudaStream_t st = ctx->stream;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_stored) *n_stored = 0;
+    if (to_rendering) cm->n_recent_temp = 0;                                   // :523-527
+    const int64_t recent_before = cm->n_recent_temp;                           // :529
+    const size_t msel = (n + (size_t)add_point_step - 1) / (size_t)add_point_step;   // points with idx % step == 0
+    if (msel > 0x7fffffffULL) return set_err(ctx, SRL_BAD_ARG, "srl_color_map_add_points: too many points");
+    if (msel) {
+        cudaPointerAttributes attr;
+        const bool on_device = cudaPointerGetAttributes(&attr, xyz_world) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+        if (!on_device) cudaGetLastError();
+        size_t tmp_sort = 0, tmp_sort32 = 0, tmp_sel = 0, tmp_scan = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (unsigned int*)nullptr,
+                                        (unsigned int*)nullptr, (int)msel, 0, 50, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort32, (unsigned int*)nullptr, (unsigned int*)nullptr, (unsigned long long*)nullptr,
+                                        (unsigned long long*)nullptr, (int)msel, 0, 32, st);
+        cub::DeviceSelect::Flagged(nullptr, tmp_sel, thrust::counting_iterator<unsigned int>(0), (unsigned char*)nullptr,
+                                   (unsigned int*)nullptr, (int*)nullptr, (int)msel, st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (unsigned int*)nullptr, (unsigned int*)nullptr, (int)msel, st);
+        const size_t tmp_bytes = std::max(std::max(tmp_sort, tmp_sort32), std::max(tmp_sel, tmp_scan));
+        const size_t need = (on_device ? 0 : align_up(n * 24)) + 5 * align_up(msel * 8) + 12 * align_up(msel * 4) + align_up(msel * 12) +
+                            align_up(msel) + 4 * 256 + align_up(tmp_bytes);
+        int rc = ensure_scratch(ctx, need);
+        if (rc != SRL_OK) return rc;
+        char* p = static_cast<char*>(ctx->d_scratch);
+        auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
+        const double* d_xyz = xyz_world;
+        if (!on_device) {
+            double* buf = reinterpret_cast<double*>(take(n * 24));
+            SRL_CUDA(ctx, cudaMemcpyAsync(buf, xyz_world, n * 24, cudaMemcpyHostToDevice, st));
+            d_xyz = buf;
+        }
+        unsigned long long* vk_a = reinterpret_cast<unsigned long long*>(take(msel * 8));
+        unsigned long long* vk_b = reinterpret_cast<unsigned long long*>(take(msel * 8));
+        unsigned long long* fk_a = reinterpret_cast<unsigned long long*>(take(msel * 8));
+        unsigned long long* fk_b = reinterpret_cast<unsigned long long*>(take(msel * 8));
+        unsigned long long* seg_key = reinterpret_cast<unsigned long long*>(take(msel * 8));
+        unsigned int* idx_a = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* idx_b = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* idx_c = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* seg_start = reinterpret_cast<unsigned int*>(take(msel * 4));
+        int* seg_slot = reinterpret_cast<int*>(take(msel * 4));
+        unsigned int* is_new = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* new_rank = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* accept_id = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* seg_first = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* seg_first_sorted = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* winner = reinterpret_cast<unsigned int*>(take(msel * 4));
+        unsigned int* wrank = reinterpret_cast<unsigned int*>(take(msel * 4));
+        float* fxyz = reinterpret_cast<float*>(take(msel * 12));
+        unsigned char* flags = reinterpret_cast<unsigned char*>(take(msel));
+        int* d_nseg = reinterpret_cast<int*>(take(256));
+        void* d_tmp = take(tmp_bytes);
+        const int T = 256;
+        const unsigned gb = (unsigned)((msel + T - 1) / T);
+        const unsigned vmask = (unsigned)(m->capacity - 1), fmask = (unsigned)(cm->fine_capacity - 1);
+        k_color_keys<<<gb, T, 0, st>>>(d_xyz, (long long)msel, add_point_step, m->voxel_size, cm->min_dist, vk_a, fk_a, idx_a, fxyz);
+        SRL_CUDA(ctx, cudaMemsetAsync(accept_id, 0xff, msel * 4, st));
+        SRL_CUDA(ctx, cudaMemsetAsync(winner, 0, msel * 4, st));
+        size_t tb = tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(d_tmp, tb, vk_a, vk_b, idx_a, idx_b, (int)msel, 0, 50, st);
+        k_seg_flags<<<gb, T, 0, st>>>(vk_b, (long long)msel, flags);
+        tb = tmp_bytes;
+        cub::DeviceSelect::Flagged(d_tmp, tb, thrust::counting_iterator<unsigned int>(0), flags, seg_start, d_nseg, (int)msel, st);
+        int n_seg = 0;
+        SRL_CUDA(ctx, cudaMemcpyAsync(&n_seg, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SRL_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->launches += 4;
+        if (n_seg > 0) {
+            const unsigned gs = (unsigned)((n_seg + T - 1) / T);
+            k_seg_lookup<<<gs, T, 0, st>>>(m->d_slots, vmask, vk_b, seg_start, d_nseg, 1, seg_slot, is_new);   // min_num_points = 0 (:539)
+            tb = tmp_bytes;
+            cub::DeviceScan::ExclusiveSum(d_tmp, tb, is_new, new_rank, n_seg, st);
+            unsigned int last_rank = 0, last_new = 0;
+            SRL_CUDA(ctx, cudaMemcpyAsync(&last_rank, new_rank + (n_seg - 1), 4, cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaMemcpyAsync(&last_new, is_new + (n_seg - 1), 4, cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaStreamSynchronize(st));
+            const long long total_new = (long long)last_rank + last_new;
+            if ((size_t)(m->n_voxels + total_new) > m->max_voxels)
+                return set_err(ctx, SRL_MAP_FULL, "srl_color_map_add_points: voxel pool exhausted (raise max_voxels)");
+            long long before = 0, after = 0;
+            SRL_CUDA(ctx, cudaMemcpyAsync(&before, m->d_counters, sizeof(long long), cudaMemcpyDeviceToHost, st));
+            if (total_new > 0)
+                k_seg_claim<<<gs, T, 0, st>>>(m->d_slots, vmask, m->d_blocks, vk_b, seg_start, d_nseg, is_new, new_rank, (long long)m->n_voxels, seg_slot);
+            k_color_seg_process<<<gs, T, 0, st>>>(m->d_slots, m->d_blocks, cm->d_cpts, cm->d_last_visited, vk_b, idx_b, fxyz, seg_start, d_nseg,
+                                                  seg_slot, is_new, (long long)msel, m->cap, time_sweep_end, time_last_process, accept_id,
+                                                  seg_first, m->d_counters);
+            m->n_voxels += total_new;
+            // ---- recent list: the voxels this sweep visited for the first time, in the order of their first point
+            k_color_seg_keys<<<gs, T, 0, st>>>(vk_b, seg_start, d_nseg, seg_key);
+            tb = tmp_bytes;
+            cub::DeviceRadixSort::SortPairs(d_tmp, tb, seg_first, seg_first_sorted, seg_key, fk_b /* reused as sorted keys */, n_seg, 0, 32, st);
+            const long long host_cnt[4] = {cm->n_rgb_points, cm->n_recent_temp, 0, 0};
+            SRL_CUDA(ctx, cudaMemcpyAsync(cm->d_counters, host_cnt, sizeof(host_cnt), cudaMemcpyHostToDevice, st));
+            k_color_append_recent<<<gs, T, 0, st>>>(seg_first_sorted, fk_b, n_seg, cm->d_recent_temp, cm->d_counters, (long long)cm->recent_capacity);
+            long long appended = 0;
+            SRL_CUDA(ctx, cudaMemcpyAsync(&appended, cm->d_counters + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaMemcpyAsync(&after, m->d_counters, sizeof(long long), cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaStreamSynchronize(st));
+            if ((size_t)(cm->n_recent_temp + appended) > cm->recent_capacity)
+                return set_err(ctx, SRL_MAP_FULL, "srl_color_map_add_points: recent-voxel list exhausted (render or clear it)");
+            cm->n_recent_temp += appended;
+            if (n_stored) *n_stored = after - before;
+            // ---- rgb_points_vec: the first accepted point of the sweep in every still-free fine cell, in sweep order
+            k_color_mask_fine<<<gb, T, 0, st>>>(fk_a, accept_id, (long long)msel);
+            tb = tmp_bytes;
+            cub::DeviceRadixSort::SortPairs(d_tmp, tb, fk_a, fk_b, idx_a, idx_c, (int)msel, 0, 50, st);
+            k_color_fine_winners<<<gb, T, 0, st>>>(cm->d_fine, fmask, fk_b, idx_c, (long long)msel, winner);
+            tb = tmp_bytes;
+            cub::DeviceScan::ExclusiveSum(d_tmp, tb, winner, wrank, (int)msel, st);
+            unsigned int lr = 0, lw = 0;
+            SRL_CUDA(ctx, cudaMemcpyAsync(&lr, wrank + (msel - 1), 4, cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaMemcpyAsync(&lw, winner + (msel - 1), 4, cudaMemcpyDeviceToHost, st));
+            SRL_CUDA(ctx, cudaStreamSynchronize(st));
+            const long long n_win = (long long)lr + lw;
+            if ((size_t)(cm->n_rgb_points + n_win) > cm->max_rgb_points)
+                return set_err(ctx, SRL_MAP_FULL, "srl_color_map_add_points: rgb point list exhausted");
+            if (n_win > 0)
+                k_color_emit_rgb<<<gb, T, 0, st>>>(cm->d_fine, fmask, fk_a, winner, wrank, accept_id, (long long)msel, cm->d_rgb_points, cm->d_counters,
+                                                   (long long)cm->max_rgb_points);
+            SRL_CUDA(ctx, cudaGetLastError());
+            cm->n_rgb_points += n_win;
+            ctx->launches += 12;
+        }
+    }
+    if (to_rendering) {                                                         // :544-550
+        if (cm->n_recent_temp) SRL_CUDA(ctx, cudaMemcpyAsync(cm->d_recent, cm->d_recent_temp, (size_t)cm->n_recent_temp * 8, cudaMemcpyDeviceToDevice, st));
+        cm->n_recent = cm->n_recent_temp;
+        cm->n_new_recent = cm->n_recent - recent_before;
+    }
+    SRL_CUDA(ctx, cudaStreamSynchronize(st));
+    return SRL_OK;
+}
+
+int srl_color_map_render_recent(srl_color_map* cm, const srl_camera* cam, const uint8_t* image_bgr, double obs_time, int64_t* n_rendered) {
+    if (!cm || !cam || !image_bgr || cam->cols < 2 || cam->rows < 2) return SRL_BAD_ARG;
+    srl_ctx* ctx = cm->ctx;
+    srl_map* m = cm->vox;
+    cudaStream_t st = ctx->stream;
+    SRL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_rendered) *n_rendered = 0;
+    const size_t nr = (size_t)cm->n_recent;
+    if (nr == 0) return SRL_OK;
+    cudaPointerAttributes attr;
+    const bool on_device = cudaPointerGetAttributes(&attr, image_bgr) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    if (!on_device) cudaGetLastError();
+    const size_t img_bytes = (size_t)cam->rows * cam->cols * 3;
+    size_t tmp_sort = 0, tmp_rle = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)nr, 0, 50, st);
+    cub::DeviceRunLengthEncode::Encode(nullptr, tmp_rle, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)nr, st);
+    const size_t tmp_bytes = std::max(tmp_sort, tmp_rle);
+    const size_t need = (on_device ? 0 : align_up(img_bytes)) + 2 * align_up(nr * 8) + align_up(nr * 4) + 2 * 256 + align_up(tmp_bytes);
+    int rc = ensure_scratch(ctx, need);
+    if (rc != SRL_OK) return rc;
+    char* p = static_cast<char*>(ctx->d_scratch);
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
+    const unsigned char* d_img = image_bgr;
+    if (!on_device) {
+        unsigned char* buf = reinterpret_cast<unsigned char*>(take(img_bytes));
+        SRL_CUDA(ctx, cudaMemcpyAsync(buf, image_bgr, img_bytes, cudaMemcpyHostToDevice, st));
+        d_img = buf;
+    }
+    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(take(nr * 8));
+    unsigned long long* uniq = reinterpret_cast<unsigned long long*>(take(nr * 8));
+    int* mult = reinterpret_cast<int*>(take(nr * 4));
+    int* d_nuniq = reinterpret_cast<int*>(take(256));
+    unsigned long long* d_count = reinterpret_cast<unsigned long long*>(take(256));
+    void* d_tmp = take(tmp_bytes);
+    SRL_CUDA(ctx, cudaMemsetAsync(d_count, 0, 8, st));
+    size_t tb = tmp_bytes;
+    cub::DeviceRadixSort::SortKeys(d_tmp, tb, cm->d_recent, sorted, (int)nr, 0, 50, st);
+    tb = tmp_bytes;
+    cub::DeviceRunLengthEncode::Encode(d_tmp, tb, sorted, uniq, mult, d_nuniq, (int)nr, st);
+    CamConst c;
+    quat_to_rot(cam->q_camera_world, c.R);
+    for (int i = 0; i < 3; ++i) { c.t_cw[i] = cam->t_camera_world[i]; c.t_wc[i] = cam->t_world_camera[i]; }
+    c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy; c.fov = cam->fov_margin; c.cols = cam->cols; c.rows = cam->rows;
+    const int T = 256;
+    k_color_render<<<(unsigned)((nr * 32 + T - 1) / T), T, 0, st>>>(m->d_slots, (unsigned)(m->capacity - 1), m->d_blocks, cm->d_cpts, uniq, mult, d_nuniq, c, d_img,
+                                                               obs_time, d_count);
+    SRL_CUDA(ctx, cudaGetLastError());
+    unsigned long long cnt = 0;
+    SRL_CUDA(ctx, cudaMemcpyAsync(&cnt, d_count, 8, cudaMemcpyDeviceToHost, st));
+    SRL_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->launches += 3;
+    if (n_rendered) *n_rendered = (int64_t)cnt;
+    return SRL_OK;
+}
+
+int srl_color_map_download_state(srl_color_map* cm, size_t max_voxels, int16_t* rgb, int16_t* n_rgb, float* cov, double* obs_dist, double* last_obs,
+                                 double* last_visited) {
+    if (!cm) return SRL_BAD_ARG;
+    srl_ctx* ctx = cm->ctx;
+    srl_map* m = cm->vox;
+    const size_t nv = (size_t)m->n_voxels;
+    if (nv == 0) return SRL_OK;
+    if (nv > max_voxels || !rgb || !n_rgb || !cov || !obs_dist || !last_obs || !last_visited) return set_err(ctx, SRL_BAD_ARG, "srl_color_map_download_state: output too small");
+    const int cap = m->cap;
+    const size_t e = nv * (size_t)cap;
+    const size_t need = align_up(e * 6) + align_up(e * 2) + align_up(e * 12) + 2 * align_up(e * 8) + align_up(nv * 8);
+    int rc = ensure_scratch(ctx, need);
+    if (rc != SRL_OK) return rc;
+    char* p = static_cast<char*>(ctx->d_scratch);
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes); return r; };
+    short* d_rgb = reinterpret_cast<short*>(take(e * 6));
+    short* d_n = reinterpret_cast<short*>(take(e * 2));
+    float* d_cov = reinterpret_cast<float*>(take(e * 12));
+    double* d_od = reinterpret_cast<double*>(take(e * 8));
+    double* d_lo = reinterpret_cast<double*>(take(e * 8));
+    double* d_lv = reinterpret_cast<double*>(take(nv * 8));
+    const int T = 256;
+    k_color_download<<<(unsigned)((e + T - 1) / T), T, 0, ctx->stream>>>(cm->d_cpts, m->d_blocks, cm->d_last_visited, (long long)nv, cap, d_rgb, d_n, d_cov, d_od, d_lo, d_lv);
+    SRL_CUDA(ctx, cudaGetLastError());
+    SRL_CUDA(ctx, cudaMemcpyAsync(rgb, d_rgb, e * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(n_rgb, d_n, e * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(cov, d_cov, e * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(obs_dist, d_od, e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(last_obs, d_lo, e * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaMemcpyAsync(last_visited, d_lv, nv * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SRL_OK;
+}
+
+int srl_color_map_download_lists(srl_color_map* cm, int16_t* rgb_points /* n_rgb_points * 4 */, int16_t* recent /* n_recent * 3 */) {
+    if (!cm) return SRL_BAD_ARG;
+    srl_ctx* ctx = cm->ctx;
+    srl_map* m = cm->vox;
+    if (cm->n_rgb_points && rgb_points) {
+        const size_t n = (size_t)cm->n_rgb_points;
+        int rc = ensure_scratch(ctx, n * 8);
+        if (rc != SRL_OK) return rc;
+        short* d_out = static_cast<short*>(ctx->d_scratch);
+        const int T = 256;
+        k_color_rgb_ids<<<(unsigned)((n + T - 1) / T), T, 0, ctx->stream>>>(cm->d_rgb_points, (long long)n, m->d_blocks, m->cap, d_out);
+        SRL_CUDA(ctx, cudaGetLastError());
+        SRL_CUDA(ctx, cudaMemcpyAsync(rgb_points, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (cm->n_recent && recent) {
+        std::vector<unsigned long long> keys((size_t)cm->n_recent);
+        SRL_CUDA(ctx, cudaMemcpyAsync(keys.data(), cm->d_recent, keys.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < keys.size(); ++i) { short x, y, z; unpack_key(keys[i], x, y, z); recent[3 * i] = x; recent[3 * i + 1] = y; recent[3 * i + 2] = z; }
+    }
+    SRL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SRL_OK;
 }
 

@@ -237,7 +237,12 @@ struct PassConst {
     int Kmin;             // min_number_neighbors
     int nb;               // voxels visited per side
     int thr_occ;          // threshold_voxel_occupancy (effective)
+    double inv_size;      // 1 / size when size is a power of two (then x * inv_size == x / size bit for bit), else 0
+    double pad_;
 };
+// the voxel coordinate of src/optimize.cpp:372-374 before truncation: a correctly rounded division (a ~35-instruction
+// subroutine on the GPU), or one multiply when the voxel size is a power of two — the quotient is exact either way then
+SRL_HD double voxel_quotient(double x, const PassConst& c) { return c.inv_size != 0.0 ? SRL_MUL(x, c.inv_size) : SRL_DIV(x, c.size); }
 
 struct PlaneRow {
     double nx, ny, nz;   // norm_vector

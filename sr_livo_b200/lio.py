@@ -148,6 +148,66 @@ class VoxelHashMap:
         return added.value
 
 
+class ColorVoxelMap:
+    """color_voxel_map + hashmap_3d_points + rgb_points_vec + voxels_recent_visited (include/lioOptimization.h:275-291,
+    include/rgbMapTracker.h:38), fed by the colour branch of addPointsToMap and coloured by renderPointsInRecentVoxel."""
+
+    def __init__(self, ctx: Context, voxel_size: float = 1.0, max_num_points_in_voxel: int = 20, max_voxels: int = 1 << 16,
+                 min_distance_points: float = 0.15):
+        self.ctx, self.cap = ctx, max_num_points_in_voxel
+        h = C.c_void_p()
+        _check(ctx.h, lib().srl_color_map_create(ctx.h, voxel_size, max_num_points_in_voxel, max_voxels, min_distance_points, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().srl_color_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        v = [C.c_int64(0) for _ in range(5)]
+        _check(self.ctx.h, lib().srl_color_map_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("voxels", "points", "rgb_points", "recent", "new_recent"), [x.value for x in v]))
+
+    def addPoints(self, xyz_world, add_point_step: int = 1, time_sweep_end: float = 1.0, time_last_process: float = 0.0,
+                  to_rendering: bool = True) -> int:
+        """the loop of src/lioOptimization.cpp:533-551 over the registered frame (host array or a device pointer + n)."""
+        xyz = f64(xyz_world).reshape(-1, 3)
+        stored = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_color_map_add_points(self.h, ptr(xyz), xyz.shape[0], add_point_step, time_sweep_end, time_last_process,
+                                                          1 if to_rendering else 0, C.byref(stored)))
+        return stored.value
+
+    def renderPointsInRecentVoxel(self, camera: "capi.Camera", image_bgr, obs_time: float) -> int:
+        img = np.ascontiguousarray(image_bgr, np.uint8)
+        assert img.shape == (camera.rows, camera.cols, 3)
+        n = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_color_map_render_recent(self.h, C.byref(camera), ptr(img), float(obs_time), C.byref(n)))
+        return n.value
+
+    def download(self) -> dict:
+        """voxel contents + colour state (block order) + the two lists."""
+        st = self.stats()
+        nv, cap = st["voxels"], self.cap
+        out = dict(keys=np.zeros((nv, 3), np.int16), counts=np.zeros(nv, np.int32), xyz=np.zeros((nv, cap, 3), np.float32),
+                   rgb=np.zeros((nv, cap, 3), np.int16), n_rgb=np.zeros((nv, cap), np.int16), cov=np.zeros((nv, cap, 3), np.float32),
+                   obs_dist=np.zeros((nv, cap)), last_obs=np.zeros((nv, cap)), last_visited=np.zeros(nv),
+                   rgb_points=np.zeros((st["rgb_points"], 4), np.int16), recent=np.zeros((st["recent"], 3), np.int16))
+        vox = C.c_void_p(lib().srl_color_map_voxels(self.h))
+        got = C.c_int64(0)
+        _check(self.ctx.h, lib().srl_map_download(vox, ptr(out["keys"]), ptr(out["counts"]), ptr(out["xyz"]), nv, C.byref(got)))
+        _check(self.ctx.h, lib().srl_color_map_download_state(self.h, nv, ptr(out["rgb"]), ptr(out["n_rgb"]), ptr(out["cov"]), ptr(out["obs_dist"]),
+                                                              ptr(out["last_obs"]), ptr(out["last_visited"])))
+        _check(self.ctx.h, lib().srl_color_map_download_lists(self.h, ptr(out["rgb_points"]), ptr(out["recent"])))
+        return out
+
+
 class Sweep:
     """The keypoints of one reconstructed sweep, resident in HBM (raw LiDAR-frame points, FP64)."""
 
@@ -416,5 +476,5 @@ class LioOptimization:
                                passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft, world
 
 
-__all__ = ["Context", "VoxelHashMap", "Sweep", "EskfEstimator", "LioOptimization", "OptimizeSummary", "PlaneResiduals",
+__all__ = ["Context", "VoxelHashMap", "ColorVoxelMap", "Sweep", "EskfEstimator", "LioOptimization", "OptimizeSummary", "PlaneResiduals",
            "IcpParams", "r3live_params", "make_frame", "SrlError"]

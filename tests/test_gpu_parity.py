@@ -563,6 +563,16 @@ def test_grid_sampling_matches_the_reference_order(L, small_world):
     ref = om.update_iekf(raw, O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=synth.prior_covariance()), sw0.t_last, O.r3live_params())
     assert summ.passes_run == ref["passes"] and summ.num_residuals_used == ref["num_residuals_used"] == 600
     assert np.allclose(ft, ref["frame_t"], atol=1e-9) and np.allclose(fq, ref["frame_q"], atol=1e-9)
+    # the frame may already live in HBM (device pointer): same sequence, no upload of the frame
+    import ctypes as C
+    import torch
+    from sr_livo_b200 import capi
+    world = sw0.raw_xyz @ O.quat_to_rot(sw0.q_init).T + sw0.t_init
+    d_world = torch.from_numpy(np.ascontiguousarray(world)).cuda()
+    out = np.zeros(world.shape[0], np.uint32)
+    m = C.c_size_t(0)
+    assert capi.lib().srl_grid_sampling(L.ctx.h, C.c_void_p(d_world.data_ptr()), world.shape[0], 0.5, capi.ptr(out), C.byref(m)) == 0
+    assert np.array_equal(out[:m.value], L.gridSampling(world, 0.5))
 
 
 def test_remove_points_far_from_location_then_keep_working(L, small_world):
@@ -732,6 +742,58 @@ def test_full_size_properties_100k_sweep_large_map():
         assert after.loss_sum < 0.2 * a.loss_sum                            # registration reduced the residual
     finally:
         L.close()
+
+
+def _color_dict(d):
+    return {tuple(k): dict(xyz=d["xyz"][i, :c].copy(), rgb=d["rgb"][i, :c].copy(), n_rgb=d["n_rgb"][i, :c].copy(), cov=d["cov"][i, :c].copy(),
+                           obs_dist=d["obs_dist"][i, :c].copy(), last_obs=d["last_obs"][i, :c].copy(), last_visited=float(d["last_visited"][i]))
+            for i, (k, c) in enumerate(zip(d["keys"].tolist(), d["counts"].tolist()))}
+
+
+def test_color_map_and_renderer_match_the_oracle(L):
+    """Row N4: addPointToColorMap (src/lioOptimization.cpp:448-551, colour branch) and renderPointsInRecentVoxel with
+    rgbPoint::updateRgb (src/rgbMapTracker.cpp:181-237, src/cloudMap.cpp:59-101) on the GPU against the sequential oracle:
+    voxel contents and order, the fine-cell dedupe that builds rgb_points_vec (order included), the recently-visited voxel
+    list (order included), and after two renderings the fused colours, covariances and observation state — all exact."""
+    from sr_livo_b200 import capi, lio
+    rng = np.random.default_rng(5)
+    room = lambda n: np.stack([rng.uniform(-4, 4, n), rng.uniform(-3, 3, n), rng.choice([0.02, 2.4], n) + rng.normal(0, 0.01, n)], axis=1)
+    sweep1, sweep2 = room(9000), np.concatenate([room(3000) + [0.4, 0.0, 0.0], room(2000) * [1.0, 1.0, 0.2]])
+    cmg = lio.ColorVoxelMap(L.ctx, max_voxels=1 << 12)
+    cmo = O.OracleColorMap()
+    cam = capi.Camera()
+    cam.q_camera_world[:] = [0.01, -0.02, 0.015, 0.9996]          # not normalised on purpose: toRotationMatrix as given
+    cam.t_camera_world[:] = [0.1, -0.2, 5.0]
+    cam.t_world_camera[:] = [-0.1, 0.2, -5.0]
+    cam.fx, cam.fy, cam.cx, cam.cy, cam.fov_margin, cam.cols, cam.rows = 310.0, 305.0, 322.5, 238.25, 0.0001, 640, 480
+    cam15 = np.array(list(cam.q_camera_world) + list(cam.t_camera_world) + list(cam.t_world_camera) + [cam.fx, cam.fy, cam.cx, cam.cy, cam.fov_margin])
+    try:
+        for step, (pts, kw) in enumerate([(sweep1, dict(add_point_step=2, time_sweep_end=1.0, time_last_process=0.0, to_rendering=True)),
+                                          (sweep2, dict(add_point_step=1, time_sweep_end=1.1, time_last_process=1.0, to_rendering=True)),
+                                          (sweep1[:500] + 0.03, dict(add_point_step=3, time_sweep_end=1.2, time_last_process=1.2, to_rendering=False))]):
+            assert cmg.addPoints(pts, **kw) == cmo.add_points(pts, **kw)
+            g, o = cmg.download(), cmo.snapshot()
+            oc = cmo.counts()
+            st = cmg.stats()
+            assert (st["voxels"], st["rgb_points"], st["recent"], st["new_recent"]) == (oc["voxels"], oc["rgb_points"], oc["recent"], oc["new_recent"])
+            o_rgb_points, o_recent = cmo.lists()
+            assert np.array_equal(g["rgb_points"], o_rgb_points)                   # rgb_points_vec: same entries, same order
+            assert np.array_equal(g["recent"].astype(np.int32), o_recent)           # voxels_recent_visited: same voxels, same order
+            if step < 2:
+                img = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+                for obs_time in (kw["time_sweep_end"], kw["time_sweep_end"] + 0.05):
+                    assert cmg.renderPointsInRecentVoxel(cam, img, obs_time) == cmo.render(cam15, img, obs_time)
+                g, o = cmg.download(), cmo.snapshot()
+            gd, od = _color_dict(g), _color_dict(o)
+            assert gd.keys() == od.keys()
+            for k in od:
+                for f in ("xyz", "rgb", "n_rgb", "cov", "obs_dist", "last_obs"):
+                    assert np.array_equal(gd[k][f], od[k][f]), (step, k, f)
+                assert gd[k]["last_visited"] == od[k]["last_visited"]
+            if step == 1:
+                assert g["n_rgb"].max() >= 3 and (g["rgb"] > 0).any()               # the renderer really coloured points, repeatedly
+    finally:
+        cmg.close()
 
 
 def _region_oracle(L, world_pts, margin=3):
