@@ -1,8 +1,15 @@
 #!/bin/bash
-# 8-GPU check exactly as the driver launches it: reference arm (rank 0 only), then the b200 arm
-N=${1:-8}; OUT=gpurun_out/${2:-m08}
+# 8-GPU check: multi-rank tests on distinct GPUs, then the bench as the driver launches it (with the cfg5 block)
+N=${2:-8}
+OUT=gpurun_out/${1:-m8}
 mkdir -p $OUT
-echo "== reference arm under torchrun"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --impl reference --gpus $N --steps 3 --warmup 1 > $OUT/bench_n${N}_reference.json 2> $OUT/bench_n${N}_reference.err; echo "rc=$?"; cut -c1-300 $OUT/bench_n${N}_reference.json
-echo "== b200 arm N=$N"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/bench_n${N}_fused.json 2> $OUT/bench_n${N}_fused.err; echo "rc=$?"; cut -c1-1200 $OUT/bench_n${N}_fused.json; grep -v "OMP_NUM\|^\*\*\*\|^$" $OUT/bench_n${N}_fused.err | tail -5
+timeout 900 python -m pytest tests -q -m gpu -x -k "exchange_ranks" > $OUT/pytest_dist.log 2>&1; echo "pytest dist rc=$?"; tail -3 $OUT/pytest_dist.log
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 60 --warmup 3 --cfg5-steps 8 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N rc=$?"; tail -3 $OUT/bench_n$N.err
+python - <<PY
+import json
+for f in ("$OUT/bench_n$N.json",):
+    try:
+        d=json.load(open(f)); print(f.split("/")[-1], "value %.1fM e2e %.1fM ms/step %.3f e2e ms %.3f k1 %.4f"%(d["value"]/1e6,d["e2e"]["value"]/1e6,d["ms_per_step"],d["e2e"]["ms_per_step"],d["roofline"]["k1_avg_ms"]), d.get("pose_check"), d.get("iekf_step"))
+        if "cfg5" in d: c=d["cfg5"]; print("  cfg5 value %.1fM e2e %.1fM ms/step %.3f frac %.3f k1 %.4f gen %s s"%(c["value"]/1e6,c["e2e"]["value"]/1e6,c["ms_per_step"],c["roofline"]["frac"],c["roofline"]["k1_avg_ms"],c["map_gen_s"]))
+    except Exception as e: print("no bench line", f, e)
+PY

@@ -338,6 +338,11 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
         const bool dry = it < 0;
         long long t0 = 0;
         if (dry) {   // warm-up: identity-like sums, typical d_x (overwritten inside iekf_post)
+            // ... unless pass 0 is already done (small shards: the pass is shorter than the cold warm-up): then every stage of
+            // the warm-up would sit on the critical path, and a cold first step is the cheaper evil
+            if (tid == 0) S.go = *reinterpret_cast<const volatile unsigned long long*>(&D->sums_seq) >= A.base + 1ull ? 0 : 1;
+            __syncthreads();
+            if (!S.go) continue;
             if (tid < 32) S.sums[tid] = (tid == 28) ? 1e9 : ((tid == 0 || tid == 6 || tid == 11 || tid == 15 || tid == 18 || tid == 20) ? 1.0 : 0.0);
             __syncthreads();
         } else {
@@ -370,8 +375,13 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
         iekf_post(S, dry);
 
         if (dry) {
-            iekf_posterior(S);     // warms the final pass's code too; its inputs are rebuilt by the next iekf_pre ...
-            iekf_pre(S, laser_cov);   // ... which also restores P and A6 (dx_new etc. are pure functions of cur / pred)
+            __syncthreads();
+            if (tid == 0) S.go = *reinterpret_cast<const volatile unsigned long long*>(&D->sums_seq) >= A.base + 1ull ? 0 : 1;
+            __syncthreads();
+            if (S.go) {
+                iekf_posterior(S);     // warms the final pass's code too; its inputs are rebuilt by the next iekf_pre ...
+                iekf_pre(S, laser_cov);   // ... which also restores P and A6 (dx_new etc. are pure functions of cur / pred)
+            }
             continue;
         }
         if (S.singular) { end_loop(A, D, S, SRL_SINGULAR, tid); return; }
