@@ -140,9 +140,14 @@ int srl_ctx_set_timing(srl_ctx* ctx, int enable);
  * reach the host through a mapped pinned buffer + sequence flag; 0: cudaMemcpyAsync + stream synchronize),
  * "exchange_in_fit" (1 default: on several GPUs k1_fit's last block runs the NVLink exchange itself when the rank
  * flagged nothing, 0: always in the fallback launch), "fast_force_ambiguous_mod" (N > 0:
- * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over).  Counters: "exact_fallbacks"
+ * k1_fast hands every N-th keypoint to k1_assoc, to test the hand-over), "device_loop" (1 default: srl_update_iekf[_dist]
+ * keep the whole iterated update on the GPU — a persistent block runs the ESIKF algebra between the passes, all passes are
+ * enqueued at once, one host wait; 0: the host-driven loop, which is also used under kernel-serialising tools and for the
+ * residual cap), "pdl" (1 default: programmatic dependent launch of the pass kernels in the device loop), "eager_order"
+ * (1 default: a sweep is Morton-ordered right behind its upload instead of at its first pass).  Counters: "exact_fallbacks"
  * (keypoints whose FP32 selection in k1_assoc was ambiguous and were redone exactly), "fast_ambiguous" (keypoints
- * k1_fast handed to k1_assoc), "kernel_launches". */
+ * k1_fast handed to k1_assoc), "kernel_launches", "device_loop_active" (1 when the device-resident loop is in use on this
+ * ctx), "iekf_step_cycles_avg" (SM clock ticks of one ESIKF step, sums seen -> pose published; resets on read). */
 int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value);
 int srl_ctx_get_counter(srl_ctx* ctx, const char* name, int64_t* value);
 int srl_ctx_pass_time(srl_ctx* ctx, double* total_ms, int64_t* launches, int reset);
@@ -230,7 +235,9 @@ int srl_optimize_host_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep
                            const double R_il[9], const double t_il[3], const srl_icp_params* prm, srl_iekf_summary* summary,
                            double* world_xyz_out, size_t* shard_begin, size_t* shard_end);
 
-/* full loop on one GPU (sweep already resident) */
+/* full loop on one GPU (sweep already resident).  Default: device-resident (see "device_loop" above); the results of both
+ * forms agree to rounding (the device forms the gain with one 6x6 inverse via the Woodbury identity, the host form with the
+ * reference's two 17x17 inverses). */
 int srl_update_iekf(srl_ctx* ctx, srl_map* map, srl_sweep* sweep, srl_eskf_state* eskf, double frame_q[4],
                     double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],
                     const srl_icp_params* prm, srl_iekf_summary* summary);

@@ -15,6 +15,8 @@
 //   gridSampling                      src/utility.cpp:188           srl::LioBackend::gridSampling (keypoint indices)
 //   distortFrameByConstant / ByImu    src/utility.cpp:203,238       srl::LioBackend::distortFrameByConstant / distortFrameByImu
 //   transformAllImuPoint              src/utility.cpp:320           srl::LioBackend::transformAllImuPoint
+//   addPointToColorMap (loop :533-551) src/lioOptimization.cpp:448  srl::LioBackend::addPointsToColorMap
+//   rgbMapTracker::renderPointsInRecentVoxel  src/rgbMapTracker.cpp:216  srl::LioBackend::renderPointsInRecentVoxel
 #pragma once
 
 #include <array>
@@ -49,6 +51,7 @@ public:
         std::memset(t_imu_lidar, 0, sizeof(t_imu_lidar));
     }
     ~LioBackend() {
+        if (color_) srl_color_map_destroy(color_);
         if (sweep_) srl_sweep_destroy(sweep_);
         if (map_) srl_map_destroy(map_);
         if (ctx_) srl_ctx_destroy(ctx_);
@@ -167,10 +170,32 @@ public:
     srl_map* map() { return map_; }
     srl_sweep* sweep() { return sweep_; }
 
+    // ---- row N4: color_voxel_map + hashmap_3d_points + rgb_points_vec + voxels_recent_visited (include/lioOptimization.h:275-291)
+    // created on first use with the LiDAR map's voxel size and cap (src/lioOptimization.cpp:539 passes map_options' values)
+    void enableColorMap(double size_voxel_map, int max_num_points_in_voxel, size_t max_voxels, double min_distance_points) {
+        if (!color_) check(srl_color_map_create(ctx_, size_voxel_map, max_num_points_in_voxel, max_voxels, min_distance_points, &color_), "srl_color_map_create");
+    }
+    // the colour branch of addPointsToMap (src/lioOptimization.cpp:533-551): every add_point_step-th point of the registered frame
+    long long addPointsToColorMap(const double* xyz_world, size_t n, int add_point_step, double time_sweep_end, double time_last_process,
+                                  bool to_rendering) {
+        int64_t stored = 0;
+        check(srl_color_map_add_points(color_, xyz_world, n, add_point_step, time_sweep_end, time_last_process, to_rendering ? 1 : 0, &stored),
+              "srl_color_map_add_points");
+        return stored;
+    }
+    // rgbMapTracker::renderPointsInRecentVoxel (src/rgbMapTracker.cpp:216-237); returns render_point_count
+    long long renderPointsInRecentVoxel(const srl_camera& cam, const uint8_t* image_bgr, double obs_time) {
+        int64_t rendered = 0;
+        check(srl_color_map_render_recent(color_, &cam, image_bgr, obs_time, &rendered), "srl_color_map_render_recent");
+        return rendered;
+    }
+    srl_color_map* colorMap() { return color_; }
+
 private:
     srl_ctx* ctx_ = nullptr;
     srl_map* map_ = nullptr;
     srl_sweep* sweep_ = nullptr;
+    srl_color_map* color_ = nullptr;
 
     void check(int rc, const char* what) {
         if (rc != SRL_OK) throw std::runtime_error(std::string(what) + ": " + (ctx_ ? srl_last_error(ctx_) : "no context"));

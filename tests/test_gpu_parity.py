@@ -964,6 +964,11 @@ int main(int argc, char** argv) {
         std::printf("%d %lld %lld %d %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", pass, added, lio.mapSize(), (int)s.success,
                     s.passes_run, s.num_residuals_used, ft[0], ft[1], ft[2], fq[0], fq[1], fq[2], fq[3], pass ? world[3 * 77 + 1] : 0.0);
     }
+    lio.enableColorMap(1.0, 20, 1 << 16, 0.15);                              // row N4 through the adapter
+    long long stored = lio.addPointsToColorMap(pts.data(), 30000, 2, 1.0, 0.0, true);
+    int64_t nv = 0, np = 0, nrgb = 0, nrec = 0, nnew = 0;
+    srl_color_map_stats(lio.colorMap(), &nv, &np, &nrgb, &nrec, &nnew);
+    std::printf("color %lld %lld %lld %lld %lld\n", stored, (long long)nv, (long long)np, (long long)nrgb, (long long)nrec);
     return 0;
 }''')
     exe = tmp_path / "drive"
@@ -973,7 +978,12 @@ int main(int argc, char** argv) {
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     rows = [ln.split() for ln in r.stdout.strip().splitlines()]
-    assert len(rows) == 2
+    assert len(rows) == 3
+    cmo = O.OracleColorMap()
+    stored = cmo.add_points(pts[:30000], add_point_step=2, time_sweep_end=1.0, time_last_process=0.0, to_rendering=True)
+    oc = cmo.counts()
+    assert [int(x) for x in rows[2][1:]] == [stored, oc["voxels"], stored, oc["rgb_points"], oc["recent"]]
+    rows = rows[:2]
     # the Python mirror on the same inputs
     Lp = lio.LioOptimization(max_voxels=1 << 18, sweep_capacity=1 << 17)
     try:
