@@ -50,6 +50,7 @@ a2 = L.addPointsToMap(reg)
 o2 = om.add_points(reg)
 print(f"second insert: gpu {a2} oracle {o2}; sizes {L.mapSize()} {om.num_points}", flush=True)
 
+print("device loop active:", L.ctx.counter("device_loop_active"), flush=True)
 prm = lio.r3live_params(max_num_residuals=2 ** 31 - 1)
 oprm = O.r3live_params(max_num_residuals=2 ** 31 - 1)
 L.setKeypoints(sw.raw_xyz)
