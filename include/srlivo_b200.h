@@ -214,7 +214,10 @@ int srl_iekf_step(srl_iekf_iter* it, const srl_normal_eq* ne, const srl_icp_para
  * the 32 sums is fused into the pass's last kernel: its final block writes them into every peer's mailbox over NVLink
  * peer memory (CUDA IPC mapping) and adds the peers' sums in rank order, so every rank ends a pass with the same
  * totals and runs the same host update.  Setup: create, export the 64-byte handle, exchange handles with any host
- * transport (rank order), connect.  All ranks must run the same sequence of passes. */
+ * transport (rank order), connect.  All ranks must run the same sequence of passes, and the same form of the loop: the
+ * device-resident and the host-driven form agree to rounding, not bit for bit — after connecting, read the counter
+ * "device_loop_active" on every rank and set option "device_loop" to 0 everywhere if any rank reports 0
+ * (sr_livo_b200/dist.py does). */
 typedef struct srl_comm srl_comm;
 int srl_comm_create(srl_ctx* ctx, int rank, int world, srl_comm** out);
 void srl_comm_destroy(srl_comm* comm);

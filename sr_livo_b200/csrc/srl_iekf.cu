@@ -465,7 +465,7 @@ cudaError_t probe_concurrent_kernels(cudaStream_t side, cudaStream_t main_stream
     if (e == cudaSuccess) e = cudaMemsetAsync(d_two_ints, 0, 2 * sizeof(int), main_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(main_stream);
     if (e != cudaSuccess) return e;
-    k_probe_wait<<<1, 1, 0, side>>>(d_two_ints, d_two_ints + 1, 40ll * 1000 * 1000);   // ~20 ms at 2 GHz
+    k_probe_wait<<<1, 1, 0, side>>>(d_two_ints, d_two_ints + 1, 100ll * 1000 * 1000);   // ~50 ms at 2 GHz
     k_probe_set<<<1, 1, 0, main_stream>>>(d_two_ints);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(side);

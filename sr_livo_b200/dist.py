@@ -112,6 +112,13 @@ class DistributedLio:
                 raise SrlError(rc, lib().srl_last_error(lio_opt.ctx.h).decode())
             tdist.barrier(group=group)
             self.comm = h
+            # every rank must run the same form of the loop (the device-resident and the host-driven form agree to rounding,
+            # not bit for bit, and the ranks' states are meant to stay bit-identical): if the device-resident loop is not
+            # usable on some rank (kernels serialised by a tool, a GPU shared with other processes), all ranks use the host form
+            active = [None] * world
+            tdist.all_gather_object(active, int(lio_opt.ctx.counter("device_loop_active")), group=group)
+            if min(active) == 0:
+                lio_opt.ctx.set_option("device_loop", 0)
 
     def close(self):
         if self.comm is not None:
