@@ -132,7 +132,9 @@ int64_t srl_ctx_kernel_launches(const srl_ctx* ctx);
 /* CUDA-event timing of the scan-matching kernel (k1_assoc) on the ctx stream: enable, then read the summed device
  * time and launch count of the passes since the last reset (bench.py "roofline"). Reading synchronises the stream. */
 int srl_ctx_set_timing(srl_ctx* ctx, int enable);
-/* tuning / test knobs: "force_exact_selection" (0|1: every keypoint takes k1_assoc's exact FP64 selection),
+/* tuning / test knobs (the kernel-variant selectors "split_lanes_per_keypoint", "fast_lanes_per_keypoint", "k1_min_blocks" and
+ * "fast_min_blocks" choose among compiled template instances and are process-wide, everything else is per ctx):
+ * "force_exact_selection" (0|1: every keypoint takes k1_assoc's exact FP64 selection),
  * "k1_variant" (0 auto; 1: k1_fast, 3: k1_scan + k1_fit, both with the exact fallback where applicable; 2: k1_assoc
  * only), "split_lanes_per_keypoint" (2|4: lanes per keypoint in k1_scan), "k1_min_blocks" (2|3|4) and
  * "fast_min_blocks" (4|5|6|8): resident-blocks-per-SM variants of the two kernels, "fast_lanes_per_keypoint" (1|2|4:

@@ -27,7 +27,12 @@ def allreduce_block(block, group=None):
     """Sum the 32-double result block over ranks, in place. `block` is a torch tensor (cuda for NCCL, cpu for gloo)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
+        if block.is_cuda and dist.get_backend(group) == "gloo":     # gloo reduces host tensors: stage the 256 bytes
+            host = block.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+            block.copy_(host)
+        else:
+            dist.all_reduce(block, op=dist.ReduceOp.SUM, group=group)
     return block
 
 

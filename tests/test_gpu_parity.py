@@ -1044,6 +1044,12 @@ assert np.allclose(o2["frame_t"], ref["frame_t"], atol=1e-9) and np.allclose(o2[
 expect = sw.raw_xyz @ O.quat_to_rot(o2["frame_q"]).T + o2["frame_t"]
 assert np.allclose(world_out[b:e], expect[b:e], rtol=0, atol=1e-10)
 assert np.isnan(world_out[:b]).all() and np.isnan(world_out[e:]).all()      # only this rank's rows are written
+# the baseline without peer memory: one all-reduce of the 32 sums per pass from Python, host-driven loop (native=False)
+Db = dist.DistributedLio(L, rank, world, native=False)
+Db.set_keypoints(sw.raw_xyz)
+L.eskf_pro = lio.EskfEstimator(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+ob = Db.updateIEKF(prm, sw.t_last)
+assert ob["passes"] == ref["passes"] and np.allclose(ob["frame_t"], o2["frame_t"], atol=1e-9) and np.allclose(ob["frame_q"], o2["frame_q"], atol=1e-9)
 D.close(); L.close(); tdist.destroy_process_group()
 print("rank", rank, "ok")
 """
