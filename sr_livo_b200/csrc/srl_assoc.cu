@@ -262,12 +262,8 @@ __device__ __forceinline__ void select_exact(const float* __restrict__ blocks, c
 __device__ __forceinline__ void publish_to_host(const K1Args& A, double tot, int lane) {
     if (!A.host_out) return;
     A.host_out[lane] = tot;
-    __threadfence_system();
     __syncwarp();
-    if (lane == 0) {
-        *reinterpret_cast<volatile unsigned long long*>(A.host_out + 32) = A.host_seq;
-        __threadfence_system();
-    }
+    if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(A.host_out + 32), A.host_seq);
 }
 
 template <int NCH, bool DEBUG, int MINB>

@@ -976,17 +976,17 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
 #pragma unroll
         for (int w = 0; w < kFastWarps; ++w) s += s_acc[w][lane];
         A.partials[(size_t)blockIdx.x * 32 + lane] = s;
-        __threadfence();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {   // release (the block's row, through the barrier) - ticket - acquire (the other blocks' rows): one thread fences
+        fence_acq_rel_gpu();
         const unsigned t = atomicAdd(A.chunk_tickets + chunk, 1u);
+        fence_acq_rel_gpu();
         s_role = (t == in_chunk - 1) ? 1 : 0;
     }
     __syncthreads();
     if (!s_role) return;
     {   // this block closes its chunk: sum the chunk's rows (warp w takes rows w, w + 4, ...: 8 independent loads each)
-        __threadfence();
         double r[kChunkBlocks / kFastWarps];
 #pragma unroll
         for (int u = 0; u < kChunkBlocks / kFastWarps; ++u) {
@@ -1004,19 +1004,19 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
 #pragma unroll
             for (int w = 0; w < kFastWarps; ++w) cs += s_acc[w][lane];
             A.chunk_sums[(size_t)chunk * 32 + lane] = cs;
-            __threadfence();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             A.chunk_tickets[chunk] = 0u;
+            fence_acq_rel_gpu();
             const unsigned t = atomicAdd(A.ticket, 1u);
+            fence_acq_rel_gpu();
             s_role = (t == n_chunks - 1) ? 2 : 0;
         }
         __syncthreads();
         if (s_role != 2) return;
     }
     {   // this block closes the last chunk: the pass's totals
-        __threadfence();
         double s = 0.0;
         for (unsigned ch = (unsigned)warp; ch < n_chunks; ch += kFastWarps) s += __ldcg(A.chunk_sums + (size_t)ch * 32 + lane);
         __syncthreads();
@@ -1042,12 +1042,8 @@ __global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
             if (final_here) publish_sums_to_loop(A.dev, A.pose_ticket, tot, lane);   // device-resident loop: the ESIKF block takes over
             if (A.host_out && final_here) {
                 A.host_out[lane] = tot;
-                __threadfence_system();
                 __syncwarp();
-                if (lane == 0) {
-                    *reinterpret_cast<volatile unsigned long long*>(A.host_out + 32) = A.host_seq;
-                    __threadfence_system();
-                }
+                if (lane == 0) st_release_sys(reinterpret_cast<unsigned long long*>(A.host_out + 32), A.host_seq);
             }
         }
     }

@@ -280,20 +280,15 @@ __device__ __forceinline__ void publish_loop_result(const IekfLoopArgs& A, const
     if (tid < kLoopMaxPasses) O->step_cycles[tid] = D->step_cycles[tid];
     if (tid < 8) O->stage_cycles[tid] = D->stage_cycles[tid];
     if (tid == 0) { O->status = D->status; O->passes_run = D->passes_run; O->num_residuals_used = D->num_residuals_used; O->converged = D->converged; }
-    __threadfence_system();
     __syncthreads();
-    if (tid == 0) {
-        *reinterpret_cast<volatile unsigned long long*>(&O->seq) = A.host_seq;
-        __threadfence_system();
-    }
+    if (tid == 0) st_release_sys(&O->seq, A.host_seq);
 }
 
 // the loop has ended: release every pass kernel still enqueued, hand the result to the host
 __device__ __forceinline__ void end_loop(const IekfLoopArgs& A, IekfDev* D, IekfShared& S, int status, int tid) {
     if (tid == 0) {
         D->status = status; D->done = 1;
-        __threadfence();
-        *reinterpret_cast<volatile unsigned long long*>(&D->pose_seq) = A.base + 63ull;
+        st_release_gpu(&D->pose_seq, A.base + 63ull);
     }
     __syncthreads();
     publish_loop_result(A, D, S.sums, tid);
@@ -347,12 +342,12 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
             __syncthreads();
         } else {
             if (tid == 0) {
-                const volatile unsigned long long* ss = &D->sums_seq;
+                const unsigned long long* ss = &D->sums_seq;
                 const unsigned long long want = A.base + (unsigned long long)it + 1ull;
                 long long spins = 0;
                 bool ok = true;
-                while (*ss < want) { if (++spins > (1ll << 27)) { ok = false; break; } }   // the pass never finished: give up, do not hang
-                __threadfence();
+                while (ld_relaxed_gpu(ss) < want) { if (++spins > (1ll << 27)) { ok = false; break; } }   // the pass never finished: give up, do not hang
+                if (ok) (void)ld_acquire_gpu(ss);
                 S.go = ok ? 1 : 0;
             }
             __syncthreads();
@@ -398,10 +393,9 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
             else if (tid >= 64 && tid < 73) D->pc.Rq[tid - 64] = S.Rq[tid - 64];
         }
         if (tid == 0 && done) D->done = 1;
-        __threadfence();
         __syncthreads();
         if (tid == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(&D->pose_seq) = done ? A.base + 63ull : A.base + (unsigned long long)it + 1ull;
+            st_release_gpu(&D->pose_seq, done ? A.base + 63ull : A.base + (unsigned long long)it + 1ull);
             if (it < kLoopMaxPasses) D->step_cycles[it] = clock64() - t0;
             for (int i = 1; i < 8; ++i) D->stage_cycles[i] = S.stamp[i] - S.stamp[0];
         }

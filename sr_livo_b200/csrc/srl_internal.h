@@ -87,6 +87,38 @@ cudaError_t launch_iekf_loop(const IekfLoopArgs& a, cudaStream_t stream);
 cudaError_t probe_concurrent_kernels(cudaStream_t side, cudaStream_t main_stream, int* d_two_ints, bool* concurrent);
 
 #if defined(__CUDACC__)
+// Message passing between kernels / GPUs / the host: payload stores, then a RELEASE store of the ticket; the reader polls
+// the ticket (relaxed) and ends with one ACQUIRE load.  __threadfence() is fence.sc (MEMBAR.SC + an L1 invalidate) executed
+// by every calling thread; the release store is one MEMBAR.ALL by one thread, the acquire load only invalidates L1 — and
+// the release is cumulative over the stores of the threads that reached it through __syncthreads() / __syncwarp().
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // Fused exchange over NVLink peer memory (one warp): publish this rank's 32 sums into every rank's mailbox, wait for the
 // others' sums of the same pass, add all of them in rank order (bitwise identical everywhere).  NaN marks a failed exchange.
 __device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, int lane) {
@@ -95,21 +127,16 @@ __device__ __forceinline__ double comm_exchange(const CommDev& cm, double tot, i
     if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(cm.seq) = seq;
     const int par = (int)(seq & 1ull);
     for (int p = 0; p < cm.world; ++p) cm.mail[p]->data[par][cm.rank][lane] = tot;
-    __threadfence_system();
     __syncwarp();
-    if (lane < cm.world) {
-        volatile unsigned long long* f = &cm.mail[lane]->flag[par][cm.rank];
-        *f = seq;
-    }
-    __threadfence_system();
+    if (lane < cm.world) st_release_sys(&cm.mail[lane]->flag[par][cm.rank], seq);   // covers the warp's 32 stores to that peer
     bool ok = true;
     if (lane < cm.world) {
-        volatile unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
+        const unsigned long long* f = &cm.mail[cm.rank]->flag[par][lane];
         long long spins = 0;
-        while (*f < seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+        while (ld_relaxed_sys(f) < seq) { if (++spins > (1ll << 27)) { ok = false; break; } }   // a peer died: give up, do not hang
+        (void)ld_acquire_sys(f);
     }
     ok = __all_sync(0xffffffffu, ok);
-    __threadfence_system();
     double sum = 0.0;
     for (int r = 0; r < cm.world; ++r) {
         const volatile double* d = &cm.mail[cm.rank]->data[par][r][lane];
@@ -207,11 +234,11 @@ __device__ __forceinline__ bool load_pass_const(const IekfDev* dev, int wait_pos
     if (dev && wait_pose) {
         __shared__ int s_go;
         if (threadIdx.x == 0) {
-            const volatile unsigned long long* ps = &dev->pose_seq;
+            const unsigned long long* ps = &dev->pose_seq;
             long long spins = 0;
             unsigned long long v;
-            while ((v = *ps) < ticket) { if (++spins > (1ll << 26)) { v = ~0ull; break; } }   // the ESIKF block died: leave, do not hang
-            __threadfence();
+            while ((v = ld_relaxed_gpu(ps)) < ticket) { if (++spins > (1ll << 26)) { v = ~0ull; break; } }   // the ESIKF block died: leave, do not hang
+            if (v != ~0ull) v = ld_acquire_gpu(ps);
             s_go = v < end_ticket ? 1 : 0;   // a ticket beyond the sweep's passes = the loop has ended (also a later sweep's)
         }
         __syncthreads();
@@ -227,12 +254,8 @@ __device__ __forceinline__ bool load_pass_const(const IekfDev* dev, int wait_pos
 __device__ __forceinline__ void publish_sums_to_loop(IekfDev* dev, unsigned long long ticket, double tot, int lane) {
     if (!dev) return;
     dev->sums[lane] = tot;
-    __threadfence();
     __syncwarp();
-    if (lane == 0) {
-        *reinterpret_cast<volatile unsigned long long*>(&dev->sums_seq) = ticket + 1ull;
-        __threadfence();
-    }
+    if (lane == 0) st_release_gpu(&dev->sums_seq, ticket + 1ull);
 }
 #endif
 
