@@ -262,6 +262,9 @@ def run_cfg5(args, torch, tdist, dist, lio, synth, rank, world, local, stream, f
                         "frac": alg_bytes / world / (k1_avg * 1e-3) / 1e9 / peak, "bytes_per_launch_per_gpu": alg_bytes / world,
                         "bytes_basis": "GPU-scanned candidates, summed over ranks (the oracle's sum C_k is an N=1 leg)",
                         "k1_avg_ms": k1_avg, "note": "per-GPU achieved bandwidth of one pass (incl. the wait for the pose ticket)"},
+           "ms_per_step_stats": {"resident": {"p50": float(np.median(ms_res)), "min": float(ms_res.min()), "max": float(ms_res.max())},
+                                 "e2e": {"p50": float(np.median(ms_e2e)), "min": float(ms_e2e.min()), "max": float(ms_e2e.max())},
+                                 "note": "this rank's per-step CUDA-event times; the values above are their means (max over ranks)"},
            "map_gen_s": round(t_gen, 1), "map_insert_s": round(t_ins, 2)}
     if D5 is not None:
         D5.close()

@@ -4,7 +4,7 @@ N=${2:-2}
 OUT=gpurun_out/${1:-m2}
 mkdir -p $OUT
 timeout 900 python -m pytest tests -q -m gpu -x -k "exchange_ranks" > $OUT/pytest_dist.log 2>&1; echo "pytest dist rc=$?"; tail -3 $OUT/pytest_dist.log
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N rc=$?"; tail -3 $OUT/bench_n$N.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 3 --cfg5-steps 6 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N rc=$?"; tail -3 $OUT/bench_n$N.err
 SRL_DEVICE_LOOP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 50 --warmup 3 --no-cfg5 > $OUT/bench_n${N}_hostloop.json 2> $OUT/bench_n${N}_hostloop.err; echo "bench hostloop rc=$?"
 python - <<PY
 import json
