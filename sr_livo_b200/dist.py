@@ -153,26 +153,17 @@ class DistributedLio:
             raise SrlError(capi.SRL_BAD_ARG, "DistributedLio.optimize needs the native exchange (native=True, world > 1)")
         raw = capi.f64(raw_xyz).reshape(-1, 3)
         n = raw.shape[0]
-        st = self.L.eskf_pro.to_c()
-        fq = capi.f64(self.L.eskf_pro.q if frame_q is None else frame_q).copy()
-        ft = capi.f64(self.L.eskf_pro.p if frame_t is None else frame_t).copy()
-        tl = capi.f64(t_last)
-        R, ti = capi.f64(self.L.R_imu_lidar).reshape(9), capi.f64(self.L.t_imu_lidar)
-        summ = capi.IekfSummary()
+        bufs = self.L._call_buffers()
+        self.L._marshal(bufs, t_last, frame_q, frame_t)
         b, e = C.c_size_t(0), C.c_size_t(0)
-        rc = lib().srl_optimize_host_dist(self.L.ctx.h, self.comm, self.L.voxel_map.h, self.L.sweep.h, ptr(raw), n, C.byref(st),
-                                          ptr(fq), ptr(ft), ptr(tl), ptr(R), ptr(ti), C.byref(prm), C.byref(summ),
+        rc = lib().srl_optimize_host_dist(self.L.ctx.h, self.comm, self.L.voxel_map.h, self.L.sweep.h, ptr(raw), n, bufs["st_ref"],
+                                          bufs["p_fq"], bufs["p_ft"], bufs["p_tl"], bufs["p_R"], bufs["p_ti"], C.byref(prm), bufs["summ_ref"],
                                           ptr(world_out) if world_out is not None else None, C.byref(b), C.byref(e))
         self.range = (b.value, e.value)
         self.L.sweep.n = e.value - b.value
-        if rc == capi.SRL_NAN_PLANARITY:
-            raise RuntimeError("error")
-        if rc not in (capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS):
-            raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
-        self.L.eskf_pro = EskfEstimator.from_c(st)
-        return dict(success=bool(summ.success) and rc == capi.SRL_OK, passes=summ.passes_run, converged=bool(summ.converged),
-                    num_residuals_used=summ.num_residuals_used, trace=capi.summary_trace(summ), frame_q=fq, frame_t=ft,
-                    range=self.range)
+        out = self._result(bufs, rc)
+        out["range"] = self.range
+        return out
 
     def _pass(self, prm: IcpParams, t_last):
         from .lio import make_frame
@@ -188,25 +179,22 @@ class DistributedLio:
             return self.block
         return fn
 
+    def _result(self, b, rc):
+        summ, fq, ft = self.L._unmarshal(b, rc)
+        return dict(success=summ.success, passes=summ.passes_run, converged=summ.converged, num_residuals_used=summ.num_residuals_used,
+                    trace=summ.trace, frame_q=fq, frame_t=ft)
+
     def updateIEKF(self, prm: IcpParams, t_last, frame_q=None, frame_t=None):
         from .lio import EskfEstimator
+        if self.comm is not None:
+            b = self.L._call_buffers()
+            self.L._marshal(b, t_last, frame_q, frame_t)
+            rc = lib().srl_update_iekf_dist(self.L.ctx.h, self.comm, self.L.voxel_map.h, self.L.sweep.h, b["st_ref"], b["p_fq"], b["p_ft"],
+                                            b["p_tl"], b["p_R"], b["p_ti"], C.byref(prm), b["summ_ref"])
+            return self._result(b, rc)
         st = self.L.eskf_pro.to_c()
         fq = capi.f64(self.L.eskf_pro.q if frame_q is None else frame_q).copy()
         ft = capi.f64(self.L.eskf_pro.p if frame_t is None else frame_t).copy()
-        if self.comm is not None:
-            tl = capi.f64(t_last)
-            R, ti = capi.f64(self.L.R_imu_lidar).reshape(9), capi.f64(self.L.t_imu_lidar)
-            summ = capi.IekfSummary()
-            rc = lib().srl_update_iekf_dist(self.L.ctx.h, self.comm, self.L.voxel_map.h, self.L.sweep.h, C.byref(st), ptr(fq),
-                                            ptr(ft), ptr(tl), ptr(R), ptr(ti), C.byref(prm), C.byref(summ))
-            if rc == capi.SRL_NAN_PLANARITY:
-                raise RuntimeError("error")
-            if rc not in (capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS):
-                raise SrlError(rc, lib().srl_last_error(self.L.ctx.h).decode())
-            self.L.eskf_pro = EskfEstimator.from_c(st)
-            trace = capi.summary_trace(summ)
-            return dict(success=bool(summ.success) and rc == capi.SRL_OK, passes=summ.passes_run, converged=bool(summ.converged),
-                        num_residuals_used=summ.num_residuals_used, trace=trace, frame_q=fq, frame_t=ft)
         out = iekf_loop(self._pass(prm, capi.f64(t_last)), st, fq, ft, prm, self.group)
         self.L.eskf_pro = EskfEstimator.from_c(st)
         out["frame_q"], out["frame_t"] = fq, ft

@@ -428,25 +428,50 @@ class LioOptimization:
                               num_residuals=ne.num_residuals, num_full_neighborhoods=ne.num_full_neighborhoods,
                               num_candidates_scanned=ne.num_candidates_scanned, success=(rc == capi.SRL_OK), **arrs)
 
-    # ---- src/optimize.cpp:133-314
-    def updateIEKF(self, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None):
-        st = self.eskf_pro.to_c()
-        fq = np.array(self.eskf_pro.q if frame_q is None else frame_q, np.float64)
-        ft = np.array(self.eskf_pro.p if frame_t is None else frame_t, np.float64)
-        tl = f64(t_last)
-        R = f64(self.R_imu_lidar).reshape(9)
-        ti = f64(self.t_imu_lidar)
-        summ = self._summ if hasattr(self, "_summ") else IekfSummary()   # 6 KB: allocated once, overwritten by every call
-        self._summ = summ
-        rc = lib().srl_update_iekf(self.ctx.h, self.voxel_map.h, self.sweep.h, C.byref(st), ptr(fq), ptr(ft), ptr(tl),
-                                   ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ))
+    def _call_buffers(self):
+        """Argument marshalling of the per-sweep calls, built once: a persistent srl_eskf_state with a float64 view over it,
+        one float64 block for frame_q | frame_t | t_last | R_il | t_il with precomputed pointers, one srl_iekf_summary.
+        (Fresh numpy arrays + ctypes pointer objects per call were ~20 us of Python inside every timed sweep.)"""
+        b = getattr(self, "_bufs", None)
+        if b is None:
+            st = capi.EskfState()
+            blk = np.zeros(4 + 3 + 3 + 9 + 3, np.float64)
+            base = blk.ctypes.data
+            b = self._bufs = dict(st=st, st_view=np.frombuffer(st, dtype=np.float64), st_ref=C.byref(st), blk=blk,
+                                  p_fq=C.c_void_p(base), p_ft=C.c_void_p(base + 32), p_tl=C.c_void_p(base + 56),
+                                  p_R=C.c_void_p(base + 80), p_ti=C.c_void_p(base + 152), summ=IekfSummary())
+            b["summ_ref"] = C.byref(b["summ"])
+        return b
+
+    def _marshal(self, b, t_last, frame_q, frame_t):
+        e, v, blk = self.eskf_pro, b["st_view"], b["blk"]
+        v[0:3] = e.p; v[3:7] = e.q; v[7:10] = e.v; v[10:13] = e.ba; v[13:16] = e.bg; v[16:19] = e.g
+        v[19:] = np.asarray(e.cov, np.float64).reshape(-1)
+        blk[0:4] = e.q if frame_q is None else frame_q
+        blk[4:7] = e.p if frame_t is None else frame_t
+        blk[7:10] = t_last
+        blk[10:19] = np.asarray(self.R_imu_lidar, np.float64).reshape(-1)
+        blk[19:22] = self.t_imu_lidar
+
+    def _unmarshal(self, b, rc):
         if rc == capi.SRL_NAN_PLANARITY:
             raise RuntimeError("error")
         _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
-        self.eskf_pro = EskfEstimator.from_c(st)
-        trace = capi.summary_trace(summ)
+        a = b["st_view"].copy()
+        self.eskf_pro = EskfEstimator(p=a[0:3], q=a[3:7], v=a[7:10], ba=a[10:13], bg=a[13:16], g=a[16:19], cov=a[19:].reshape(NS, NS))
+        summ = b["summ"]
+        blk = b["blk"]
         return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
-                               passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft
+                               passes_run=summ.passes_run, converged=bool(summ.converged), trace=capi.summary_trace(summ)), \
+            blk[0:4].copy(), blk[4:7].copy()
+
+    # ---- src/optimize.cpp:133-314
+    def updateIEKF(self, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None):
+        b = self._call_buffers()
+        self._marshal(b, t_last, frame_q, frame_t)
+        rc = lib().srl_update_iekf(self.ctx.h, self.voxel_map.h, self.sweep.h, b["st_ref"], b["p_fq"], b["p_ft"], b["p_tl"],
+                                   b["p_R"], b["p_ti"], C.byref(cur_icp_options), b["summ_ref"])
+        return self._unmarshal(b, rc)
 
     # ---- src/optimize.cpp:428-448 with the keypoints already selected (gridSampling is a "next" row)
     def optimize(self, raw_xyz, cur_icp_options: IcpParams, t_last, frame_q=None, frame_t=None, want_world: bool = True,
@@ -455,25 +480,15 @@ class LioOptimization:
         buffer to avoid staging); raw_xyz may likewise live in pinned memory."""
         raw = f64(raw_xyz).reshape(-1, 3)
         n = raw.shape[0]
-        st = self.eskf_pro.to_c()
-        fq = f64(self.eskf_pro.q if frame_q is None else frame_q).copy()
-        ft = f64(self.eskf_pro.p if frame_t is None else frame_t).copy()
-        tl = f64(t_last)
-        R = f64(self.R_imu_lidar).reshape(9)
-        ti = f64(self.t_imu_lidar)
-        summ = IekfSummary()
+        b = self._call_buffers()
+        self._marshal(b, t_last, frame_q, frame_t)
         world = (world_out if world_out is not None else np.empty((n, 3))) if want_world else None
-        rc = lib().srl_optimize_host(self.ctx.h, self.voxel_map.h, self.sweep.h, ptr(raw), n, C.byref(st), ptr(fq), ptr(ft),
-                                     ptr(tl), ptr(R), ptr(ti), C.byref(cur_icp_options), C.byref(summ),
+        rc = lib().srl_optimize_host(self.ctx.h, self.voxel_map.h, self.sweep.h, ptr(raw), n, b["st_ref"], b["p_fq"], b["p_ft"],
+                                     b["p_tl"], b["p_R"], b["p_ti"], C.byref(cur_icp_options), b["summ_ref"],
                                      ptr(world) if want_world else None)
         self.sweep.n = n
-        if rc == capi.SRL_NAN_PLANARITY:
-            raise RuntimeError("error")
-        _check(self.ctx.h, rc, ok=(capi.SRL_OK, capi.SRL_TOO_FEW_RESIDUALS))
-        self.eskf_pro = EskfEstimator.from_c(st)
-        trace = capi.summary_trace(summ)
-        return OptimizeSummary(success=bool(summ.success) and rc == capi.SRL_OK, num_residuals_used=summ.num_residuals_used,
-                               passes_run=summ.passes_run, converged=bool(summ.converged), trace=trace), fq, ft, world
+        summ, fq, ft = self._unmarshal(b, rc)
+        return summ, fq, ft, world
 
 
 __all__ = ["Context", "VoxelHashMap", "ColorVoxelMap", "Sweep", "EskfEstimator", "LioOptimization", "OptimizeSummary", "PlaneResiduals",
