@@ -633,7 +633,7 @@ int srl_build_plane_residuals(srl_ctx* ctx, srl_map* map, srl_sweep* sw, const s
 
 // ---- iterated update ---------------------------------------------------------------------------------------
 // Row N1: the whole updateIEKF loop enqueued at once.  Pass 0 takes its pose by value; every later pass reads the pose
-// k_iekf_step left in HBM and leaves immediately once the loop has ended on the device.  One host wait at the end, on
+// the persistent ESIKF block (k_iekf_loop) left in HBM and leaves immediately once the loop has ended on the device.  One host wait at the end, on
 // the sequence flag the finishing step writes into mapped pinned memory after the state, the trace and the summary.
 static int update_iekf_device(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep* sw, srl_eskf_state* eskf, double frame_q[4],
                               double frame_t[3], const double t_last[3], const double R_il[9], const double t_il[3],

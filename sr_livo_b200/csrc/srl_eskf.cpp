@@ -1,4 +1,5 @@
-// srl_eskf.cpp — host side of the iterated ESIKF update (O(1) per pass, stays on the CPU).
+// srl_eskf.cpp — the iterated ESIKF update on the host: the algebra of the host-driven loop (residual cap, profilers, A/B; the
+// default loop runs the same algebra on the device, srl_iekf.cu) and eskfEstimator::observe.
 //
 // Implements what lioOptimization::updateIEKF does around buildPlaneResiduals
 // (src/optimize.cpp:138-143 snapshot, :172-232 boxminus + covariance projection, :234-244 gain and d_x,

@@ -3,7 +3,7 @@
 // What lioOptimization::updateIEKF does around buildPlaneResiduals is 3-, 4- and 17-dimensional algebra
 // (src/optimize.cpp:172-310) on top of the numType helpers (include/utility.h:194-330), AngularDistance
 // (src/utility.cpp:146-153) and eskfEstimator::observe (src/eskfEstimator.cpp:219-230).  The same source is compiled
-// for the host loop (srl_eskf.cpp, srl_iekf_step) and for the device-resident loop (srl_iekf.cu, k_iekf_step).
+// for the host loop (srl_eskf.cpp, srl_iekf_step) and for the device-resident loop (srl_iekf.cu, k_iekf_loop).
 // Operation order follows Eigen's fixed-size reductions (a0 + (a1 + a2)) where the reference uses them.
 #pragma once
 

@@ -35,7 +35,7 @@ struct CommDev {              // by-value kernel argument; world <= 1 disables t
 // ---- device-resident updateIEKF loop (srl_iekf.cu, row N1) ------------------------------------------------------
 // One persistent 128-thread block per sweep (k_iekf_loop, on the ctx's side stream) runs the ESIKF algebra of every
 // pass; the pass kernels on the main stream and that block hand data to each other through HBM and three tickets:
-//   alive_seq : the block is resident (the pass kernels may spin on it without starving it)
+//   alive_seq : set by the block when it starts (diagnostics: the block is launched before any pass kernel that waits for it)
 //   sums_seq  : ticket + 1 once the sums of the pass with that ticket are in `sums` (written by the pass's last block)
 //   pose_seq  : >= ticket once the constants of the pass with that ticket are in `pc` (written by the ESIKF block); the
 //               block stores a ticket beyond every pass of the sweep when the loop has ended (`done`)

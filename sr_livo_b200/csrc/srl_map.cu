@@ -311,7 +311,6 @@ __global__ void k_color_emit_rgb(Slot* fine, unsigned int fmask, const unsigned 
     short x, y, z;
     unpack_key(k, x, y, z);
     slot_claim(fine, fmask, k, x, y, z, (unsigned)pos, 1u);       // hashmap_3d_points.insert (:481, :506)
-    if (j + 1 == m || true) { /* the count is finalised by the host from rank/winner of the last element */ }
 }
 
 struct CamConst { double R[9], t_cw[3], t_wc[3], fx, fy, cx, cy, fov; int cols, rows; };

@@ -445,7 +445,7 @@ def test_update_iekf_matches_oracle(L, small_world, kw):
 @pytest.mark.parametrize("kw", [dict(), dict(frame_id=5, num_iters_icp=3), dict(threshold_translation_norm=0.0),
                                 dict(threshold_translation_norm=0.0, num_iters_icp=2), dict(num_iters_icp=0)])
 def test_device_resident_loop_equals_host_driven_loop(L, small_world, kw):
-    """Row N1: k_iekf_step on the device (all passes enqueued at once, one host wait) against the round-1 host loop
+    """Row N1: the persistent ESIKF block on the device (all passes enqueued at once, one host wait) against the round-1 host loop
     (srl_iekf_step per pass): same passes, same early exit, state to 1e-9 — the two differ only in how the gain is formed
     (one 6x6 inverse via the Woodbury identity instead of two 17x17 inverses)."""
     from sr_livo_b200 import lio
