@@ -242,3 +242,40 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and line["value"] > 0
     assert "workload" in line["config"]
+
+
+def test_c_shard_range_matches_the_python_one():
+    """srl_shard_range (what srl_optimize_host_dist uses) == dist.shard_range (what the Python loop uses)."""
+    import ctypes as C
+    from sr_livo_b200 import dist
+    L = capi.lib()
+    for n in (0, 1, 31, 32, 33, 1000, 12345, 100000, 500000):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                b, e = C.c_size_t(0), C.c_size_t(0)
+                L.srl_shard_range(n, r, world, C.byref(b), C.byref(e))
+                assert (b.value, e.value) == dist.shard_range(n, r, world)
+
+
+def test_python_mirror_marshals_the_state_into_persistent_buffers():
+    """LioOptimization._marshal / _unmarshal: the srl_eskf_state view and the pose block carry exactly what to_c() carried."""
+    from sr_livo_b200 import lio
+
+    class Bare(lio.LioOptimization):
+        def __init__(self):
+            self.R_imu_lidar = np.arange(9.0).reshape(3, 3)
+            self.t_imu_lidar = np.array([0.1, 0.2, 0.3])
+            self.eskf_pro = lio.EskfEstimator(p=np.array([1.0, 2.0, 3.0]), q=np.array([0.1, 0.2, 0.3, 0.9]), v=np.array([4.0, 5.0, 6.0]),
+                                              ba=np.array([7.0, 8.0, 9.0]), bg=np.array([1.5, 2.5, 3.5]), g=np.array([0.0, 0.1, 9.8]),
+                                              cov=np.arange(289.0).reshape(17, 17))
+            self.ctx = None
+    L = Bare()
+    b = L._call_buffers()
+    L._marshal(b, [9.0, 8.0, 7.0], None, [5.0, 5.5, 6.0])
+    ref = L.eskf_pro.to_c()
+    for f in ("p", "q", "v", "ba", "bg", "g", "cov"):
+        assert list(getattr(b["st"], f)) == list(getattr(ref, f)), f
+    blk = b["blk"]
+    assert np.array_equal(blk[0:4], L.eskf_pro.q) and np.array_equal(blk[4:7], [5.0, 5.5, 6.0]) and np.array_equal(blk[7:10], [9.0, 8.0, 7.0])
+    assert np.array_equal(blk[10:19], np.arange(9.0)) and np.array_equal(blk[19:22], [0.1, 0.2, 0.3])
+    assert L._call_buffers() is b                                    # built once
