@@ -683,7 +683,14 @@ static int update_iekf_device(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sw
         ap.end_ticket = la.base + 63ull;
         ap.wait_pose = p ? 1 : 0;                                    // pass 0: pose by value
         if (ctx->timing) cudaEventRecord(ctx->loop_ev0[p], ctx->stream);
-        if ((rc = launch_pass(ctx, sw, ap, false, false, ctx->pdl && !ctx->timing)) != SRL_OK) return rc;
+        if ((rc = launch_pass(ctx, sw, ap, false, false, ctx->pdl && !ctx->timing)) != SRL_OK) {
+            // the persistent block is waiting for a pass that will never come: tell it, wait for it to leave, report the launch error
+            const std::string why = ctx->err;
+            launch_iekf_abort(ctx->d_iekf, ctx->stream);
+            cudaStreamSynchronize(ctx->loop_stream);
+            cudaGetLastError();
+            return set_err(ctx, rc, why);
+        }
         if (ctx->timing) cudaEventRecord(ctx->loop_ev1[p], ctx->stream);
     }
     // the one host wait of the sweep
@@ -955,8 +962,8 @@ int srl_optimize_host_dist(srl_ctx* ctx, srl_comm* comm, srl_map* map, srl_sweep
 // ---- host unit hook for the per-keypoint math (same source as the kernel's phase 2) -------------------------
 struct HostNb {
     const double* p;
-    bool use(int) const { return true; }
-    void get(int j, float& x, float& y, float& z) const { x = (float)p[3 * j]; y = (float)p[3 * j + 1]; z = (float)p[3 * j + 2]; }
+    SRL_HD bool use(int) const { return true; }
+    SRL_HD void get(int j, float& x, float& y, float& z) const { x = (float)p[3 * j]; y = (float)p[3 * j + 1]; z = (float)p[3 * j + 2]; }
 };
 int srl_host_plane_fit(const double* nbr_xyz, int32_t K, double normal[3], double* a2D, double evals[3]) {
     if (!nbr_xyz || K < 1 || !normal || !a2D || !evals) return SRL_BAD_ARG;

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
     // ---- srl_iekf_begin (src/optimize.cpp:135-147): install the loop state
     if (tid == 0) {
         *reinterpret_cast<volatile unsigned long long*>(&D->alive_seq) = A.base;
-        D->done = 0; D->status = SRL_OK; D->pass_index = -1; D->max_iter = init.max_iter;
+        D->done = 0; D->abort = 0; D->status = SRL_OK; D->pass_index = -1; D->max_iter = init.max_iter;
         D->passes_run = 0; D->converged = 0; D->num_residuals_used = 0; D->frame_id = init.frame_id;
         D->min_neighbors = init.min_neighbors;
         D->laser_cov = init.laser_cov; D->thr_t = init.thr_t; D->thr_r = init.thr_r;
@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
                 const unsigned long long want = A.base + (unsigned long long)it + 1ull;
                 long long spins = 0;
                 bool ok = true;
-                while (ld_relaxed_gpu(ss) < want) { if (++spins > (1ll << 27)) { ok = false; break; } }   // the pass never finished: give up, do not hang
+                while (ld_relaxed_gpu(ss) < want) {   // the pass never finished (or the host gave up enqueueing): end the loop, do not hang
+                    if (++spins > (1ll << 27) || ((spins & 63) == 0 && *reinterpret_cast<const volatile int*>(&D->abort))) { ok = false; break; }
+                }
                 if (ok) (void)ld_acquire_gpu(ss);
                 S.go = ok ? 1 : 0;
             }
@@ -439,6 +441,12 @@ __global__ void __launch_bounds__(kIekfThreads, 1) k_iekf_loop(const __grid_cons
     }
 }
 
+__global__ void k_iekf_abort(IekfDev* D) { *reinterpret_cast<volatile int*>(&D->abort) = 1; }
+cudaError_t launch_iekf_abort(IekfDev* dev, cudaStream_t stream) {
+    k_iekf_abort<<<1, 1, 0, stream>>>(dev);
+    return cudaGetLastError();
+}
+
 // ---- can two kernels of this process run at the same time?  Under kernel-serialising tools (ncu, some sanitizer modes,
 //      CUDA_LAUNCH_BLOCKING=1) they cannot, and a persistent block that waits for other kernels would only time out.
 //      One probe per ctx: a one-thread kernel on the side stream waits (bounded) for a word that a kernel on the main
@@ -455,6 +463,7 @@ cudaError_t probe_concurrent_kernels(cudaStream_t side, cudaStream_t main_stream
     cudaFuncAttributes at;   // load all three kernels now: a lazy load during the probe would wait for the waiting kernel
     cudaError_t e = cudaFuncGetAttributes(&at, k_probe_wait);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k_probe_set);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k_iekf_abort);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, k_iekf_loop);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_two_ints, 0, 2 * sizeof(int), main_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(main_stream);

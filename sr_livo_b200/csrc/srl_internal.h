@@ -49,7 +49,8 @@ struct IekfDev {              // one per ctx, in HBM
     int pass_index;           // i of the next step, starts at -1 (src/optimize.cpp:147)
     int max_iter;
     int passes_run, converged, num_residuals_used, frame_id;
-    int min_neighbors, pad0;
+    int min_neighbors;
+    int abort;                // set by k_iekf_abort when the host could not enqueue a pass: the block stops waiting and ends the loop
     double laser_cov, thr_t, thr_r;
     double sums[32];          // the (all-reduced) sums of the pass in flight
     srl_eskf_state cur, predict;   // eskf_pro now / the snapshot of :138-143
@@ -84,6 +85,7 @@ struct IekfLoopArgs {
     IekfInit init;
 };
 cudaError_t launch_iekf_loop(const IekfLoopArgs& a, cudaStream_t stream);
+cudaError_t launch_iekf_abort(IekfDev* dev, cudaStream_t stream);
 cudaError_t probe_concurrent_kernels(cudaStream_t side, cudaStream_t main_stream, int* d_two_ints, bool* concurrent);
 
 #if defined(__CUDACC__)
