@@ -267,7 +267,7 @@ __device__ __forceinline__ void publish_to_host(const K1Args& A, double tot, int
 }
 
 template <int NCH, bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const K1Args A) {
+__global__ void __launch_bounds__(kK1Threads, MINB) k1_assoc(const __grid_constant__ K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -90,7 +90,7 @@ __device__ __forceinline__ float key_value(unsigned key) {   // packed key -> (t
 // network over shuffles and lane 0 of the group finishes.  More lanes per keypoint = shorter dependent chain per
 // thread and more warps in flight (a 100k-point sweep is only 21 warps per SM at LPK = 1).
 template <bool DEBUG, int MINB, int NU, int LPK>
-__global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const FastArgs A) {
+__global__ void __launch_bounds__(kFastThreads, MINB) k1_fast(const __grid_constant__ FastArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     constexpr int KPW = 32 / LPK;                 // keypoints per warp
@@ -468,7 +468,7 @@ __device__ __forceinline__ void sort_bitonic16(unsigned (&x)[16]) {
 }
 
 template <int LPK, int NLS, int MINB>
-__global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const FastArgs A) {
+__global__ void __launch_bounds__(kScanThreads, MINB) k1_scan(const __grid_constant__ FastArgs A) {
     static_assert(LPK == 2 || LPK == 4, "lanes per keypoint");
     constexpr int KPW = 32 / LPK;                 // keypoints per warp
     constexpr int KPB = kScanThreads / LPK;       // keypoints per block
@@ -786,7 +786,7 @@ __device__ __forceinline__ unsigned visit_id(const float* blocks, unsigned cp, d
 }
 
 template <bool DEBUG, int MINB>
-__global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const FastArgs A) {
+__global__ void __launch_bounds__(kFastThreads, MINB) k1_fit(const __grid_constant__ FastArgs A) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     __shared__ PassConst s_c;

@@ -246,8 +246,9 @@ __device__ __forceinline__ bool load_pass_const(const IekfDev* dev, int wait_pos
         __syncthreads();
         if (!s_go) return false;
         if (threadIdx.x < ND) reinterpret_cast<double*>(&s_c)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(&dev->pc) + threadIdx.x);
-    } else if (threadIdx.x == 0) {
-        s_c = by_value;
+    } else if (threadIdx.x < ND) {   // by value: the kernel argument is __grid_constant__, so it can be indexed like memory (a
+        // copy by thread 0 alone kept every warp of the block at the barrier below for ~10 % of k1_fit's duration)
+        reinterpret_cast<double*>(&s_c)[threadIdx.x] = reinterpret_cast<const double*>(&by_value)[threadIdx.x];
     }
     __syncthreads();
     return true;
