@@ -413,6 +413,8 @@ def main():
     ms_res, _, _, launches = timed(step_resident, True)
     step_cycles = L.ctx.counter("iekf_step_cycles_avg")
     loop_on_device = bool(L.ctx.counter("device_loop_active"))
+    order_impl = {1: "single-launch cluster radix sort (k_sweep_order_cluster), verified against the CUB order at first use",
+                  0: "CUB radix sort", -1: "not used yet"}.get(L.ctx.counter("cluster_order_active"), "?")
     stage_cycles = [L.ctx.counter(f"iekf_stage_{i}") for i in range(8)]
     ms_e2e, _, _, _ = timed(step_e2e, False)
     # roofline leg: the same resident steps again with CUDA events around every pass's launches on the launching stream
@@ -547,7 +549,7 @@ def main():
                                            + ("inside the pass's last kernel over NVLink peer memory (CUDA IPC mailboxes)" if native else
                                               "with one NCCL all-reduce")) if world > 1 else "single GPU",
                            "l2": "no flush" if args.no_flush else "256 MB L2 flush between timed steps; 8 distinct sweeps cycled",
-                           "map_offered_points": int(n_offered), "map_gen_s": round(t_gen, 2), "map_insert_s": round(t_ins, 2)},
+                           "sweep_order": order_impl, "map_offered_points": int(n_offered), "map_gen_s": round(t_gen, 2), "map_insert_s": round(t_ins, 2)},
                 "sweeps_per_s": 1e3 / ms_step, "clocks": clk, "gpu_launches": int(launches),
                 "ms_per_step_stats": {"p50": float(np.median(ms_res)), "min": float(ms_res.min()), "max": float(ms_res.max()),
                                       "note": "this rank's per-step CUDA-event times; ms_per_step is their mean (max over ranks)"},

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "srl_internal.h"
@@ -1072,14 +1073,172 @@ __global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double
     idx[i] = (unsigned)i;
 }
 
+// ---- the same order in ONE launch: a thread-block cluster sorts the sweep's keys with a stable LSD radix sort (3 passes of
+// 8 bits over the 24-bit Morton keys).  The CUB path above is six launch-latency-bound kernels (~30 us for 100k keys);
+// here the CTAs of one cluster (8 portable, 16 where the device allows it) own consecutive chunks of the sequence, every
+// warp a consecutive sub-chunk; per pass: warp-private digit counts in shared memory -> CTA totals, which the other CTAs
+// read through distributed shared memory -> every CTA derives the global position of its first key of every digit ->
+// the warps scatter their keys in order (rank inside a round of 32 consecutive keys by __match_any_sync) -> cluster
+// barrier.  A stable sort has exactly one result, so the order is identical to the CUB one (checked once per ctx at first use).
+namespace cg = cooperative_groups;
+constexpr int kSortThreads = 1024, kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads, 1)
+k_sweep_order_cluster(const double* __restrict__ raw, long long n, double cell, unsigned* keys_a, unsigned* idx_a, unsigned* keys_b, unsigned* order_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned cta = cluster.block_rank(), n_cta = cluster.num_blocks();
+    __shared__ unsigned s_cnt[kSortWarps][256];   // per-warp digit counts, then the warp's running offset inside the CTA's run of that digit
+    __shared__ unsigned s_block[256];             // this CTA's digit totals (the other CTAs read them through DSMEM)
+    __shared__ unsigned s_base[256];              // global position of this CTA's first key with that digit
+    __shared__ unsigned s_scan[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n_warps = (long long)n_cta * kSortWarps;
+    const long long per = ((n + n_warps - 1) / n_warps + 31) / 32 * 32;   // keys per warp: consecutive, a multiple of 32
+    const long long gw = (long long)cta * kSortWarps + warp;
+    const long long begin = min(n, gw * per), end = min(n, begin + per);
+
+    for (long long i = (long long)cta * kSortThreads + tid; i < n; i += (long long)n_cta * kSortThreads) {
+        const double fx = fmin(fmax(floor(raw[3 * i] / cell) + 128.0, 0.0), 255.0);
+        const double fy = fmin(fmax(floor(raw[3 * i + 1] / cell) + 128.0, 0.0), 255.0);
+        const double fz = fmin(fmax(floor(raw[3 * i + 2] / cell) + 128.0, 0.0), 255.0);
+        keys_a[i] = spread8((unsigned)fx) | (spread8((unsigned)fy) << 1) | (spread8((unsigned)fz) << 2);
+        idx_a[i] = (unsigned)i;
+    }
+    __threadfence();
+    cluster.sync();
+
+    const unsigned* kin = keys_a;
+    const unsigned* iin = idx_a;
+    unsigned* kout = keys_b;
+    unsigned* iout = order_out;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = 8 * pass;
+        for (int d = lane; d < 256; d += 32) s_cnt[warp][d] = 0u;
+        __syncwarp();
+        for (long long j = begin + lane; j < end; j += 32) atomicAdd(&s_cnt[warp][(kin[j] >> shift) & 255u], 1u);
+        __syncthreads();
+        if (tid < 256) {   // exclusive prefix over the CTA's warps, and the CTA's total, per digit
+            unsigned run = 0;
+            for (int w = 0; w < kSortWarps; ++w) { const unsigned c = s_cnt[w][tid]; s_cnt[w][tid] = run; run += c; }
+            s_block[tid] = run;
+        }
+        cluster.sync();    // every CTA's s_block is complete
+        if (tid < 256) {
+            unsigned tot = 0, before = 0;
+            for (unsigned c = 0; c < n_cta; ++c) {
+                const unsigned v = *cluster.map_shared_rank(&s_block[tid], c);
+                tot += v;
+                if (c < cta) before += v;
+            }
+            s_scan[tid] = tot;
+            s_base[tid] = before;
+        }
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan of the 256 digit totals: 8 per lane, then a warp scan of the lane sums
+            unsigned v[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { v[q] = s_scan[lane * 8 + q]; sum += v[q]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += t; }
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { s_scan[lane * 8 + q] = run; run += v[q]; }
+        }
+        __syncthreads();
+        if (tid < 256) s_base[tid] += s_scan[tid];
+        __syncthreads();
+        for (long long j0 = begin; j0 < end; j0 += 32) {   // rounds of 32 consecutive keys, in order
+            const long long j = j0 + lane;
+            const bool valid = j < end;
+            const unsigned key = valid ? kin[j] : 0u;
+            const unsigned d = (key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(FULLM, valid ? d : (256u + (unsigned)lane));   // lanes past the end match nobody
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            if (valid) {
+                const unsigned pos = s_base[d] + s_cnt[warp][d] + rank;
+                kout[pos] = key;
+                iout[pos] = iin[j];
+            }
+            __syncwarp();
+            if (valid && rank + 1u == (unsigned)__popc(peers)) s_cnt[warp][d] += (unsigned)__popc(peers);   // the last peer moves the running offset
+            __syncwarp();
+        }
+        __threadfence();
+        cluster.sync();    // all keys of the pass are placed, and nobody reads this pass's s_block any more
+        // a -> (b, order) -> (a, idx_a) -> (b, order): the third pass leaves the sorted indices in order_out
+        if (pass == 0) { kin = keys_b; iin = order_out; kout = keys_a; iout = idx_a; }
+        else { kin = keys_a; iin = idx_a; kout = keys_b; iout = order_out; }
+    }
+}
+
+__global__ void k_order_mismatch(const unsigned* __restrict__ a, const unsigned* __restrict__ b, long long n, unsigned* count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicAdd(count, 1u);
+}
+
+// scratch needs 3 * n * 4 bytes (aligned); returns cudaErrorNotSupported when no cluster size is launchable
+static cudaError_t sweep_order_cluster(const double* d_raw, long long n, unsigned* d_order, void* scratch, cudaStream_t stream) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    char* p = static_cast<char*>(scratch);
+    unsigned* ka = reinterpret_cast<unsigned*>(p); p += al(n * 4);
+    unsigned* kb = reinterpret_cast<unsigned*>(p); p += al(n * 4);
+    unsigned* ia = reinterpret_cast<unsigned*>(p);
+    static int s_cluster = 0;   // 0: not decided yet; -1: unsupported
+    if (s_cluster < 0) return cudaErrorNotSupported;
+    const int sizes[2] = {16, 8};
+    for (int t = 0; t < 2; ++t) {
+        const int cs = s_cluster > 0 ? s_cluster : sizes[t];
+        if (cs > 8 && cudaFuncSetAttribute(k_sweep_order_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(kSortThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_sweep_order_cluster, d_raw, n, 1.0, ka, ia, kb, d_order);
+        if (e == cudaSuccess) { s_cluster = cs; return cudaSuccess; }
+        cudaGetLastError();
+        if (s_cluster > 0) break;
+    }
+    s_cluster = -1;
+    return cudaErrorNotSupported;
+}
+
+static int g_order_impl = -1;   // -1: cluster kernel, to be verified against CUB at first use; 1: cluster kernel (verified); 0: CUB
+void sweep_order_set_impl(int v) { g_order_impl = v ? -1 : 0; }
+int sweep_order_impl() { return g_order_impl; }
+
 cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
                                 size_t* needed, cudaStream_t stream) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, 24, stream);
-    const size_t need = al(n * 4) * 3 + al(tmp);
+    const size_t need = al(n * 4) * 4 + al(tmp) + 256;
     if (needed) *needed = need;
     if (!scratch || scratch_bytes < need) return cudaSuccess;
+    if (g_order_impl != 0 && n < (1ll << 31)) {
+        if (g_order_impl == 1) {
+            if (sweep_order_cluster(d_raw, n, d_order, scratch, stream) == cudaSuccess) return cudaSuccess;
+            g_order_impl = 0;
+        } else {
+            // first use: run both, compare on the device, keep the cluster kernel only if the orders are identical
+            char* q = static_cast<char*>(scratch) + al(n * 4) * 3 + al(tmp);
+            unsigned* ref = reinterpret_cast<unsigned*>(q);                      // the 4th n-word array
+            unsigned* cnt = reinterpret_cast<unsigned*>(q + al(n * 4));
+            g_order_impl = 0;
+            cudaError_t e = sweep_compute_order(d_raw, n, ref, scratch, scratch_bytes, nullptr, stream);   // CUB (first 3 arrays + its temp) into `ref`
+            if (e != cudaSuccess) return e;
+            unsigned mism = 1u;
+            if (sweep_order_cluster(d_raw, n, d_order, scratch, stream) == cudaSuccess) {
+                cudaMemsetAsync(cnt, 0, 4, stream);
+                k_order_mismatch<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_order, ref, n, cnt);
+                if (cudaMemcpyAsync(&mism, cnt, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaGetLastError(); mism = 1u; }
+            }
+            if (mism == 0u) { g_order_impl = 1; return cudaSuccess; }
+            return cudaMemcpyAsync(d_order, ref, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);   // keep CUB's order, and CUB from now on
+        }
+    }
     char* p = static_cast<char*>(scratch);
     unsigned* ka = reinterpret_cast<unsigned*>(p); p += al(n * 4);
     unsigned* kb = reinterpret_cast<unsigned*>(p); p += al(n * 4);

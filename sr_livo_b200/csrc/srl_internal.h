@@ -286,6 +286,8 @@ void k1_fast_set_lanes_per_keypoint(int v);
 int k1_fast_lanes_per_keypoint();
 cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
                                 size_t* needed, cudaStream_t stream);
+void sweep_order_set_impl(int v);   // 1: the single-launch cluster sort (verified against the CUB order at first use), 0: CUB
+int sweep_order_impl();             // -1 cluster kernel not verified yet, 1 verified and in use, 0 CUB
 
 size_t k1_smem_bytes(int K);
 int k1_max_blocks_per_sm(int K, int nb);
