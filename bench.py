@@ -414,7 +414,7 @@ def main():
     step_cycles = L.ctx.counter("iekf_step_cycles_avg")
     loop_on_device = bool(L.ctx.counter("device_loop_active"))
     order_impl = {1: "single-launch cluster radix sort (k_sweep_order_cluster), verified against the CUB order at first use",
-                  0: "CUB radix sort", -1: "not used yet"}.get(L.ctx.counter("cluster_order_active"), "?")
+                  0: "CUB radix sort", -1: "cluster radix sort, still in its first verified uses"}.get(L.ctx.counter("cluster_order_active"), "?")
     stage_cycles = [L.ctx.counter(f"iekf_stage_{i}") for i in range(8)]
     ms_e2e, _, _, _ = timed(step_e2e, False)
     # roofline leg: the same resident steps again with CUDA events around every pass's launches on the launching stream

@@ -326,7 +326,7 @@ int srl_ctx_create(int device, void* cuda_stream, srl_ctx** out) {
     std::memset(ctx->h_iekf, 0, sizeof(IekfHostOut));
     if (const char* e = getenv("SRL_DEVICE_LOOP")) ctx->device_loop = atoi(e) != 0;
     if (const char* e = getenv("SRL_PDL")) ctx->pdl = atoi(e) != 0;
-    if (const char* e = getenv("SRL_CLUSTER_ORDER")) sweep_order_set_impl(atoi(e) != 0 ? 1 : 0);
+    if (const char* e = getenv("SRL_CLUSTER_ORDER")) sweep_order_set_impl(atoi(e));
     if (const char* e = getenv("SRL_MAPPED_RESULT")) ctx->mapped_result = atoi(e) != 0;   // A/B switch (bench runs)
     if (const char* e = getenv("SRL_EXCHANGE_IN_FIT")) ctx->exchange_in_fit = atoi(e) != 0;
     *out = ctx;
@@ -371,7 +371,7 @@ int srl_ctx_set_option(srl_ctx* ctx, const char* name, int64_t value) {
     if (n == "device_loop") { ctx->device_loop = value != 0; return SRL_OK; }
     if (n == "eager_order") { ctx->eager_order = value != 0; return SRL_OK; }
     if (n == "pdl") { ctx->pdl = value != 0; return SRL_OK; }
-    if (n == "cluster_order") { sweep_order_set_impl(value != 0 ? 1 : 0); return SRL_OK; }   // process-wide
+    if (n == "cluster_order") { sweep_order_set_impl((int)value); return SRL_OK; }   // process-wide
     if (n == "exchange_in_fit") { ctx->exchange_in_fit = value != 0; return SRL_OK; }
     if (n == "split_lanes_per_keypoint") {
         if (value != 2 && value != 4) return set_err(ctx, SRL_BAD_ARG, "split_lanes_per_keypoint must be 2 or 4");

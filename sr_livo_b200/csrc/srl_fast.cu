@@ -1074,17 +1074,173 @@ __global__ void k_sweep_keys(const double* __restrict__ raw, long long n, double
 }
 
 // ---- the same order in ONE launch: a thread-block cluster sorts the sweep's keys with a stable LSD radix sort (3 passes of
-// 8 bits over the 24-bit Morton keys).  The CUB path above is six launch-latency-bound kernels (~30 us for 100k keys);
-// here the CTAs of one cluster (8 portable, 16 where the device allows it) own consecutive chunks of the sequence, every
-// warp a consecutive sub-chunk; per pass: warp-private digit counts in shared memory -> CTA totals, which the other CTAs
-// read through distributed shared memory -> every CTA derives the global position of its first key of every digit ->
-// the warps scatter their keys in order (rank inside a round of 32 consecutive keys by __match_any_sync) -> cluster
-// barrier.  A stable sort has exactly one result, so the order is identical to the CUB one (checked once per ctx at first use).
+// 8 bits over the 24-bit Morton keys).  The CUB path above is six launch-latency-bound kernels (~45 us of GPU time for
+// 100k keys plus the gaps between them); here the CTAs of one cluster (16 where the device allows it, else the portable 8)
+// own consecutive chunks of the sequence, every warp a consecutive sub-chunk of at most 8 x 32 keys that it keeps in
+// REGISTERS for the whole pass.  Per pass: load (pass 0 derives the keys from the raw points, so no key array is written
+// first) -> warp-private digit counts in shared memory, remembering each key's rank among the warp's keys of that digit ->
+// a shuffle scan over the 32 warps per digit -> CTA totals, which the other CTAs read through distributed shared memory ->
+// every CTA derives the global position of its first key of every digit -> scatter straight from the registers -> cluster
+// barrier (release/acquire at cluster scope orders the global stores; the next pass reads them with ld.global.cg).
+// A stable sort has exactly one result, so the order is identical to the CUB one (checked once per process at first use).
 namespace cg = cooperative_groups;
-constexpr int kSortThreads = 1024, kSortWarps = kSortThreads / 32;
+constexpr int kSortThreads = 1024, kSortWarps = kSortThreads / 32, kSortRounds = 8;
+constexpr int kSortKeysPerCta = kSortWarps * kSortRounds * 32;   // 8192
 
+template <bool LOCAL_SORT>
 __global__ void __launch_bounds__(kSortThreads, 1)
-k_sweep_order_cluster(const double* __restrict__ raw, long long n, double cell, unsigned* keys_a, unsigned* idx_a, unsigned* keys_b, unsigned* order_out) {
+k_sweep_order_cluster(const double* __restrict__ raw, int n, double cell, unsigned* keys_a, unsigned* idx_a, unsigned* keys_b, unsigned* order_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned cta = cluster.block_rank(), n_cta = cluster.num_blocks();
+    __shared__ unsigned s_cnt[kSortWarps][257];   // per-warp digit counts, then the warp's offset inside the CTA's run of that digit (padded: the scan reads columns)
+    __shared__ unsigned s_block[256];             // this CTA's digit totals (the other CTAs read them through DSMEM)
+    __shared__ unsigned s_part[2][4][256];        // partial sums over a quarter of the CTAs: [all | the CTAs before this one]
+    __shared__ unsigned s_base[256];              // keys with that digit in the CTAs before this one
+    __shared__ unsigned s_scan[256];              // keys with a smaller digit in the whole sequence
+    __shared__ unsigned s_start[256];             // keys with a smaller digit in this CTA
+    extern __shared__ unsigned s_stage[];         // LOCAL_SORT: the CTA's keys [0, 8192) and indices [8192, 16384) in digit order
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_warps = (int)n_cta * kSortWarps;
+    const int per = ((n + n_warps - 1) / n_warps + 31) / 32 * 32;   // keys per warp: consecutive, a multiple of 32, <= 256 (host)
+    const int gw = (int)cta * kSortWarps + warp;
+    const int begin = min(n, gw * per), end = min(n, begin + per);
+    const int cta_n = min(n, ((int)cta + 1) * kSortWarps * per) - min(n, (int)cta * kSortWarps * per);
+    const unsigned lt = (1u << lane) - 1u;
+
+    const unsigned* kin = nullptr;
+    const unsigned* iin = nullptr;
+    unsigned* kout = keys_b;
+    unsigned* iout = order_out;
+    unsigned key[kSortRounds], idx[kSortRounds], lrk[kSortRounds];
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = 8 * pass;
+        for (int d = lane; d < 256; d += 32) s_cnt[warp][d] = 0u;
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {
+            const int j = begin + r * 32 + lane;
+            key[r] = 0u; idx[r] = 0u;
+            if (j < end) {
+                if (pass == 0) {
+                    const double x = raw[3 * (long long)j], y = raw[3 * (long long)j + 1], z = raw[3 * (long long)j + 2];
+                    const double fx = fmin(fmax(floor(cell == 1.0 ? x : x / cell) + 128.0, 0.0), 255.0);
+                    const double fy = fmin(fmax(floor(cell == 1.0 ? y : y / cell) + 128.0, 0.0), 255.0);
+                    const double fz = fmin(fmax(floor(cell == 1.0 ? z : z / cell) + 128.0, 0.0), 255.0);
+                    key[r] = spread8((unsigned)fx) | (spread8((unsigned)fy) << 1) | (spread8((unsigned)fz) << 2);
+                    idx[r] = (unsigned)j;
+                } else {
+                    key[r] = __ldcg(kin + j);
+                    idx[r] = __ldcg(iin + j);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kSortRounds; ++r) {   // every round runs on the full warp: lanes past the end match nobody
+            const bool valid = begin + r * 32 + lane < end;
+            const unsigned d = (key[r] >> shift) & 255u;
+            const unsigned peers = __match_any_sync(FULLM, valid ? d : (256u + (unsigned)lane));
+            const unsigned rank = __popc(peers & lt);
+            const unsigned prior = valid ? s_cnt[warp][d] : 0u;
+            __syncwarp();
+            if (valid && rank == 0u) s_cnt[warp][d] = prior + (unsigned)__popc(peers);
+            __syncwarp();
+            lrk[r] = prior + rank;   // rank among the warp's keys of this digit
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {   // exclusive prefix over the CTA's warps, and the CTA's total: warp w scans digits 8w..8w+7
+            const int dig = warp * 8 + q;
+            const unsigned c = s_cnt[lane][dig];
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULLM, incl, o); if (lane >= o) incl += t; }
+            s_cnt[lane][dig] = incl - c;
+            if (lane == 31) s_block[dig] = incl;
+        }
+        cluster.sync();    // every CTA's s_block is complete (and this CTA's s_cnt offsets are)
+        {
+            const int dig = tid & 255, part = tid >> 8;
+            unsigned tot = 0, before = 0;
+            for (unsigned c = (unsigned)part; c < n_cta; c += 4u) {
+                const unsigned v = *cluster.map_shared_rank(&s_block[dig], c);
+                tot += v;
+                if (c < cta) before += v;
+            }
+            s_part[0][part][dig] = tot;
+            s_part[1][part][dig] = before;
+        }
+        __syncthreads();
+        {   // exclusive scans over the 256 digits of the cluster's totals and of this CTA's: 8 digits per lane, then a warp scan
+            // of the lane sums (every warp computes them -- no shuffle under a branch --, warp 0 stores)
+            unsigned v[8], w[8], sum = 0, sum_l = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dig = lane * 8 + q;
+                v[q] = s_part[0][0][dig] + s_part[0][1][dig] + s_part[0][2][dig] + s_part[0][3][dig];
+                w[q] = s_block[dig];
+                sum += v[q]; sum_l += w[q];
+            }
+            unsigned incl = sum, incl_l = sum_l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(FULLM, incl, o), u = __shfl_up_sync(FULLM, incl_l, o);
+                if (lane >= o) { incl += t; incl_l += u; }
+            }
+            unsigned run = incl - sum, run_l = incl_l - sum_l;
+            if (warp == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { s_scan[lane * 8 + q] = run; run += v[q]; s_start[lane * 8 + q] = run_l; run_l += w[q]; }
+            }
+        }
+        if (tid < 256) s_base[tid] = s_part[1][0][tid] + s_part[1][1][tid] + s_part[1][2][tid] + s_part[1][3][tid];
+        __syncthreads();
+        if (LOCAL_SORT) {
+            // a scattered 4-byte store costs a full L2 transaction, and 16 SMs issue all of them: order the CTA's keys by digit
+            // in shared memory first, then every run of equal digits leaves as consecutive addresses
+#pragma unroll
+            for (int r = 0; r < kSortRounds; ++r) {
+                if (begin + r * 32 + lane < end) {
+                    const unsigned d = (key[r] >> shift) & 255u;
+                    const unsigned li = s_start[d] + s_cnt[warp][d] + lrk[r];
+                    s_stage[li] = key[r];
+                    s_stage[kSortKeysPerCta + li] = idx[r];
+                }
+            }
+            __syncthreads();
+            if (tid < 256) s_base[tid] += s_scan[tid] - s_start[tid];   // global position of local slot i with this digit: s_base[d] + i
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kSortRounds; ++k) {
+                const int i = k * kSortThreads + tid;
+                if (i < cta_n) {
+                    const unsigned ky = s_stage[i];
+                    const unsigned pos = s_base[(ky >> shift) & 255u] + (unsigned)i;
+                    if (pass < 2) kout[pos] = ky;
+                    iout[pos] = s_stage[kSortKeysPerCta + i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kSortRounds; ++r) {
+                if (begin + r * 32 + lane < end) {
+                    const unsigned d = (key[r] >> shift) & 255u;
+                    const unsigned pos = s_scan[d] + s_base[d] + s_cnt[warp][d] + lrk[r];
+                    if (pass < 2) kout[pos] = key[r];
+                    iout[pos] = idx[r];
+                }
+            }
+        }
+        cluster.sync();    // all keys of the pass are placed, and nobody reads this pass's s_block any more
+        // regs -> (b, order) -> (a, idx_a) -> order: the third pass leaves the sorted indices in order_out
+        if (pass == 0) { kin = keys_b; iin = order_out; kout = keys_a; iout = idx_a; }
+        else { kin = keys_a; iin = idx_a; kout = keys_b; iout = order_out; }
+    }
+}
+
+// round-2 first version, kept selectable for the A/B in profiles/ (keys re-read from HBM in the scatter phase)
+__global__ void __launch_bounds__(kSortThreads, 1)
+k_sweep_order_cluster_v1(const double* __restrict__ raw, long long n, double cell, unsigned* keys_a, unsigned* idx_a, unsigned* keys_b, unsigned* order_out) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned cta = cluster.block_rank(), n_cta = cluster.num_blocks();
     __shared__ unsigned s_cnt[kSortWarps][256];   // per-warp digit counts, then the warp's running offset inside the CTA's run of that digit
@@ -1177,26 +1333,44 @@ __global__ void k_order_mismatch(const unsigned* __restrict__ a, const unsigned*
     if (i < n && a[i] != b[i]) atomicAdd(count, 1u);
 }
 
-// scratch needs 3 * n * 4 bytes (aligned); returns cudaErrorNotSupported when no cluster size is launchable
+// scratch needs 3 * n * 4 bytes (aligned); returns cudaErrorNotSupported when no cluster size is launchable or n exceeds
+// what the cluster holds in registers (16 CTAs: 131072 keys, 8 CTAs: 65536) -- the caller then uses CUB
+static int s_cluster = 0;   // 0: not decided yet; -1: unsupported; else the cluster size in use
+static int g_order_variant = 3;   // 3: keys in registers + CTA-local digit order before the stores; 2: registers, direct scatter; 1: first version
+static long long sweep_cluster_capacity() { return s_cluster < 0 ? 0 : (long long)(s_cluster > 0 ? s_cluster : 16) * kSortKeysPerCta; }
 static cudaError_t sweep_order_cluster(const double* d_raw, long long n, unsigned* d_order, void* scratch, cudaStream_t stream) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     char* p = static_cast<char*>(scratch);
     unsigned* ka = reinterpret_cast<unsigned*>(p); p += al(n * 4);
     unsigned* kb = reinterpret_cast<unsigned*>(p); p += al(n * 4);
     unsigned* ia = reinterpret_cast<unsigned*>(p);
-    static int s_cluster = 0;   // 0: not decided yet; -1: unsupported
     if (s_cluster < 0) return cudaErrorNotSupported;
     const int sizes[2] = {16, 8};
     for (int t = 0; t < 2; ++t) {
         const int cs = s_cluster > 0 ? s_cluster : sizes[t];
-        if (cs > 8 && cudaFuncSetAttribute(k_sweep_order_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (n > (long long)cs * kSortKeysPerCta) {
+            if (s_cluster > 0) return cudaErrorNotSupported;   // this sweep is too long; the kernel stays in use for shorter ones
+            continue;
+        }
+        if (s_cluster == 0) {   // first launch: opt in to the 16-CTA cluster and to the staging buffer
+            if (cs > 8 && (cudaFuncSetAttribute(k_sweep_order_cluster<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                           cudaFuncSetAttribute(k_sweep_order_cluster<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                           cudaFuncSetAttribute(k_sweep_order_cluster_v1, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) { cudaGetLastError(); continue; }
+            if (cudaFuncSetAttribute(k_sweep_order_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSortKeysPerCta * (int)sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); break; }
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(kSortThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_sweep_order_cluster, d_raw, n, 1.0, ka, ia, kb, d_order);
+        cudaError_t e;
+        if (g_order_variant == 1) e = cudaLaunchKernelEx(&cfg, k_sweep_order_cluster_v1, d_raw, n, 1.0, ka, ia, kb, d_order);
+        else if (g_order_variant == 2) e = cudaLaunchKernelEx(&cfg, k_sweep_order_cluster<false>, d_raw, (int)n, 1.0, ka, ia, kb, d_order);
+        else {
+            cfg.dynamicSmemBytes = 2 * kSortKeysPerCta * sizeof(unsigned);
+            e = cudaLaunchKernelEx(&cfg, k_sweep_order_cluster<true>, d_raw, (int)n, 1.0, ka, ia, kb, d_order);
+        }
         if (e == cudaSuccess) { s_cluster = cs; return cudaSuccess; }
         cudaGetLastError();
         if (s_cluster > 0) break;
@@ -1205,8 +1379,9 @@ static cudaError_t sweep_order_cluster(const double* d_raw, long long n, unsigne
     return cudaErrorNotSupported;
 }
 
-static int g_order_impl = -1;   // -1: cluster kernel, to be verified against CUB at first use; 1: cluster kernel (verified); 0: CUB
-void sweep_order_set_impl(int v) { g_order_impl = v ? -1 : 0; }
+static int g_order_impl = -1;   // -1: cluster kernel, still being verified against CUB; 1: cluster kernel (verified); 0: CUB
+static int g_order_checks_left = 4;   // the first uses in a process run both sorts and compare the orders on the device
+void sweep_order_set_impl(int v) { g_order_impl = v ? -1 : 0; g_order_checks_left = 4; if (v >= 1 && v <= 3) g_order_variant = v == 1 ? 3 : (v == 2 ? 2 : 1); }   // 1 default kernel, 2/3 the earlier variants
 int sweep_order_impl() { return g_order_impl; }
 
 cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_order, void* scratch, size_t scratch_bytes,
@@ -1217,12 +1392,12 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
     const size_t need = al(n * 4) * 4 + al(tmp) + 256;
     if (needed) *needed = need;
     if (!scratch || scratch_bytes < need) return cudaSuccess;
-    if (g_order_impl != 0 && n < (1ll << 31)) {
+    if (g_order_impl != 0 && n <= sweep_cluster_capacity()) {
         if (g_order_impl == 1) {
             if (sweep_order_cluster(d_raw, n, d_order, scratch, stream) == cudaSuccess) return cudaSuccess;
-            g_order_impl = 0;
+            if (s_cluster < 0) g_order_impl = 0;   // else: only this sweep is too long for the cluster
         } else {
-            // first use: run both, compare on the device, keep the cluster kernel only if the orders are identical
+            // first uses: run both, compare on the device, keep the cluster kernel only if the orders are identical
             char* q = static_cast<char*>(scratch) + al(n * 4) * 3 + al(tmp);
             unsigned* ref = reinterpret_cast<unsigned*>(q);                      // the 4th n-word array
             unsigned* cnt = reinterpret_cast<unsigned*>(q + al(n * 4));
@@ -1235,7 +1410,7 @@ cudaError_t sweep_compute_order(const double* d_raw, long long n, unsigned* d_or
                 k_order_mismatch<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_order, ref, n, cnt);
                 if (cudaMemcpyAsync(&mism, cnt, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaGetLastError(); mism = 1u; }
             }
-            if (mism == 0u) { g_order_impl = 1; return cudaSuccess; }
+            if (mism == 0u) { g_order_impl = --g_order_checks_left > 0 ? -1 : 1; return cudaSuccess; }
             return cudaMemcpyAsync(d_order, ref, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream);   // keep CUB's order, and CUB from now on
         }
     }

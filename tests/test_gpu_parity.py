@@ -142,6 +142,36 @@ def test_pass_matches_oracle(L, small_world, kw):
     _assert_pass_equal(g, o)
 
 
+def test_single_launch_sweep_order_is_the_cub_order(L, small_world):
+    """The thread-block-cluster radix sort (k_sweep_order_cluster) orders a sweep exactly like the CUB sort it replaces: the
+    library runs both for the first uses after the option is set and keeps the cluster kernel only if the orders are
+    identical on the device (counter 1; 0 = it fell back to CUB).  Sizes: a full cluster (131072), the bench sweep, a
+    handful of points, a ragged size; 150000 exceeds what 16 CTAs hold in registers and goes through CUB without
+    retiring the kernel.  The pass sums are summed in sweep order, so they are bit-identical under either sort."""
+    from sr_livo_b200 import lio
+    L = lio.LioOptimization(max_voxels=1 << 18, sweep_capacity=160000)   # the shared fixture stops at 131072 points
+    om, sw = _load_world(L, small_world)
+    rng = np.random.default_rng(11)
+    prm = lio.r3live_params(max_num_residuals=BIG)
+    try:
+        L.ctx.set_option("cluster_order", 1)
+        for n in (131072, 100000, 7, 40001, 150000, 1000):
+            raw = rng.uniform(-140.0, 140.0, size=(n, 3))          # beyond +-128 m: clamped cells
+            raw[: n // 2] = sw.raw_xyz[rng.integers(0, sw.raw_xyz.shape[0], n // 2)]
+            L.setKeypoints(raw)
+            L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+        assert L.ctx.counter("cluster_order_active") == 1
+        out = {}
+        for mode in (1, 0):
+            L.ctx.set_option("cluster_order", mode)
+            L.setKeypoints(sw.raw_xyz)
+            out[mode] = L.buildPlaneResiduals(prm, sw.q_init, sw.t_init, sw.t_last)
+        assert np.array_equal(out[1].HTH, out[0].HTH) and np.array_equal(out[1].HTh, out[0].HTh)
+        assert out[1].num_residuals == out[0].num_residuals
+    finally:
+        L.ctx.set_option("cluster_order", 1)
+
+
 def _close(a, b, rel=1e-12):
     return np.abs(a - b).max() <= rel * np.abs(b).max()
 
