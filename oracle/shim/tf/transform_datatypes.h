@@ -1,0 +1,2 @@
+#pragma once
+#include "srl_shim_ext.h"
