@@ -60,6 +60,8 @@ def lib():
     L.ref_build_plane_residuals.restype = I32
     L.ref_update_iekf.argtypes = [P, P, I64, C.POINTER(EskfState), P, P, P, P, P, C.POINTER(IcpParams), C.POINTER(I32), C.POINTER(I32)]
     L.ref_update_iekf.restype = I32
+    L.ref_update_iekf_many.argtypes = [P, P, I64, I32, P, P, P, P, P, P, C.POINTER(IcpParams), I32]
+    L.ref_update_iekf_many.restype = I32
     L.ref_optimize.argtypes = [P, P, P, I64, D, C.POINTER(EskfState), P, P, P, P, P, C.POINTER(IcpParams), C.POINTER(I32), C.POINTER(I32)]
     L.ref_optimize.restype = I32
     L.ref_eskf_observe.argtypes = [C.POINTER(EskfState), P]
@@ -173,6 +175,19 @@ class Reference:
         rc = lib().ref_update_iekf(self._h, _ptr(raw), raw.shape[0], C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
                                    C.byref(params), C.byref(ok), C.byref(used))
         return dict(threw=rc < 0, success=bool(ok.value), num_residuals_used=used.value, eskf=Eskf.from_c(st), frame_q=fq, frame_t=ft)
+
+    def update_iekf_many(self, raws, eskfs, t_lasts, params: IcpParams, n_threads: int, R_il=None, t_il=None):
+        """`len(raws)` independent sweeps (same keypoint count) against this object's voxel_map on n_threads host threads, each through
+        the reference's single-threaded updateIEKF (ref_update_iekf_many).  Returns (sweeps that succeeded, list of Eskf, frame_q, frame_t)."""
+        raw = np.ascontiguousarray(np.stack([_f64(r).reshape(-1, 3) for r in raws]))
+        ns, n = raw.shape[0], raw.shape[1]
+        st = (EskfState * ns)(*[e.to_c() for e in eskfs])
+        fq = np.ascontiguousarray(np.stack([_f64(e.q) for e in eskfs])); ft = np.ascontiguousarray(np.stack([_f64(e.p) for e in eskfs]))
+        tl = np.ascontiguousarray(np.stack([_f64(t) for t in t_lasts]))
+        R, ti = _ext(R_il, t_il)
+        ok = lib().ref_update_iekf_many(self._h, _ptr(raw), n, ns, C.cast(st, C.c_void_p), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
+                                        C.byref(params), int(n_threads))
+        return int(ok), [Eskf.from_c(s) for s in st], fq, ft
 
     def optimize(self, frame_world, frame_raw, sample_voxel_size, eskf: Eskf, t_last, params: IcpParams, frame_q=None, frame_t=None,
                  R_il=None, t_il=None):

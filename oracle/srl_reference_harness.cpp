@@ -51,11 +51,13 @@ namespace {
 
 struct RefCtx {
     lioOptimization* lio = nullptr;
+    std::vector<RefCtx*> workers;        // owned: one lioOptimization per host thread for ref_update_iekf_many
     std::vector<state*> states;          // owned
     std::vector<cloudFrame*> frames;     // owned
     ~RefCtx() {
         for (cloudFrame* f : frames) delete f;
         for (state* s : states) delete s;
+        for (RefCtx* w : workers) delete w;
         // lioOptimization has no destructor for its helpers; leak-free enough for a test process
         delete lio;
     }
@@ -369,6 +371,49 @@ int32_t ref_optimize(void* ctx, double* frame_world, const double* frame_raw, in
     put3(frame_t, frame->p_state->translation);
     for (int64_t i = 0; i < n; ++i) put3(frame_world + 3 * i, frame->point_frame[(size_t)i].point);
     return 0;
+}
+
+// Throughput form for the CPU arm of bench.py: `n_sweeps` independent sweeps (n keypoints each, their own prior state and
+// pose) registered against THIS context's voxel_map by `n_threads` host threads, each thread driving its own
+// lioOptimization object through the reference's single-threaded updateIEKF (the map is passed by reference and only read:
+// tsl::robin_map::find).  The reference has no threading of its own on this path; independent sweeps are the one way it
+// can use more than one core.  Returns the number of sweeps whose update succeeded.
+int32_t ref_update_iekf_many(void* ctx, const double* raw_xyz, int64_t n, int32_t n_sweeps, orc_eskf_state* eskf, double* frame_q,
+                             double* frame_t, const double* t_last, const double R_il[9], const double t_il[3], const orc_icp_params* prm,
+                             int32_t n_threads) {
+    RefCtx* c = static_cast<RefCtx*>(ctx);
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_sweeps) n_threads = n_sweeps;
+    while ((int)c->workers.size() < n_threads) { RefCtx* w = new RefCtx(); w->lio = new lioOptimization(); c->workers.push_back(w); }
+    std::atomic<int> next(0), ok(0);
+    auto run = [&](int tid) {
+        RefCtx* w = c->workers[(size_t)tid];
+        set_extrinsics(w, R_il, t_il);
+        w->lio->laser_point_cov = prm->laser_point_cov;
+        const icpOptions opt = make_options(prm);
+        for (;;) {
+            const int s = next.fetch_add(1);
+            if (s >= n_sweeps) break;
+            eskf_from_c(w->lio->eskf_pro, eskf + s);
+            std::vector<point3D> keypoints((size_t)n);
+            const double* raw = raw_xyz + (size_t)s * n * 3;
+            for (int64_t i = 0; i < n; ++i) keypoints[(size_t)i].raw_point = v3(raw + 3 * i);
+            std::vector<point3D> none;
+            cloudFrame* frame = make_frames(w, frame_q + 4 * s, frame_t + 3 * s, t_last + 3 * s, prm->frame_id, none);
+            try {
+                optimizeSummary summary = w->lio->updateIEKF(opt, c->lio->voxel_map, keypoints, frame);
+                if (summary.success) ok.fetch_add(1);
+            } catch (const std::runtime_error&) {}
+            eskf_to_c(w->lio->eskf_pro, eskf + s);
+            putq(frame_q + 4 * s, frame->p_state->rotation);
+            put3(frame_t + 3 * s, frame->p_state->translation);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(run, t);
+    run(0);
+    for (auto& t : th) t.join();
+    return ok.load();
 }
 
 void ref_eskf_observe(orc_eskf_state* s, const double dx[17]) {   // eskfEstimator::observe (src/eskfEstimator.cpp:219-230)

@@ -229,19 +229,26 @@ int main() {
         assert r.returncode == 3 and "no CPU fallback" in r.stdout
 
 
-def test_bench_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference runs the CPU oracle only (no GPU) and prints one JSON line with the contract's keys."""
+@pytest.mark.parametrize("arm", ["reference", "port"])
+def test_bench_reference_arm_prints_the_contract_line(arm):
+    """bench.py --impl reference runs on the CPU only (no GPU) and prints one JSON line with the contract's keys: the reference's
+    own sources compiled where they lie (oracle/_ref/libsrl_reference.so) when that library exists, else / on request the oracle port."""
     import json
+    from oracle import reference_py as Rf
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--points", "3000", "--map-extent", "80"], capture_output=True, text=True, timeout=600)
+                        "--points", "3000", "--map-extent", "80"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SRL_CPU_ARM=arm))
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    want = "reference" if (arm == "reference" and Rf.available()) else "port"
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == want and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and line["value"] > 0
     assert "workload" in line["config"]
+    if want == "reference":
+        assert line["cpu_baseline"]["pose_equals_port"] is True
 
 
 def test_c_shard_range_matches_the_python_one():

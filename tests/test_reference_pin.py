@@ -1,0 +1,409 @@
+"""Pins the oracle restatement (oracle/srl_oracle.cpp) against the REFERENCE'S OWN CODE.
+
+oracle/_ref/libsrl_reference.so holds /root/reference/src/{optimize,utility,eskfEstimator,cloudMap,state,lioOptimization,
+rgbMapTracker,parameters}.cpp compiled unmodified from where they lie (oracle/Makefile target `reference`), over the stand-in
+headers of oracle/shim/ — Eigen, OpenCV, ROS and PCL are not in this image.  So the left-hand side of every comparison below
+is produced by the reference's own control flow, containers (tsl::robin_map, std::tr1::unordered_map, std::priority_queue),
+member functions, casts and quirks; the right-hand side by the oracle, which the GPU parity tests use as their checker.
+
+What stays unpinned: the arithmetic INSIDE Eigen / OpenCV calls (reduction order of small dot products, SelfAdjointEigenSolver,
+PartialPivLU, saturating Vec3b operators) — oracle/shim restates it with the same evaluation orders the oracle assumes, so
+equality here says nothing about those.  Everything else that a restatement can get wrong is checked.
+
+CPU only; skipped when the library was not built (no /root/reference on the box and no prebuilt copy).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from oracle import reference_py as Rf
+from sr_livo_b200 import synth
+
+pytestmark = pytest.mark.skipif(not Rf.available(), reason="oracle/_ref/libsrl_reference.so not built (needs /root/reference)")
+
+BIG = 2 ** 31 - 1
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def sm():
+    return np.load(os.path.join(HERE, "golden", "scan_matching.npz"))
+
+
+@pytest.fixture(scope="module")
+def sp():
+    return np.load(os.path.join(HERE, "golden", "sweep_prep.npz"))
+
+
+def _pair(sm):
+    ref = Rf.Reference(); ref.load(sm["map_keys"], sm["map_counts"], sm["map_xyz"])
+    om = O.OracleMap(); om.load(sm["map_keys"], sm["map_counts"], sm["map_xyz"])
+    return ref, om
+
+
+def _tsl():
+    return "tsl" in O.backend()
+
+
+def _as_dict(keys, counts, xyz):
+    return {tuple(k): x[:c].copy() for k, c, x in zip(keys.tolist(), counts.tolist(), xyz)}
+
+
+# ---- the reference object itself ----------------------------------------------------------------------------------
+def test_reference_constructor_and_hash():
+    ref = Rf.Reference()
+    assert Rf.lib().ref_laser_point_cov(ref._h) == 0.001                     # src/lioOptimization.cpp:364, what orc_icp_params carries
+    rng = np.random.default_rng(0)
+    for x, y, z in [(-1, 2, 3), (0, 0, 0), (-32767, 32767, -1)] + rng.integers(-32767, 32767, (200, 3)).tolist():
+        assert Rf.voxel_hash(x, y, z) == O.voxel_hash(x, y, z)              # std::hash<voxel>, include/cloudMap.h:173-184
+
+
+# ---- A7 addPointsToMap / addPointToMap, N4 removePointsFarFromLocation -------------------------------------------
+@pytest.mark.parametrize("case", [dict(voxel_size=1.0, cap=20, min_dist=0.15, min_num=0), dict(voxel_size=0.5, cap=8, min_dist=0.05, min_num=0),
+                                  dict(voxel_size=1.0, cap=20, min_dist=0.0, min_num=0)])
+def test_add_points_to_map_equals_the_oracle(case):
+    rng = np.random.default_rng(11)
+    ref = Rf.Reference(); om = O.OracleMap()
+    for sweep in range(4):
+        pts = np.concatenate([rng.uniform(-6, 6, (6000, 3)), rng.normal(0, 0.3, (3000, 3)) + [2.2, -1.7, 0.4],
+                              np.array([[0.99999999999, 0.1, 0.1], [-0.5, -0.5, -0.5], [0.5, 0.5, 0.5]])])
+        a = ref.add_points_to_map(pts, case["voxel_size"], case["cap"], case["min_dist"], case["min_num"])
+        b = om.add_points(pts, case["voxel_size"], case["cap"], case["min_dist"], case["min_num"])
+        assert a == b
+    s = ref.snapshot(cap=case["cap"]); k, c, x = om.snapshot(cap=case["cap"])
+    assert ref.num_points() == om.num_points and ref.num_voxels() == om.num_voxels
+    da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(k, c, x)
+    assert da.keys() == db.keys()
+    assert all(np.array_equal(da[key], db[key]) for key in da)              # contents AND order inside every voxel
+    if _tsl():                                                               # same container, same insertions: same iteration order
+        assert np.array_equal(s["keys"], k) and np.array_equal(s["xyz"], x)
+    # min_num_points > 0: only voxels that already hold enough points accept more, unknown voxels are not created (:431,:439)
+    more = rng.uniform(-7, 7, (5000, 3))
+    assert ref.add_points_to_map(more, case["voxel_size"], case["cap"], case["min_dist"], 3) == om.add_points(more, case["voxel_size"], case["cap"], case["min_dist"], 3)
+    s = ref.snapshot(cap=case["cap"]); k, c, x = om.snapshot(cap=case["cap"])
+    da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(k, c, x)
+    assert da.keys() == db.keys() and all(np.array_equal(da[key], db[key]) for key in da)
+    # removePointsFarFromLocation (src/lioOptimization.cpp:556-572)
+    loc = np.array([1.0, -0.5, 0.2])
+    assert ref.remove_far(loc, 4.0) == om.remove_far(loc, 4.0)
+    s = ref.snapshot(cap=case["cap"]); k, c, x = om.snapshot(cap=case["cap"])
+    da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(k, c, x)
+    assert da.keys() == db.keys() and all(np.array_equal(da[key], db[key]) for key in da)
+
+
+# ---- A3 searchNeighbors ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nb,thr", [(1, 1), (2, 1), (1, 3)])
+def test_search_neighbors_equals_the_oracle(sm, nb, thr):
+    ref, om = _pair(sm)
+    blocks = _as_dict(sm["map_keys"], sm["map_counts"], sm["map_xyz"])
+    prm = O.r3live_params(max_num_residuals=BIG, frame_id=100 if nb == 1 else 5, threshold_voxel_occupancy=thr)
+    o = om.build_plane_residuals(sm["raw_xyz"], sm["q_init"], sm["t_init"], sm["t_last"], prm, debug=True)
+    assert o.num_fragile == 0
+    idx = np.flatnonzero(o.status >= 0)[::7]
+    n_full = 0
+    for k in idx:
+        xyz, vox = ref.search_neighbors(o.world_xyz[k], nb=nb, size=1.0, K=20, thr=1 if nb == 2 else thr)
+        if o.status[k] == 0:
+            assert xyz.shape[0] < 20                                          # :78: fewer than min_number_neighbors, keypoint skipped
+            continue
+        n_full += 1
+        assert xyz.shape[0] == 20
+        want = np.array([blocks[tuple(v[:3])][v[3]] for v in o.nbr[k].tolist()], np.float64)
+        assert np.array_equal(xyz, want)                                      # same 20 map points, nearest first
+        assert np.array_equal(vox, o.nbr[k][:, :3])
+        d = np.sqrt(((xyz - o.world_xyz[k]) ** 2)[:, 0] + (((xyz - o.world_xyz[k]) ** 2)[:, 1] + ((xyz - o.world_xyz[k]) ** 2)[:, 2]))
+        assert np.array_equal(d, o.nbr_dist[k])
+    assert n_full > 50
+
+
+# ---- A2 / A4 buildPlaneResiduals + computeNeighborhoodDistribution ------------------------------------------------
+PASS_CASES = {
+    "nb1": dict(max_num_residuals=BIG, frame_id=100),
+    "nb2_init_frames": dict(max_num_residuals=BIG, frame_id=5),
+    "cap100": dict(max_num_residuals=100, frame_id=100),
+    "cap600_yaml": dict(max_num_residuals=600, frame_id=100),
+    "cap_default_minus1": dict(max_num_residuals=-1, frame_id=100),
+    "occupancy3": dict(max_num_residuals=BIG, frame_id=100, threshold_voxel_occupancy=3),
+    "gate_tight": dict(max_num_residuals=BIG, frame_id=100, max_dist_to_plane_icp=0.05),
+    "weights": dict(max_num_residuals=BIG, frame_id=100, weight_alpha=-0.7, weight_neighborhood=0.4, power_planarity=1.0),
+    "too_few": dict(max_num_residuals=BIG, frame_id=100, min_number_neighbors=20, max_dist_to_plane_icp=-1.0),
+}
+
+
+@pytest.mark.parametrize("tag", list(PASS_CASES))
+@pytest.mark.parametrize("ext", [False, True])
+def test_build_plane_residuals_equals_the_oracle(sm, tag, ext):
+    ref, om = _pair(sm)
+    prm = O.r3live_params(**PASS_CASES[tag])
+    R_il = synth.quat_to_rot(synth.quat_from_rotvec([0.02, -0.01, 0.03])) if ext else None
+    t_il = np.array([0.05, -0.02, 0.1]) if ext else None
+    raw = sm["raw_xyz"] if not ext else (sm["raw_xyz"] - t_il) @ R_il     # same body-frame points through a non-trivial extrinsic
+    r = ref.build_plane_residuals(raw, sm["q_init"], sm["t_init"], sm["t_last"], prm, R_il, t_il)
+    o = om.build_plane_residuals(raw, sm["q_init"], sm["t_init"], sm["t_last"], prm, R_il, t_il, debug=True)
+    assert not r["threw"] and not o.nan_planarity
+    assert r["success"] == o.success and r["num_residuals_used"] == o.num_residuals
+    visited = o.status >= 0
+    assert np.array_equal(r["world_xyz"][visited], o.world_xyz[visited])     # transformKeypoints (:31-42), bit for bit
+    rows = o.plane[o.status == 2][:, :15]                                     # accepted keypoints in keypoint order = plane_residuals
+    assert r["rows"].shape == rows.shape
+    assert np.array_equal(r["rows"], rows)                                    # raw_point, normal, Jacobian, offset, distance, weight: bit for bit
+    assert r["loss_sum"] == o.loss_sum
+    # the normal equations the oracle hands to the GPU tests are those rows' products (src/optimize.cpp:160-170,235,239)
+    if rows.shape[0]:
+        J = rows[:, 6:12]; h = rows[:, 13] * rows[:, 14]
+        assert np.allclose(J.T @ J, o.HTH, rtol=1e-12, atol=1e-18) and np.allclose(J.T @ h, o.HTh, rtol=1e-11, atol=1e-18)
+
+
+def test_neighborhood_distribution_on_random_and_degenerate_sets(sm):
+    ref, om = _pair(sm)
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        kind = trial % 4
+        pts = rng.normal(0, 1, (20, 3)) * ([1, 1, 0.01] if kind == 0 else [1, 0.02, 0.02] if kind == 1 else [1, 1, 1] if kind == 2 else [1, 1, 1e-7])
+        pts = pts @ synth.quat_to_rot(synth.quat_from_rotvec(rng.normal(0, 1, 3))).T + rng.uniform(-50, 50, 3)
+        rc, nh = ref.neighborhood(pts)
+        assert rc == 0
+        # against the oracle's eigen restatement (same covariance accumulation order as src/optimize.cpp:327-335)
+        bary = np.zeros(3)
+        for p in pts:
+            bary = bary + p
+        bary = bary / 20.0
+        cov = np.zeros((3, 3))
+        for p in pts:
+            for k in range(3):
+                for l in range(k, 3):
+                    cov[k, l] += (p[k] - bary[k]) * (p[l] - bary[l])
+        cov[1, 0], cov[2, 0], cov[2, 1] = cov[0, 1], cov[0, 2], cov[1, 2]
+        assert np.array_equal(nh["center"], bary) and np.array_equal(nh["covariance"], cov)
+        ev, evec = O.eig3_sym(cov)
+        n = evec[:, 0]
+        nn = n[0] * n[0] + (n[1] * n[1] + n[2] * n[2])
+        n = n / np.sqrt(nn) if nn > 0 else n
+        assert np.array_equal(nh["normal"], n)
+        s1, s2, s3 = np.sqrt(abs(ev[2])), np.sqrt(abs(ev[1])), np.sqrt(abs(ev[0]))
+        assert nh["a2D"] == (s2 - s3) / s1
+    # all points identical: 0 / 0 -> NaN planarity -> the reference throws (:348-350)
+    rc, _ = ref.neighborhood(np.tile([[1.0, 2.0, 3.0]], (20, 1)))
+    assert rc == 1
+
+
+def test_nan_planarity_throws_in_both(sm):
+    # a map whose voxels hold 20 copies of one point each: every neighbourhood is degenerate
+    keys = np.array([[0, 0, 0], [1, 0, 0]], np.int16); counts = np.array([20, 20], np.int32)
+    xyz = np.zeros((2, 20, 3), np.float32); xyz[0] = [0.5, 0.5, 0.5]; xyz[1] = [1.5, 0.5, 0.5]
+    ref = Rf.Reference(); ref.load(keys, counts, xyz)
+    om = O.OracleMap(); om.load(keys, counts, xyz)
+    raw = np.array([[0.6, 0.5, 0.5]])
+    prm = O.r3live_params(max_num_residuals=BIG)
+    q, t = np.array([0, 0, 0, 1.0]), np.zeros(3)
+    assert ref.build_plane_residuals(raw, q, t, t, prm)["threw"]
+    assert om.build_plane_residuals(raw, q, t, t, prm).nan_planarity
+
+
+# ---- A1 / A8 updateIEKF + observe ---------------------------------------------------------------------------------
+IEKF_CASES = {
+    "steady": dict(max_num_residuals=BIG),
+    "cap600_yaml": dict(max_num_residuals=600),
+    "init_frame_15_iterations": dict(max_num_residuals=BIG, frame_id=5),
+    "frame_1_never_converges_early": dict(max_num_residuals=BIG, frame_id=1, init_num_frames=0),
+    "loose_thresholds_early_exit": dict(max_num_residuals=BIG, threshold_orientation_norm=5.0, threshold_translation_norm=0.5),
+    "one_iteration": dict(max_num_residuals=BIG, num_iters_icp=1),
+    "too_few_residuals": dict(max_num_residuals=BIG, max_dist_to_plane_icp=-1.0),
+}
+
+
+def _assert_eskf_equal(a: O.Eskf, b: O.Eskf, rtol, atol):
+    for name in ("p", "q", "v", "ba", "bg", "g"):
+        assert np.allclose(getattr(a, name), getattr(b, name), rtol=rtol, atol=atol), name
+    # (P / c)^-1 is ill-conditioned (c = 0.001, prior entries 1e-5 .. 1): small entries move in their 7th digit between two
+    # LU loop orders; measured against the matrix's scale the two covariances agree to 1e-11
+    assert np.allclose(a.cov, b.cov, rtol=1e-6, atol=1e-11 * np.abs(b.cov).max())
+
+
+@pytest.mark.parametrize("tag", list(IEKF_CASES))
+def test_update_iekf_equals_the_oracle(sm, tag):
+    ref, om = _pair(sm)
+    prm = O.r3live_params(**IEKF_CASES[tag])
+    rng = np.random.default_rng(3)
+    e0 = O.Eskf(p=sm["t_init"].copy(), q=sm["q_init"].copy(), v=rng.normal(0, 0.3, 3), ba=rng.normal(0, 0.01, 3), bg=rng.normal(0, 0.001, 3),
+                g=np.array([0.03, -0.02, 9.8]), cov=sm["prior_cov"].copy())
+    R_il = synth.quat_to_rot(synth.quat_from_rotvec([0.01, 0.02, -0.015])); t_il = np.array([0.04, 0.0, -0.03])
+    raw = (sm["raw_xyz"] - t_il) @ R_il
+    r = ref.update_iekf(raw, e0, sm["t_last"], prm, R_il=R_il, t_il=t_il)
+    o = om.update_iekf(raw, e0, sm["t_last"], prm, R_il=R_il, t_il=t_il)
+    assert not r["threw"]
+    assert r["success"] == o["success"] and r["num_residuals_used"] == o["num_residuals_used"]
+    # the associations are identical pass by pass (previous test), so the two states can only differ by the rounding of the
+    # 17-dimensional algebra (Eigen's GEMM / LU loop orders are restated, not pinned): 1e-9
+    _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(r["frame_q"], o["frame_q"], rtol=1e-9, atol=1e-12) and np.allclose(r["frame_t"], o["frame_t"], rtol=1e-9, atol=1e-11)
+    if tag == "too_few_residuals":
+        assert not r["success"]
+        assert np.array_equal(r["eskf"].p, e0.p) and np.array_equal(r["eskf"].cov, e0.cov)   # early return (:155) leaves the filter untouched
+    else:
+        assert r["success"] and np.linalg.norm(r["eskf"].p - sm["t_true"]) < np.linalg.norm(e0.p - sm["t_true"])
+
+
+def test_eskf_observe_equals_the_oracle():
+    rng = np.random.default_rng(9)
+    for trial in range(100):
+        q = rng.normal(0, 1, 4); q /= np.linalg.norm(q)
+        e = O.Eskf(p=rng.normal(0, 5, 3), q=q, v=rng.normal(0, 1, 3), ba=rng.normal(0, 0.1, 3), bg=rng.normal(0, 0.01, 3),
+                   g=np.array([0, 0, 9.81]) + rng.normal(0, 0.2, 3))
+        dx = rng.normal(0, 1, 17) * (1e-6 if trial % 3 == 0 else 1e-2 if trial % 3 == 1 else 0.5)   # both branches of so3ToQuat / so3ToRotation
+        a, b = Rf.eskf_observe(e, dx), e.observe(dx)
+        for name in ("p", "q", "v", "ba", "bg", "g"):
+            assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-14, atol=1e-15), name
+
+
+# ---- the caller: optimize() = gridSampling -> updateIEKF -> transformPoint (src/optimize.cpp:428-447) -------------
+def test_optimize_equals_the_composition_of_oracle_pieces(sm):
+    ref, om = _pair(sm)
+    prm = O.r3live_params(max_num_residuals=600)
+    raw = sm["raw_xyz"]
+    R0 = synth.quat_to_rot(sm["q_init"])
+    world0 = raw @ R0.T + sm["t_init"]                      # point_frame[i].point as the caller left it (pose prediction)
+    e0 = O.Eskf(p=sm["t_init"].copy(), q=sm["q_init"].copy(), cov=sm["prior_cov"].copy())
+    size = 1.5
+    r = ref.optimize(world0, raw, size, e0, sm["t_last"], prm)
+    idx = O.grid_sampling(world0, size)
+    assert np.array_equal(idx, Rf.grid_sampling(world0, size))
+    o = om.update_iekf(raw[idx], e0, sm["t_last"], prm)
+    assert r["success"] == o["success"] and r["num_residuals_used"] == o["num_residuals_used"]
+    _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
+    want = Rf.transform_point(raw, o["frame_q"], o["frame_t"])
+    assert np.allclose(r["world"], want, rtol=0, atol=1e-8)
+
+
+# ---- N2 gridSampling: the iteration order of std::tr1::unordered_map ------------------------------------------------
+@pytest.mark.parametrize("n,size,spread", [(5000, 1.5, 40.0), (20000, 0.8, 60.0), (300, 1.0, 3.0), (1, 1.0, 1.0)])
+def test_grid_sampling_order_equals_the_oracle(n, size, spread):
+    rng = np.random.default_rng(n)
+    xyz = rng.uniform(-spread, spread, (n, 3))
+    xyz[: n // 10] = xyz[n // 10: 2 * (n // 10)][: n // 10] + 1e-3            # several points per cell: the first one wins
+    a, b = Rf.grid_sampling(xyz, size), O.grid_sampling(xyz, size)
+    assert np.array_equal(a, b)
+
+
+# ---- N3 undistortion / per-point transforms --------------------------------------------------------------------------
+def _states(sp):
+    return [dict(timestamp=r[0], quat=r[1:5], trans=r[5:8], vel=r[8:11], un_acc=r[11:14], un_gyr=r[14:17]) for r in sp["imu_states"]]
+
+
+def test_point_transforms_equal_the_oracle(sp):
+    states = _states(sp)
+    raw, rel, t0 = sp["raw"], sp["rel"], float(sp["t0"])
+    R_il, t_il = sp["R_il"], sp["t_il"]
+    a = Rf.distort_frame_by_constant(raw, rel, states, t0, R_il, t_il)
+    b = O.distort_frame_by_constant(raw, rel, states, t0, R_il, t_il)
+    assert np.array_equal(a, b)
+    seed_in = np.full_like(raw, -7.0)                                       # points the iterator never reaches keep their value
+    a = Rf.distort_frame_by_imu(raw, rel, states, t0, R_il, t_il, seed_in)
+    b, m = O.distort_frame_by_imu(raw, rel, states, t0, R_il, t_il, seed_in)
+    assert np.array_equal(a, b) and 0 < m <= raw.shape[0]
+    # a point outside every IMU interval stops the one-iterator walk for good (src/utility.cpp:263-308)
+    rel2 = rel.copy(); rel2[rel.shape[0] // 3] = 1e6
+    a = Rf.distort_frame_by_imu(raw, rel2, states, t0, R_il, t_il, seed_in)
+    b, m2 = O.distort_frame_by_imu(raw, rel2, states, t0, R_il, t_il, seed_in)
+    assert np.array_equal(a, b) and m2 == rel.shape[0] // 3
+    a = Rf.transform_all_imu_point(b, states[-1], R_il, t_il)
+    c = O.transform_all_imu_point(b, states[-1], R_il, t_il)
+    assert np.array_equal(a, c)
+
+
+# ---- N4 colour map + renderer -------------------------------------------------------------------------------------------
+def test_color_map_and_renderer_equal_the_oracle():
+    rng = np.random.default_rng(21)
+    ref = Rf.Reference()
+    oc = O.OracleColorMap(voxel_size=0.5, max_num_points_in_voxel=8, min_distance_points=0.05)
+    om = O.OracleMap()
+    rows, cols = 96, 128
+    fx = fy = 90.0; cx, cy = cols / 2.0, rows / 2.0
+    for sweep in range(3):
+        pts = np.concatenate([rng.uniform(-2.5, 2.5, (2500, 2)), rng.uniform(3.0, 6.0, (2500, 1))], axis=1)   # in front of the camera
+        t_end, t_proc = 10.0 + sweep, 10.0 + sweep - (0.0 if sweep == 1 else 0.5)       # sweep 1: |dt| < 1e-5 -> no voxel becomes recent
+        a = ref.add_points_to_map(pts, 1.0, 20, 0.15, 0, color_voxel_size=0.5, color_max_points=8, color_min_distance=0.05, add_point_step=3,
+                                  time_sweep_end=t_end, time_last_process=t_proc, to_rendering=True)
+        assert a == om.add_points(pts, 1.0, 20, 0.15, 0)
+        oc.add_points(pts, add_point_step=3, time_sweep_end=t_end, time_last_process=t_proc, to_rendering=True)
+        ca, cb = ref.color_counts(), oc.counts()
+        assert ca == cb
+        la, lb = ref.color_lists(), oc.lists()
+        assert np.array_equal(la[0], lb[0]) and np.array_equal(la[1], lb[1])  # rgb_points_vec and voxels_recent_visited, in order
+        # render twice (first observation, then the fusion branch of updateRgb)
+        for k in range(2):
+            img = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+            q_cw = synth.quat_from_rotvec(rng.normal(0, 0.02, 3)); t_cw = rng.normal(0, 0.05, 3)
+            R = synth.quat_to_rot(q_cw); t_wc = -R.T @ t_cw
+            cam = np.concatenate([q_cw, t_cw, t_wc, [fx, fy, cx, cy, 0.005]])
+            obs = t_end + 0.01 * (k + 1)
+            assert ref.color_render(cam, img, obs) == oc.render(cam, img, obs)
+        sa = ref.snapshot(which=1, cap=8, color=True); sb = oc.snapshot()
+        da = {tuple(k): i for i, k in enumerate(sa["keys"].tolist())}
+        assert da.keys() == {tuple(k) for k in sb["keys"].tolist()}
+        for j, key in enumerate(sb["keys"].tolist()):
+            i = da[tuple(key)]
+            for f in ("counts", "xyz", "rgb", "n_rgb", "cov", "obs_dist", "last_obs", "last_visited"):
+                assert np.array_equal(sa[f][i], sb[f][j]), (f, key)
+    assert ca["rgb_points"] > 500 and (sa["n_rgb"] > 1).sum() > 100
+
+
+# ---- a different, larger scene: several sweeps and poses, map built by the reference's own addPointsToMap -------------
+def test_randomized_scene_passes_equal_the_oracle():
+    pts = synth.sample_map_points(80.0, 40.0, seed=3)
+    ref = Rf.Reference(); om = O.OracleMap()
+    assert ref.add_points_to_map(pts) == om.add_points(pts)
+    total = 0
+    for i, kw in enumerate([dict(yaw=0.4, position=(0.0, 3.0, 1.8)), dict(yaw=-2.0, position=(6.0, -4.0, 2.2), pattern="spinning"),
+                            dict(yaw=1.3, position=(-9.0, 8.0, 1.5), dp_max=0.3, dth_max_deg=3.0)]):
+        sw = synth.make_sweep(2500, seed=3100 + i, **kw)
+        for frame_id, cap in [(100, BIG), (3, BIG), (100, 600)]:
+            prm = O.r3live_params(max_num_residuals=cap, frame_id=frame_id)
+            r = ref.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, prm)
+            o = om.build_plane_residuals(sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last, prm, debug=True)
+            assert o.num_fragile == 0
+            assert r["success"] == o.success and r["num_residuals_used"] == o.num_residuals
+            assert np.array_equal(r["rows"], o.plane[o.status == 2][:, :15]) and r["loss_sum"] == o.loss_sum
+            total += o.num_residuals
+    assert total > 5000
+
+
+# ---- config 4 in miniature: insert, register the next sweep, insert it — all through the reference's member functions --
+def test_streaming_insert_then_register_equals_the_oracle():
+    ref = Rf.Reference(); om = O.OracleMap()
+    prm = O.r3live_params(max_num_residuals=BIG)
+    e_r = e_o = None
+    for i in range(4):
+        sw = synth.make_sweep(6000, seed=3300 + i, yaw=0.5, position=(-4.0 + 1.0 * i, 3.0, 1.8))
+        if i >= 2:                                                            # the first sweeps only build the map
+            e0 = O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=synth.prior_covariance())
+            r = ref.update_iekf(sw.raw_xyz, e0, sw.t_last, prm)
+            o = om.update_iekf(sw.raw_xyz, e0, sw.t_last, prm)
+            assert r["success"] and o["success"] and r["num_residuals_used"] == o["num_residuals_used"]
+            _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
+            assert np.linalg.norm(r["eskf"].p - sw.t_true) < 0.03
+        reg = synth.registered_points(sw)
+        assert ref.add_points_to_map(reg) == om.add_points(reg)
+    s = ref.snapshot(); k, c, x = om.snapshot()
+    da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(k, c, x)
+    assert da.keys() == db.keys() and all(np.array_equal(da[key], db[key]) for key in da)
+
+
+def test_many_sweeps_on_host_threads_equal_the_single_calls(sm):
+    """ref_update_iekf_many (the throughput form bench.py's CPU arm times): every sweep's result equals the single-sweep call."""
+    ref, om = _pair(sm)
+    prm = O.r3live_params(max_num_residuals=BIG)
+    rng = np.random.default_rng(17)
+    raws, eskfs, tls = [], [], []
+    for s in range(6):
+        keep = rng.permutation(sm["raw_xyz"].shape[0])[:400]
+        raws.append(sm["raw_xyz"][keep])
+        eskfs.append(O.Eskf(p=sm["t_init"] + rng.normal(0, 0.02, 3), q=sm["q_init"].copy(), cov=sm["prior_cov"].copy()))
+        tls.append(sm["t_last"])
+    ok, out, fq, ft = ref.update_iekf_many(raws, eskfs, tls, prm, n_threads=3)
+    assert ok == 6
+    for s in range(6):
+        one = ref.update_iekf(raws[s], eskfs[s], tls[s], prm)
+        assert np.array_equal(out[s].p, one["eskf"].p) and np.array_equal(out[s].cov, one["eskf"].cov) and np.array_equal(fq[s], one["frame_q"])
