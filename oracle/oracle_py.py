@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package sr_livo_b200 never imports this.
 
-PARITY UNPINNED: see oracle/srl_oracle.h (the reference has no golden vectors for this path).
+PARITY: pinned against the reference's own compiled code (oracle/reference_py.py, tests/test_reference_pin.py) except for the
+arithmetic inside Eigen / OpenCV calls, which stays unpinned — see oracle/srl_oracle.h.
 """
 from __future__ import annotations
 

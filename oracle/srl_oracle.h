@@ -8,11 +8,15 @@
  * and bench.py's cpu_baseline / --impl reference legs can check and time the
  * reference algorithm.  Nothing under sr_livo_b200/ may include, link or call it.
  *
- * PARITY UNPINNED: the reference ships no test, golden vector or fixture for this
- * path and cannot be compiled here (Eigen/PCL/OpenCV/ROS
- * absent), so this restatement is pinned only by its own self-checks
- * (tests/test_oracle_*.py: brute-force kNN, numpy eigh, finite-difference Jacobians,
- * numpy ESIKF algebra).
+ * PARITY: the reference ships no test, golden vector or fixture for this path.  Since round 2 the
+ * restatement is pinned against the REFERENCE'S OWN CODE: oracle/_ref/libsrl_reference.so holds src/optimize.cpp,
+ * utility.cpp, eskfEstimator.cpp, cloudMap.cpp, state.cpp, lioOptimization.cpp, rgbMapTracker.cpp compiled unmodified
+ * from where they lie, over stand-in headers for Eigen / OpenCV / ROS / PCL (oracle/shim/, none of them is in this
+ * image), and tests/test_reference_pin.py compares every function of this file with it (rows of buildPlaneResiduals bit
+ * for bit).  PARITY STILL UNPINNED for the arithmetic INSIDE Eigen / OpenCV calls (reduction order of 3-vector dot
+ * products, SelfAdjointEigenSolver, PartialPivLU, saturating Vec3b operators): oracle/shim restates it the same way
+ * this file does, so those two cannot check each other; the self-checks (tests/test_oracle_selfcheck.py: brute-force
+ * kNN, numpy eigh, finite-difference Jacobians, numpy ESIKF algebra) bound their effect.
  */
 #ifndef SRL_ORACLE_H
 #define SRL_ORACLE_H
