@@ -407,3 +407,20 @@ def test_many_sweeps_on_host_threads_equal_the_single_calls(sm):
     for s in range(6):
         one = ref.update_iekf(raws[s], eskfs[s], tls[s], prm)
         assert np.array_equal(out[s].p, one["eskf"].p) and np.array_equal(out[s].cov, one["eskf"].cov) and np.array_equal(fq[s], one["frame_q"])
+
+
+# ---- a 1.6M-point map (the bench's world, 240 m side) and a sample of a 100k-point sweep: the scale the GPU id tests run at
+def test_mid_scale_sample_equals_the_oracle():
+    pts = synth.sample_map_points(240.0, 60.0, seed=1)
+    om = O.OracleMap(); om.add_points(pts)
+    del pts
+    ref = Rf.Reference(); ref.load(*om.snapshot())
+    assert ref.num_points() == om.num_points > 1_500_000
+    sw = synth.make_sweep(100000, seed=1000, yaw=0.5)
+    pick = np.random.default_rng(1).permutation(100000)[:6000]
+    raw = sw.raw_xyz[pick]
+    prm = O.r3live_params(max_num_residuals=BIG)
+    r = ref.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, prm)
+    o = om.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, prm, debug=True)
+    assert o.num_fragile == 0 and r["num_residuals_used"] == o.num_residuals > 4000
+    assert np.array_equal(r["rows"], o.plane[o.status == 2][:, :15]) and np.array_equal(r["world_xyz"], o.world_xyz)
