@@ -18,20 +18,28 @@ from .oracle_py import Eskf, EskfState, IcpParams, _f64, _ptr, imu_states_array
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PATH = os.path.join(_HERE, "_ref", "libsrl_reference.so")
-_lib = None
+# the same reference objects with updateIEKF / addPointsToMap replaced at link time by the product's C++ adapter (the maintainer
+# patch of INTEGRATION.md section 2: oracle/srl_reference_gpu_patch.cpp); needs a GPU at run time
+PATH_GPU = os.path.join(_HERE, "_ref", "libsrl_reference_gpu.so")
+_libs = {}
 
 
-def available() -> bool:
-    return os.path.exists(PATH)
+def available(gpu: bool = False) -> bool:
+    return os.path.exists(PATH_GPU if gpu else PATH)
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not available():
-        raise RuntimeError("oracle/_ref/libsrl_reference.so missing: run `make -C oracle reference` where /root/reference exists")
-    L = C.CDLL(PATH)
+def lib(gpu: bool = False):
+    if gpu in _libs:
+        return _libs[gpu]
+    if not available(gpu):
+        raise RuntimeError("oracle/_ref/libsrl_reference*.so missing: run `make -C oracle` where /root/reference exists")
+    L = C.CDLL(PATH_GPU if gpu else PATH)
+    if gpu:
+        L.refgpu_map_points.argtypes = [C.c_void_p]
+        L.refgpu_map_points.restype = C.c_int64
+        L.refgpu_map_is_on_gpu.argtypes = [C.c_void_p]
+        L.refgpu_map_is_on_gpu.restype = C.c_int32
+        L.refgpu_release.argtypes = [C.c_void_p]
     P, I64, I32, D = C.c_void_p, C.c_int64, C.c_int32, C.c_double
     L.ref_build_info.restype = C.c_char_p
     L.ref_create.restype = P
@@ -77,7 +85,7 @@ def lib():
     L.ref_color_lists.argtypes = [P, P, P]
     L.ref_color_render.argtypes = [P, P, P, I32, I32, D]
     L.ref_color_render.restype = I64
-    _lib = L
+    _libs[gpu] = L
     return L
 
 
@@ -92,40 +100,51 @@ def voxel_hash(x, y, z) -> int:
 class Reference:
     """One lioOptimization object of the reference (its real constructor over the stub ROS NodeHandle)."""
 
-    def __init__(self):
-        self._h = C.c_void_p(lib().ref_create())
+    def __init__(self, gpu: bool = False):
+        """gpu=True: the link-time patched library (updateIEKF and addPointsToMap run on the GPU through the product's adapter)."""
+        self._L = lib(gpu)
+        self._gpu = gpu
+        self._h = C.c_void_p(self._L.ref_create())
 
     def __del__(self):
         try:
             if self._h:
-                lib().ref_destroy(self._h)
+                if self._gpu:
+                    self._L.refgpu_release(self._h)
+                self._L.ref_destroy(self._h)
                 self._h = None
         except Exception:
             pass
 
+    def gpu_map_points(self) -> int:
+        return int(self._L.refgpu_map_points(self._h))
+
+    def gpu_map_is_on_gpu(self) -> bool:
+        return bool(self._L.refgpu_map_is_on_gpu(self._h))
+
     # ---- maps (which: 0 = voxel_map, 1 = color_voxel_map)
     def num_voxels(self, which=0) -> int:
-        return int(lib().ref_map_num_voxels(self._h, which))
+        return int(self._L.ref_map_num_voxels(self._h, which))
 
     def num_points(self, which=0) -> int:
-        return int(lib().ref_map_num_points(self._h, which))
+        return int(self._L.ref_map_num_points(self._h, which))
 
     def load(self, keys, counts, xyz):
         keys = np.ascontiguousarray(keys, np.int16); counts = np.ascontiguousarray(counts, np.int32); xyz = np.ascontiguousarray(xyz, np.float32)
-        lib().ref_map_load(self._h, _ptr(keys), _ptr(counts), _ptr(xyz), keys.shape[0], xyz.shape[1])
+        self._L.ref_map_load(self._h, _ptr(keys), _ptr(counts), _ptr(xyz), keys.shape[0], xyz.shape[1])
 
     def add_points_to_map(self, world_xyz, voxel_size=1.0, max_num_points_in_voxel=20, min_distance_points=0.15, min_num_points=0,
                           color_voxel_size=0.1, color_max_points=20, color_min_distance=0.01, add_point_step=4,
                           time_sweep_end=1.0, time_last_process=-1e5, to_rendering=False) -> int:
         """lioOptimization::addPointsToMap (src/lioOptimization.cpp:520-554): LIO map and colour map in one call."""
         xyz = _f64(world_xyz).reshape(-1, 3)
-        return int(lib().ref_add_points_to_map(self._h, _ptr(xyz), xyz.shape[0], voxel_size, max_num_points_in_voxel, min_distance_points,
+        return int(self._L.ref_add_points_to_map(self._h, _ptr(xyz), xyz.shape[0], voxel_size, max_num_points_in_voxel, min_distance_points,
                                                min_num_points, color_voxel_size, color_max_points, color_min_distance, add_point_step,
                                                time_sweep_end, time_last_process, 1 if to_rendering else 0))
 
     def remove_far(self, location, distance) -> int:
         loc = _f64(location).reshape(3)
-        return int(lib().ref_map_remove_far(self._h, _ptr(loc), float(distance)))
+        return int(self._L.ref_map_remove_far(self._h, _ptr(loc), float(distance)))
 
     def snapshot(self, which=0, cap=20, color=False):
         nv = self.num_voxels(which)
@@ -135,7 +154,7 @@ class Reference:
             out.update(rgb=np.zeros((nv, cap, 3), np.int16), n_rgb=np.zeros((nv, cap), np.int16), cov=np.zeros((nv, cap, 3), np.float32),
                        obs_dist=np.zeros((nv, cap)), last_obs=np.zeros((nv, cap)), last_visited=np.zeros(nv))
             extra = [_ptr(out[k]) for k in ("rgb", "n_rgb", "cov", "obs_dist", "last_obs", "last_visited")]
-        got = lib().ref_map_snapshot(self._h, which, cap, _ptr(out["keys"]), _ptr(out["counts"]), _ptr(out["xyz"]), *extra)
+        got = self._L.ref_map_snapshot(self._h, which, cap, _ptr(out["keys"]), _ptr(out["counts"]), _ptr(out["xyz"]), *extra)
         assert got == nv
         return out
 
@@ -143,13 +162,13 @@ class Reference:
     def search_neighbors(self, point, nb=1, size=1.0, K=20, thr=1):
         p = _f64(point).reshape(3)
         xyz = np.zeros((K, 3)); vox = np.zeros((K, 3), np.int16)
-        m = lib().ref_search_neighbors(self._h, _ptr(p), nb, size, K, thr, _ptr(xyz), _ptr(vox))
+        m = self._L.ref_search_neighbors(self._h, _ptr(p), nb, size, K, thr, _ptr(xyz), _ptr(vox))
         return xyz[:m].copy(), vox[:m].copy()
 
     def neighborhood(self, pts):
         pts = _f64(pts).reshape(-1, 3)
         out = np.zeros(16)
-        rc = lib().ref_neighborhood(self._h, _ptr(pts), pts.shape[0], _ptr(out))
+        rc = self._L.ref_neighborhood(self._h, _ptr(pts), pts.shape[0], _ptr(out))
         return rc, dict(center=out[0:3], normal=out[3:6], covariance=out[6:15].reshape(3, 3), a2D=out[15])
 
     def build_plane_residuals(self, raw_xyz, q_cur, t_cur, t_last, params: IcpParams, R_il=None, t_il=None):
@@ -159,7 +178,7 @@ class Reference:
         q, t, tl = _f64(q_cur), _f64(t_cur), _f64(t_last)
         ok, used, loss = C.c_int32(0), C.c_int32(0), C.c_double(0)
         rows = np.zeros((n, 15)); world = np.zeros((n, 3))
-        m = lib().ref_build_plane_residuals(self._h, _ptr(raw), n, _ptr(q), _ptr(t), _ptr(tl), _ptr(R), _ptr(ti), C.byref(params),
+        m = self._L.ref_build_plane_residuals(self._h, _ptr(raw), n, _ptr(q), _ptr(t), _ptr(tl), _ptr(R), _ptr(ti), C.byref(params),
                                             C.byref(ok), C.byref(used), C.byref(loss), _ptr(rows), _ptr(world))
         if m < 0:
             return dict(threw=True)
@@ -172,7 +191,7 @@ class Reference:
         tl = _f64(t_last)
         st = eskf.to_c()
         ok, used = C.c_int32(0), C.c_int32(0)
-        rc = lib().ref_update_iekf(self._h, _ptr(raw), raw.shape[0], C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
+        rc = self._L.ref_update_iekf(self._h, _ptr(raw), raw.shape[0], C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
                                    C.byref(params), C.byref(ok), C.byref(used))
         return dict(threw=rc < 0, success=bool(ok.value), num_residuals_used=used.value, eskf=Eskf.from_c(st), frame_q=fq, frame_t=ft)
 
@@ -185,7 +204,7 @@ class Reference:
         fq = np.ascontiguousarray(np.stack([_f64(e.q) for e in eskfs])); ft = np.ascontiguousarray(np.stack([_f64(e.p) for e in eskfs]))
         tl = np.ascontiguousarray(np.stack([_f64(t) for t in t_lasts]))
         R, ti = _ext(R_il, t_il)
-        ok = lib().ref_update_iekf_many(self._h, _ptr(raw), n, ns, C.cast(st, C.c_void_p), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
+        ok = self._L.ref_update_iekf_many(self._h, _ptr(raw), n, ns, C.cast(st, C.c_void_p), _ptr(fq), _ptr(ft), _ptr(tl), _ptr(R), _ptr(ti),
                                         C.byref(params), int(n_threads))
         return int(ok), [Eskf.from_c(s) for s in st], fq, ft
 
@@ -197,25 +216,25 @@ class Reference:
         tl = _f64(t_last)
         st = eskf.to_c()
         ok, used = C.c_int32(0), C.c_int32(0)
-        rc = lib().ref_optimize(self._h, _ptr(world), _ptr(raw), raw.shape[0], float(sample_voxel_size), C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl),
+        rc = self._L.ref_optimize(self._h, _ptr(world), _ptr(raw), raw.shape[0], float(sample_voxel_size), C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl),
                                 _ptr(R), _ptr(ti), C.byref(params), C.byref(ok), C.byref(used))
         return dict(threw=rc < 0, success=bool(ok.value), num_residuals_used=used.value, eskf=Eskf.from_c(st), frame_q=fq, frame_t=ft, world=world)
 
     # ---- colour map
     def color_counts(self):
-        L = lib()
+        L = self._L
         return dict(voxels=self.num_voxels(1), rgb_points=int(L.ref_color_num_rgb_points(self._h)), recent=int(L.ref_color_num_recent(self._h)),
                     new_recent=int(L.ref_color_num_new_recent(self._h)))
 
     def color_lists(self):
         c = self.color_counts()
         rgb_points = np.zeros((c["rgb_points"], 4), np.int16); recent = np.zeros((c["recent"], 3), np.int32)
-        lib().ref_color_lists(self._h, _ptr(rgb_points), _ptr(recent))
+        self._L.ref_color_lists(self._h, _ptr(rgb_points), _ptr(recent))
         return rgb_points, recent
 
     def color_render(self, cam15, image_bgr, obs_time) -> int:
         cam = _f64(cam15).reshape(15); img = np.ascontiguousarray(image_bgr, np.uint8)
-        return int(lib().ref_color_render(self._h, _ptr(cam), _ptr(img), img.shape[0], img.shape[1], float(obs_time)))
+        return int(self._L.ref_color_render(self._h, _ptr(cam), _ptr(img), img.shape[0], img.shape[1], float(obs_time)))
 
 
 def eskf_observe(e: Eskf, dx) -> Eskf:

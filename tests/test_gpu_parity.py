@@ -1154,3 +1154,35 @@ def test_gpu_update_equals_the_compiled_reference(L, small_world):
             assert np.allclose(getattr(L.eskf_pro, f), getattr(r["eskf"], f), rtol=REL, atol=1e-9), f
         assert np.allclose(L.eskf_pro.cov, r["eskf"].cov, rtol=1e-4, atol=1e-12)
         assert np.allclose(fq, r["frame_q"], atol=1e-9) and np.allclose(ft, r["frame_t"], atol=1e-9)
+
+
+def test_reference_runs_on_the_gpu_backend(small_world):
+    """The maintainer patch of INTEGRATION.md section 2, for real: oracle/_ref/libsrl_reference_gpu.so is the reference's own objects
+    with lioOptimization::updateIEKF and ::addPointsToMap replaced at link time by the product's C++ adapter
+    (include/srlivo_b200_lio.hpp -> C ABI -> CUDA).  The reference's unmodified optimize() (gridSampling -> updateIEKF ->
+    transformPoint) then registers a sweep through its own call sites on the GPU; the result equals the unpatched reference's."""
+    Rf = _reference_or_skip()
+    if not Rf.available(gpu=True):
+        pytest.skip("oracle/_ref/libsrl_reference_gpu.so did not travel to this box")
+    pts, sw = small_world["pts"], small_world["sweep"]
+    ref, rg = Rf.Reference(), Rf.Reference(gpu=True)
+    assert ref.add_points_to_map(pts) > 0                       # the reference's own insertion into its host voxelHashMap
+    rg.add_points_to_map(pts)                                   # the same call site, patched: the product's insert kernel
+    assert rg.gpu_map_is_on_gpu() and rg.num_points() == 0 and rg.gpu_map_points() == ref.num_points()
+    P = synth.prior_covariance()
+    world0 = synth.registered_points(sw, sw.q_init, sw.t_init)  # point_frame[i].point as the pose prediction left it
+    for kw in (dict(max_num_residuals=600), dict(max_num_residuals=BIG)):
+        e0 = O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), v=np.array([0.3, 0.0, 0.0]), cov=P.copy())
+        r = ref.optimize(world0, sw.raw_xyz, 1.0, e0, sw.t_last, O.r3live_params(**kw))
+        g = rg.optimize(world0, sw.raw_xyz, 1.0, e0, sw.t_last, O.r3live_params(**kw))
+        assert not g["threw"] and not r["threw"] and g["success"] and r["success"]
+        assert g["num_residuals_used"] == r["num_residuals_used"]
+        for f in ("p", "q", "v", "ba", "bg", "g"):
+            assert np.allclose(getattr(g["eskf"], f), getattr(r["eskf"], f), rtol=REL, atol=1e-9), f
+        assert np.allclose(g["eskf"].cov, r["eskf"].cov, rtol=1e-4, atol=1e-12)
+        assert np.allclose(g["frame_q"], r["frame_q"], atol=1e-9) and np.allclose(g["frame_t"], r["frame_t"], atol=1e-9)
+        assert np.allclose(g["world"], r["world"], rtol=0, atol=1e-6)     # the re-transformed frame (src/optimize.cpp:441-445)
+        assert np.linalg.norm(g["eskf"].p - sw.t_true) < 0.02
+    reg = synth.registered_points(sw)                            # the registered sweep goes into both maps: streaming through the patch
+    ref.add_points_to_map(reg); rg.add_points_to_map(reg)
+    assert rg.gpu_map_points() == ref.num_points()
