@@ -135,15 +135,18 @@ def run_reference(args):
         n_s = min(args.points, 25000)
 
         def batch(n_keypoints, first):
-            idx = [(first + j) % len(sweeps) for j in range(cores)]
-            raws = [sweeps[i].raw_xyz[:n_keypoints] for i in idx]
-            es = [O.Eskf(p=sweeps[i].t_init.copy(), q=sweeps[i].q_init.copy(), cov=P.copy()) for i in idx]
-            tls = [sweeps[i].t_last for i in idx]
+            # every thread registers its own slice of keypoints of ONE sweep (consecutive sweeps of a 10 Hz stream come from
+            # almost the same place: the threads then share the map region in the caches, as the port's keypoint ranges do)
+            sw = sweeps[first % len(sweeps)]
+            n_slices = max(1, sw.raw_xyz.shape[0] // n_keypoints)
+            raws = [sw.raw_xyz[(j % n_slices) * n_keypoints:(j % n_slices + 1) * n_keypoints] for j in range(cores)]
+            es = [O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy()) for j in range(cores)]
+            tls = [sw.t_last] * cores
             t = time.perf_counter()
             ok, out, fq, ft = ref.update_iekf_many(raws, es, tls, prm, n_threads=cores)
             dt = time.perf_counter() - t
             assert ok == cores, (ok, cores)
-            return dt, out, idx
+            return dt, out, [first % len(sweeps)]
         t_w = [batch(n_s, i)[0] for i in range(max(args.warmup, 1))]
         if args.steps * min(t_w) > 150.0:                       # keep the whole run within a few minutes on a slow box
             n_s = max(2000, int(n_s * 150.0 / (args.steps * min(t_w))))
@@ -162,14 +165,24 @@ def run_reference(args):
         po = om.update_iekf(sweeps[idx[0]].raw_xyz[:n_s], O.Eskf(p=sweeps[idx[0]].t_init.copy(), q=sweeps[idx[0]].q_init.copy(), cov=P.copy()),
                             sweeps[idx[0]].t_last, prm, nthreads=cores)
         assert po["passes"] == N_PASSES, po["passes"]
-        t = time.perf_counter()
-        om.update_iekf(sweeps[idx[0]].raw_xyz, O.Eskf(p=sweeps[idx[0]].t_init.copy(), q=sweeps[idx[0]].q_init.copy(), cov=P.copy()),
-                       sweeps[idx[0]].t_last, prm, nthreads=cores)
-        t_port = time.perf_counter() - t
+        # the oracle port on the same host: whole sweeps, keypoint ranges over all threads (the other way to use every core)
+        t_ports = []
+        for i in range(max(3, min(args.steps, 20))):
+            sw = sweeps[(args.warmup + i) % len(sweeps)]
+            t = time.perf_counter()
+            om.update_iekf(sw.raw_xyz, O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy()), sw.t_last, prm, nthreads=cores)
+            t_ports.append(time.perf_counter() - t)
+        port_value = args.points * N_PASSES / (float(np.sum(t_ports[1:])) / (len(t_ports) - 1))
+        ref_value = value
         kind = "reference"
-        sample = (f"{args.steps} batches x {cores} independent sweeps x {n_s} keypoints (prefix of a {args.points}-pt sweep) x {N_PASSES} passes, "
+        sample = (f"{args.steps} batches x {cores} independent sweeps ({n_s}-keypoint slices of one {args.points}-pt sweep per batch) x {N_PASSES} passes, "
                   f"one sweep per host thread through the reference's own single-threaded updateIEKF, shared map")
-        extra = {"single_thread_value": n_s * N_PASSES / t_one, "port_value_all_threads": args.points * N_PASSES / t_port,
+        if port_value > ref_value:
+            # report the stronger CPU number: a ratio against the weaker one would flatter the GPU
+            value, dt, kind = port_value, args.points * N_PASSES / port_value, "port"
+            sample = (f"the oracle port was the faster CPU form on this host: whole {args.points}-keypoint sweeps x {N_PASSES} passes, keypoint ranges over "
+                      f"{cores} std::threads, {len(t_ports) - 1} sweeps; reference_value = " + sample)
+        extra = {"reference_value": ref_value, "port_value": port_value, "single_thread_value": n_s * N_PASSES / t_one,
                  "pose_equals_port": bool(np.allclose(out[0].p, po["eskf"].p, rtol=0, atol=1e-9) and np.allclose(one["eskf"].p, po["eskf"].p, rtol=0, atol=1e-9)),
                  "library": Rf.lib().ref_build_info().decode()}
         container = "tsl::robin_map 0.6.3 (reference vendored header), the reference's own voxelHashMap"
@@ -547,12 +560,12 @@ def main():
             if Rf.available() and os.environ.get("SRL_CPU_ARM", "reference") != "port":
                 ref = Rf.Reference()
                 ref.load(keys, counts, xyz)
-                idx = [j % len(sweeps) for j in range(cores)]
-                raws = [sweeps[i].raw_xyz[:n1] for i in idx]
-                tls = [sweeps[i].t_last for i in idx]
+                n_slices = max(1, sw0.raw_xyz.shape[0] // n1)             # every thread its own keypoint slice of the same sweep
+                raws = [sw0.raw_xyz[(j % n_slices) * n1:(j % n_slices + 1) * n1] for j in range(cores)]
+                tls = [sw0.t_last] * cores
                 t_many = []
                 for rep in range(2):
-                    es = [O.Eskf(p=sweeps[i].t_init.copy(), q=sweeps[i].q_init.copy(), cov=P.copy()) for i in idx]
+                    es = [O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=P.copy()) for j in range(cores)]
                     t0 = time.perf_counter()
                     ok, out, _, _ = ref.update_iekf_many(raws, es, tls, oprm, n_threads=cores)
                     t_many.append(time.perf_counter() - t0)
@@ -561,13 +574,16 @@ def main():
                 t_ref_one = time.perf_counter() - t0
                 po = om.update_iekf(sw0.raw_xyz[:n1], O.Eskf(p=sw0.t_init.copy(), q=sw0.q_init.copy(), cov=P.copy()), sw0.t_last, oprm, nthreads=cores)
                 if ok == cores:
+                    ref_value = cores * n1 * N_PASSES / min(t_many)
                     cpu_baseline.update({
                         "port_value": cpu_baseline["value"], "port_single_thread_value": cpu_baseline["single_thread_value"],
-                        "value": cores * n1 * N_PASSES / min(t_many), "kind": "reference", "single_thread_value": n1 * N_PASSES / t_ref_one,
-                        "sample": f"{cores} independent sweeps x {n1} keypoints (prefix of a {args.points}-pt sweep) x {N_PASSES} passes, one sweep per host "
-                                  f"thread through the reference's own single-threaded updateIEKF (oracle/_ref/libsrl_reference.so), shared map, "
-                                  f"best of 2; single thread: one such sweep; port_*: the oracle port (one {args.points}-keypoint sweep over {cores} std::threads)",
-                        "pose_equals_port": bool(np.allclose(one["eskf"].p, po["eskf"].p, rtol=0, atol=1e-9))})
+                        "reference_value": ref_value, "reference_single_thread_value": n1 * N_PASSES / t_ref_one,
+                        "pose_equals_port": bool(np.allclose(one["eskf"].p, po["eskf"].p, rtol=0, atol=1e-9)),
+                        "sample": cpu_baseline["sample"] + f"; reference_*: the reference's own sources (oracle/_ref/libsrl_reference.so), {cores} independent "
+                                  f"sweeps ({n1}-keypoint slices of the same sweep) x {N_PASSES} passes, one per host thread through its single-threaded "
+                                  f"updateIEKF, shared map, best of 2; value = the faster of the two CPU forms"})
+                    if ref_value > cpu_baseline["value"]:
+                        cpu_baseline.update({"value": ref_value, "kind": "reference", "single_thread_value": n1 * N_PASSES / t_ref_one})
                 del ref
         except Exception as ex:   # the port numbers above stand
             cpu_baseline["reference_library_error"] = repr(ex)[:200]
