@@ -186,7 +186,8 @@ def run_reference(args):
                  "pose_equals_port": bool(np.allclose(out[0].p, po["eskf"].p, rtol=0, atol=1e-9) and np.allclose(one["eskf"].p, po["eskf"].p, rtol=0, atol=1e-9)),
                  "library": Rf.lib().ref_build_info().decode()}
         container = "tsl::robin_map 0.6.3 (reference vendored header), the reference's own voxelHashMap"
-        workload_note = f"; CPU arm sample: {n_s}-keypoint prefix per sweep"
+        workload_note = (f"; sample: {n_s}-keypoint slices of one sweep, one per host thread" if kind == "reference"
+                         else "; whole sweeps, keypoint ranges over the host threads (faster than the compiled reference's one-sweep-per-thread form here)")
     else:
         def step(sw):
             e = O.Eskf(p=sw.t_init.copy(), q=sw.q_init.copy(), cov=P.copy())
