@@ -21,20 +21,26 @@ PATH = os.path.join(_HERE, "_ref", "libsrl_reference.so")
 # the same reference objects with updateIEKF / addPointsToMap replaced at link time by the product's C++ adapter (the maintainer
 # patch of INTEGRATION.md section 2: oracle/srl_reference_gpu_patch.cpp); needs a GPU at run time
 PATH_GPU = os.path.join(_HERE, "_ref", "libsrl_reference_gpu.so")
+# sensitivity build: 3-term reductions of the Eigen stand-in in the other plausible order, (c0 + c1) + c2
+PATH_PACKET = os.path.join(_HERE, "_ref", "libsrl_reference_packet.so")
 _libs = {}
 
 
-def available(gpu: bool = False) -> bool:
-    return os.path.exists(PATH_GPU if gpu else PATH)
+def _path(gpu):
+    return PATH_PACKET if gpu == "packet" else (PATH_GPU if gpu else PATH)
 
 
-def lib(gpu: bool = False):
+def available(gpu=False) -> bool:
+    return os.path.exists(_path(gpu))
+
+
+def lib(gpu=False):
     if gpu in _libs:
         return _libs[gpu]
     if not available(gpu):
         raise RuntimeError("oracle/_ref/libsrl_reference*.so missing: run `make -C oracle` where /root/reference exists")
-    L = C.CDLL(PATH_GPU if gpu else PATH)
-    if gpu:
+    L = C.CDLL(_path(gpu))
+    if gpu is True:
         L.refgpu_map_points.argtypes = [C.c_void_p]
         L.refgpu_map_points.restype = C.c_int64
         L.refgpu_map_is_on_gpu.argtypes = [C.c_void_p]
@@ -100,10 +106,11 @@ def voxel_hash(x, y, z) -> int:
 class Reference:
     """One lioOptimization object of the reference (its real constructor over the stub ROS NodeHandle)."""
 
-    def __init__(self, gpu: bool = False):
-        """gpu=True: the link-time patched library (updateIEKF and addPointsToMap run on the GPU through the product's adapter)."""
+    def __init__(self, gpu=False):
+        """gpu=True: the link-time patched library (updateIEKF and addPointsToMap run on the GPU through the product's adapter);
+        gpu="packet": the sensitivity build (packet-first 3-term reductions in the Eigen stand-in)."""
         self._L = lib(gpu)
-        self._gpu = gpu
+        self._gpu = gpu is True
         self._h = C.c_void_p(self._L.ref_create())
 
     def __del__(self):

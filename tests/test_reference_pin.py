@@ -424,3 +424,39 @@ def test_mid_scale_sample_equals_the_oracle():
     o = om.build_plane_residuals(raw, sw.q_init, sw.t_init, sw.t_last, prm, debug=True)
     assert o.num_fragile == 0 and r["num_residuals_used"] == o.num_residuals > 4000
     assert np.array_equal(r["rows"], o.plane[o.status == 2][:, :15]) and np.array_equal(r["world_xyz"], o.world_xyz)
+
+
+# ---- the one unpinned choice that reaches a discrete outcome: the order of a 3-term reduction inside Eigen ------------------
+@pytest.mark.skipif(not Rf.available("packet"), reason="oracle/_ref/libsrl_reference_packet.so not built")
+def test_no_discrete_outcome_depends_on_the_order_of_three_term_reductions(sm):
+    """oracle/_ref/libsrl_reference_packet.so = the same reference sources over the stand-in with dot / norm / product rows of three
+    terms evaluated as (c0 + c1) + c2 (what a vectorised Eigen 3.3 most likely does for plain Vector3d operands) instead of
+    c0 + (c1 + c2) (what the oracle, the default stand-in and the CUDA kernels do).  Transformed keypoints and distances move by an
+    ulp; the accepted keypoints, their 20 neighbours (same map points, same order) and the final pose do not change on any scene."""
+    scenes = [(sm["map_keys"], sm["map_counts"], sm["map_xyz"], sm["raw_xyz"], sm["q_init"], sm["t_init"], sm["t_last"])]
+    om = O.OracleMap(); om.add_points(synth.sample_map_points(80.0, 40.0, seed=3))
+    sw = synth.make_sweep(3000, seed=3100, yaw=0.4)
+    scenes.append((*om.snapshot(), sw.raw_xyz, sw.q_init, sw.t_init, sw.t_last))
+    moved = 0
+    for keys, counts, xyz, raw, q, t, tl in scenes:
+        a, b = Rf.Reference(), Rf.Reference("packet")
+        a.load(keys, counts, xyz); b.load(keys, counts, xyz)
+        for kw in (dict(max_num_residuals=BIG), dict(max_num_residuals=BIG, frame_id=5), dict(max_num_residuals=600)):
+            prm = O.r3live_params(**kw)
+            ra, rb = a.build_plane_residuals(raw, q, t, tl, prm), b.build_plane_residuals(raw, q, t, tl, prm)
+            assert ra["num_residuals_used"] == rb["num_residuals_used"] and ra["rows"].shape == rb["rows"].shape
+            assert np.array_equal(ra["rows"][:, 0:3], rb["rows"][:, 0:3])                       # the same keypoints were accepted, in order
+            assert np.allclose(ra["rows"], rb["rows"], rtol=1e-11, atol=1e-13)
+            assert np.abs(ra["world_xyz"] - rb["world_xyz"]).max() < 1e-13
+            moved += int((ra["world_xyz"] != rb["world_xyz"]).sum())
+        nb = 0
+        for k in range(0, raw.shape[0], 5):                                                       # neighbour lists: identical map points, identical order
+            xa, va = a.search_neighbors(ra["world_xyz"][k]); xb, vb = b.search_neighbors(rb["world_xyz"][k])
+            assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+            nb += xa.shape[0] == 20
+        assert nb > 50
+        e0 = O.Eskf(p=t.copy(), q=q.copy(), cov=synth.prior_covariance())
+        ua, ub = a.update_iekf(raw, e0, tl, O.r3live_params(max_num_residuals=BIG)), b.update_iekf(raw, e0, tl, O.r3live_params(max_num_residuals=BIG))
+        assert ua["success"] and ub["success"] and ua["num_residuals_used"] == ub["num_residuals_used"]
+        assert np.allclose(ua["eskf"].p, ub["eskf"].p, rtol=0, atol=1e-11) and np.allclose(ua["eskf"].q, ub["eskf"].q, rtol=0, atol=1e-12)
+    assert moved > 100          # the two orders do differ in the last place — the test is not vacuous
