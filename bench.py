@@ -147,9 +147,12 @@ def run_reference(args):
             dt = time.perf_counter() - t
             assert ok == cores, (ok, cores)
             return dt, out, [first % len(sweeps)]
-        t_w = [batch(n_s, i)[0] for i in range(max(args.warmup, 1))]
-        if args.steps * min(t_w) > 150.0:                       # keep the whole run within a few minutes on a slow box
-            n_s = max(2000, int(n_s * 150.0 / (args.steps * min(t_w))))
+        t_probe = batch(n_s, 0)[0]                               # first warm-up batch, also sizes the sample:
+        budget_s = 45.0                                           # all warm-up + timed batches together stay near this
+        if (args.steps + args.warmup) * t_probe > budget_s:
+            n_s = max(2000, int(n_s * budget_s / ((args.steps + args.warmup) * t_probe)) // 32 * 32)
+        for i in range(1, max(args.warmup, 1)):
+            batch(n_s, i)
         ts = []
         for i in range(args.steps):
             dt_i, out, idx = batch(n_s, args.warmup + i)
