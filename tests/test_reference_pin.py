@@ -460,3 +460,35 @@ def test_no_discrete_outcome_depends_on_the_order_of_three_term_reductions(sm):
         assert ua["success"] and ub["success"] and ua["num_residuals_used"] == ub["num_residuals_used"]
         assert np.allclose(ua["eskf"].p, ub["eskf"].p, rtol=0, atol=1e-11) and np.allclose(ua["eskf"].q, ub["eskf"].q, rtol=0, atol=1e-12)
     assert moved > 100          # the two orders do differ in the last place — the test is not vacuous
+
+
+# ---- exact distance ties and keypoints on cell boundaries: the heap's behaviour among equal distances is the reference's own ----
+def test_exact_ties_and_cell_boundaries_equal_the_oracle():
+    g = np.arange(-2.0, 4.0, 0.25)
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    lattice = lattice[np.random.default_rng(2).permutation(lattice.shape[0])]
+    ref = Rf.Reference(); om = O.OracleMap()
+    assert ref.add_points_to_map(lattice, 1.0, 20, 0.15, 0) == om.add_points(lattice, 1.0, 20, 0.15, 0)
+    s = ref.snapshot(); k, c, x = om.snapshot()
+    assert np.array_equal(s["keys"], k) and np.array_equal(s["xyz"], x) if _tsl() else True
+    # keypoints on lattice points, on cell faces / edges / corners (exact integers), at cell centres, and on the doubled cell 0
+    kp = np.concatenate([lattice[:300], np.stack(np.meshgrid([-1.0, 0.0, 1.0, 2.0], [0.0, 1.0, 0.5], [1.0, 1.5, -0.0], indexing="ij"), -1).reshape(-1, 3),
+                         np.array([[0.999999999999, 0.5, 0.5], [-0.999999999999, 0.5, 0.5], [1e-300, -1e-300, 0.5]])])
+    q, t = np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3)
+    for kw in (dict(max_num_residuals=BIG), dict(max_num_residuals=BIG, frame_id=5), dict(max_num_residuals=BIG, max_dist_to_plane_icp=10.0)):
+        prm = O.r3live_params(**kw)
+        r = ref.build_plane_residuals(kp, q, t, np.array([-5.0, 0.3, 0.2]), prm)
+        o = om.build_plane_residuals(kp, q, t, np.array([-5.0, 0.3, 0.2]), prm, debug=True)
+        assert o.num_fragile > 100                                            # ties and boundaries everywhere: exactly what the other tests exclude
+        if r["threw"]:
+            assert o.nan_planarity
+            continue
+        assert r["num_residuals_used"] == o.num_residuals and np.array_equal(r["world_xyz"], o.world_xyz)
+        assert np.array_equal(r["rows"], o.plane[o.status == 2][:, :15])
+    blocks = _as_dict(k, c, x)
+    o = om.build_plane_residuals(kp, q, t, np.array([-5.0, 0.3, 0.2]), O.r3live_params(max_num_residuals=BIG), debug=True)
+    for i in range(0, kp.shape[0], 3):                                        # the neighbour lists themselves, ties included
+        xyz, vox = ref.search_neighbors(kp[i])
+        if o.status[i] >= 1:
+            want = np.array([blocks[tuple(v[:3])][v[3]] for v in o.nbr[i].tolist()], np.float64)
+            assert np.array_equal(xyz, want) and np.array_equal(vox, o.nbr[i][:, :3])
