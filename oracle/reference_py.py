@@ -76,6 +76,9 @@ def lib(gpu=False):
     L.ref_update_iekf.restype = I32
     L.ref_update_iekf_many.argtypes = [P, P, I64, I32, P, P, P, P, P, P, C.POINTER(IcpParams), I32]
     L.ref_update_iekf_many.restype = I32
+    L.ref_stream_reset.argtypes = [P]
+    L.ref_stream_push.argtypes = [P, P, I64, I32, P, P, C.POINTER(EskfState), P, P, C.POINTER(IcpParams), P, P, C.POINTER(I32), C.POINTER(I32), P, P, P]
+    L.ref_stream_push.restype = I32
     L.ref_optimize.argtypes = [P, P, P, I64, D, C.POINTER(EskfState), P, P, P, P, P, C.POINTER(IcpParams), C.POINTER(I32), C.POINTER(I32)]
     L.ref_optimize.restype = I32
     L.ref_eskf_observe.argtypes = [C.POINTER(EskfState), P]
@@ -225,6 +228,27 @@ class Reference:
         ok, used = C.c_int32(0), C.c_int32(0)
         rc = self._L.ref_optimize(self._h, _ptr(world), _ptr(raw), raw.shape[0], float(sample_voxel_size), C.byref(st), _ptr(fq), _ptr(ft), _ptr(tl),
                                 _ptr(R), _ptr(ti), C.byref(params), C.byref(ok), C.byref(used))
+        return dict(threw=rc < 0, success=bool(ok.value), num_residuals_used=used.value, eskf=Eskf.from_c(st), frame_q=fq, frame_t=ft, world=world)
+
+    # ---- the caller: stateEstimation over a stream of sweeps
+    def stream_reset(self):
+        self._L.ref_stream_reset(self._h)
+
+    def stream_push(self, raw_xyz, index_frame, q_pred, t_pred, eskf: Eskf, params: IcpParams, R_il=None, t_il=None, init_voxel_size=0.2,
+                    init_sample_voxel_size=1.0, voxel_size=0.5, sample_voxel_size=1.5, min_distance_points=0.1, init_num_frames=20,
+                    max_num_points_in_voxel=20):
+        """One sweep through lioOptimization::stateEstimation (src/lioOptimization.cpp:983-1035): optimize() for frames after the
+        first, then addPointsToMap; the odometryOptions defaults are include/parameters.h:58-95."""
+        raw = _f64(raw_xyz).reshape(-1, 3)
+        R, ti = _ext(R_il, t_il)
+        qp, tp = _f64(q_pred), _f64(t_pred)
+        st = eskf.to_c()
+        odo_d = _f64([init_voxel_size, init_sample_voxel_size, voxel_size, sample_voxel_size, min_distance_points])
+        odo_i = np.ascontiguousarray([init_num_frames, max_num_points_in_voxel], np.int32)
+        ok, used = C.c_int32(0), C.c_int32(0)
+        fq, ft, world = np.zeros(4), np.zeros(3), np.zeros_like(raw)
+        rc = self._L.ref_stream_push(self._h, _ptr(raw), raw.shape[0], int(index_frame), _ptr(qp), _ptr(tp), C.byref(st), _ptr(R), _ptr(ti),
+                                     C.byref(params), _ptr(odo_d), _ptr(odo_i), C.byref(ok), C.byref(used), _ptr(fq), _ptr(ft), _ptr(world))
         return dict(threw=rc < 0, success=bool(ok.value), num_residuals_used=used.value, eskf=Eskf.from_c(st), frame_q=fq, frame_t=ft, world=world)
 
     # ---- colour map

@@ -416,6 +416,71 @@ int32_t ref_update_iekf_many(void* ctx, const double* raw_xyz, int64_t n, int32_
     return ok.load();
 }
 
+// ---- the caller of the path: lioOptimization::stateEstimation (src/lioOptimization.cpp:983-1035) over a stream of sweeps ----------
+// ref_stream_reset forgets the frames pushed so far (all_cloud_frame) and empties both maps.
+void ref_stream_reset(void* ctx) {
+    RefCtx* c = static_cast<RefCtx*>(ctx);
+    for (cloudFrame* f : c->frames) delete f;
+    for (state* s : c->states) delete s;
+    c->frames.clear(); c->states.clear();
+    c->lio->all_cloud_frame.clear();
+    c->lio->voxel_map.clear();
+    c->lio->color_voxel_map.clear();
+}
+// One sweep through stateEstimation.  The frame is built the way buildFrame (src/lioOptimization.cpp:800-893) leaves it for the
+// estimator: point = the raw point under the predicted pose (identity for the first two frames, :866-878), id = position in
+// all_cloud_frame, frame_id = index_frame.  odo: init_voxel_size, init_sample_voxel_size, voxel_size, sample_voxel_size,
+// min_distance_points (doubles) ; init_num_frames, max_num_points_in_voxel (ints).  prm carries the icpOptions; its frame_id is ignored.
+// Outputs: the frame's pose, the filter, the re-transformed points (world_out, n*3).  Returns 0, or -1 on the NaN throw.
+int32_t ref_stream_push(void* ctx, const double* raw_xyz, int64_t n, int32_t index_frame, const double q_pred[4], const double t_pred[3],
+                        orc_eskf_state* eskf, const double R_il[9], const double t_il[3], const orc_icp_params* prm, const double odo_d[5],
+                        const int32_t odo_i[2], int32_t* success, int32_t* num_residuals_used, double frame_q[4], double frame_t[3], double* world_out) {
+    RefCtx* c = static_cast<RefCtx*>(ctx);
+    lioOptimization* L = c->lio;
+    set_extrinsics(c, R_il, t_il);
+    L->laser_point_cov = prm->laser_point_cov;
+    L->odometry_options.init_voxel_size = odo_d[0];
+    L->odometry_options.init_sample_voxel_size = odo_d[1];
+    L->odometry_options.voxel_size = odo_d[2];
+    L->odometry_options.sample_voxel_size = odo_d[3];
+    L->odometry_options.min_distance_points = odo_d[4];
+    L->odometry_options.init_num_frames = odo_i[0];
+    L->odometry_options.max_num_points_in_voxel = odo_i[1];
+    L->odometry_options.optimize_options = make_options(prm);
+    L->odometry_options.optimize_options.init_num_frames = odo_i[0];       // initialValue(), src/lioOptimization.cpp:391
+    L->map_options.add_point_step = 1 << 30;                               // the colour map is not part of this check
+    eskf_from_c(L->eskf_pro, eskf);
+    state* st = new state();
+    st->rotation = q4(q_pred);
+    st->translation = v3(t_pred);
+    std::vector<point3D> pts((size_t)n);
+    Eigen::Quaterniond qp = index_frame > 2 ? q4(q_pred) : Eigen::Quaterniond::Identity();
+    Eigen::Vector3d tp = index_frame > 2 ? v3(t_pred) : Eigen::Vector3d(Eigen::Vector3d::Zero());
+    for (int64_t i = 0; i < n; ++i) {
+        pts[(size_t)i].raw_point = v3(raw_xyz + 3 * i);
+        transformPoint(pts[(size_t)i], qp, tp, L->R_imu_lidar, L->t_imu_lidar);
+    }
+    cloudFrame* frame = new cloudFrame(pts, st);
+    frame->id = (int)L->all_cloud_frame.size();
+    frame->sub_id = 0;
+    frame->frame_id = index_frame;
+    frame->time_sweep_end = 0.1 * index_frame;
+    L->index_frame = index_frame;
+    L->all_cloud_frame.push_back(frame);
+    c->frames.push_back(frame); c->states.push_back(st);
+    optimizeSummary summary;
+    try {
+        summary = L->stateEstimation(frame, false);
+    } catch (const std::runtime_error&) { return -1; }
+    *success = (index_frame > 1) ? (summary.success ? 1 : 0) : 1;           // frame 1 runs no optimisation: the default-constructed summary says false
+    *num_residuals_used = summary.num_residuals_used;
+    eskf_to_c(L->eskf_pro, eskf);
+    putq(frame_q, frame->p_state->rotation);
+    put3(frame_t, frame->p_state->translation);
+    for (int64_t i = 0; i < n; ++i) put3(world_out + 3 * i, frame->point_frame[(size_t)i].point);
+    return 0;
+}
+
 void ref_eskf_observe(orc_eskf_state* s, const double dx[17]) {   // eskfEstimator::observe (src/eskfEstimator.cpp:219-230)
     eskfEstimator e;
     eskf_from_c(&e, s);

@@ -492,3 +492,57 @@ def test_exact_ties_and_cell_boundaries_equal_the_oracle():
         if o.status[i] >= 1:
             want = np.array([blocks[tuple(v[:3])][v[3]] for v in o.nbr[i].tolist()], np.float64)
             assert np.array_equal(xyz, want) and np.array_equal(vox, o.nbr[i][:, :3])
+
+
+# ---- the caller of the path: stateEstimation over a stream (src/lioOptimization.cpp:983-1035) ------------------------------------------
+def _rel_pose(q0, t0, q, t):
+    """pose (q, t) expressed in the frame of pose (q0, t0)"""
+    R0 = synth.quat_to_rot(q0)
+    q0_inv = np.array([-q0[0], -q0[1], -q0[2], q0[3]])
+    return synth._quat_mul_xyzw(q0_inv, q), R0.T @ (t - t0)
+
+
+def test_state_estimation_stream_equals_the_composition_of_oracle_pieces():
+    """Seven sweeps through the reference's own stateEstimation — frame 1 only fills the map, frames 2-3 run with the init-frame
+    parameters (nb = 2, >= 15 iterations, init_sample_voxel_size), the rest with the steady ones — against gridSampling -> updateIEKF ->
+    transformPoint -> addPointsToMap composed from the oracle's pieces with the same per-frame switches (the Python the GPU tests use)."""
+    n_frames, init_num_frames, n = 7, 4, 5000
+    sweeps = [synth.make_sweep(n, seed=3500 + i, yaw=0.2, position=(0.05 * i, 3.0, 1.8), dp_max=0.03, dth_max_deg=0.3) for i in range(n_frames)]
+    q0, t0 = sweeps[0].q_true, sweeps[0].t_true
+    ref = Rf.Reference(); ref.stream_reset()
+    om = O.OracleMap()
+    P = synth.prior_covariance()
+    t_prev = None
+    for k, sw in enumerate(sweeps, start=1):
+        if k <= 2:
+            q_pred, t_pred = np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3)        # stateInitialization: identity for the first two frames
+        else:
+            q_pred, t_pred = _rel_pose(q0, t0, sw.q_init, sw.t_init)            # a perturbed prediction in the frame of sweep 0
+        e0 = O.Eskf(p=t_pred.copy(), q=q_pred.copy(), cov=P.copy())
+        prm = O.r3live_params(frame_id=k, init_num_frames=init_num_frames)      # yaml cap 600
+        r = ref.stream_push(sw.raw_xyz, k, q_pred, t_pred, e0, prm, init_num_frames=init_num_frames)
+        assert not r["threw"] and r["success"]
+        # the same step from the oracle's pieces
+        if k > 1:
+            world_pred = sw.raw_xyz if k <= 2 else Rf.transform_point(sw.raw_xyz, q_pred, t_pred)
+            idx = O.grid_sampling(world_pred, 1.0 if k < init_num_frames else 1.5)
+            o = om.update_iekf(sw.raw_xyz[idx], e0, t_prev, prm, frame_q=q_pred, frame_t=t_pred)
+            assert o["success"] and o["num_residuals_used"] == r["num_residuals_used"]
+            assert o["passes"] >= (2 if k >= init_num_frames else 2)
+            _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
+            assert np.allclose(r["frame_q"], o["frame_q"], atol=1e-11) and np.allclose(r["frame_t"], o["frame_t"], atol=1e-11)
+            world = Rf.transform_point(sw.raw_xyz, o["frame_q"], o["frame_t"])
+            assert np.allclose(r["world"], world, rtol=0, atol=1e-9)
+            t_prev = o["frame_t"].copy()
+            if k > 2:                                                            # registration pulls the perturbed prediction back to the truth
+                q_true, t_true = _rel_pose(q0, t0, sw.q_true, sw.t_true)
+                assert np.linalg.norm(o["frame_t"] - t_true) < 0.02
+        else:
+            world = sw.raw_xyz.copy()                                            # frame 1: identity, no optimisation (:1010-1019)
+            assert np.array_equal(r["world"], world) and np.array_equal(r["frame_t"], np.zeros(3))
+            t_prev = np.zeros(3)
+        om.add_points(r["world"], 1.0, 20, 0.1, 0)                               # odometryOptions::min_distance_points = 0.1
+        assert ref.num_points() == om.num_points
+    s = ref.snapshot(); kk, cc, xx = om.snapshot()
+    da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(kk, cc, xx)
+    assert da.keys() == db.keys() and all(np.array_equal(da[key], db[key]) for key in da)
