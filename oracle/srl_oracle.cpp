@@ -5,9 +5,10 @@
  * and bench.py's cpu_baseline / --impl reference legs.  The product (sr_livo_b200/)
  * never includes, links or calls anything in this directory.
  *
- * PARITY UNPINNED (see srl_oracle.h): the reference has no tests/golden vectors for
- * this path and cannot be built here; this file restates the algorithm line by line
- * and is pinned by self-checks only.
+ * PARITY (see srl_oracle.h): the reference has no tests/golden vectors for this path; this
+ * file restates the algorithm line by line and is pinned against the reference's own sources
+ * compiled where they lie (oracle/_ref/libsrl_reference.so, tests/test_reference_pin.py) and by
+ * self-checks.  PARITY UNPINNED only for the arithmetic inside Eigen / OpenCV calls.
  *
  * What is restated, with the reference location each piece follows
  * (paths relative to /root/reference):
@@ -1303,7 +1304,7 @@ int32_t orc_mat17_inverse(const double* A, double* Ainv) { return mat_inverse(A,
 //   rgbPoint::updateRgb                           src/cloudMap.cpp:59-101
 // Third-party arithmetic absent from /root/reference: OpenCV's cv::Vec3b operators (double * Vec3b and
 // Vec3b + Vec3b saturate every element to uchar with cvRound = round-half-to-even) — restated from
-// OpenCV 4's matx.hpp / saturate.hpp; PARITY UNPINNED like the rest of the oracle.
+// OpenCV 4's matx.hpp / saturate.hpp; PARITY UNPINNED for that arithmetic (the stand-in cv::Vec3b of oracle/shim restates it the same way).
 // ======================================================================================
 struct voxelId { int kx, ky, kz; };   // include/cloudMap.h:88-95
 struct ColorMap {

@@ -1,6 +1,7 @@
-"""Generates tests/golden/*.npz with the CPU oracle (the reference itself cannot be built or imported here and
-ships no vectors of its own: SURVEY.md §8(c)), so these fixtures pin the ORACLE's outputs — parity stays
-"unpinned" with respect to the reference.  Run from the repo root:  python tests/golden/make_golden.py
+"""Generates tests/golden/{scan_matching,map_insert,sweep_prep}.npz with the CPU oracle (the reference ships no vectors of its
+own: SURVEY.md §8(c)): inputs plus the ORACLE's outputs incl. the neighbour ids the reference never exposes.  The outputs of the
+reference's own compiled code on the same inputs are in reference_outputs.npz (make_reference_golden.py); tests/test_golden.py
+checks the oracle and the CUDA path against both.  Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys
