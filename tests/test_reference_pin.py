@@ -546,3 +546,16 @@ def test_state_estimation_stream_equals_the_composition_of_oracle_pieces():
     s = ref.snapshot(); kk, cc, xx = om.snapshot()
     da, db = _as_dict(s["keys"], s["counts"], s["xyz"]), _as_dict(kk, cc, xx)
     assert da.keys() == db.keys() and all(np.array_equal(da[key], db[key]) for key in da)
+
+
+def test_threaded_oracle_port_equals_the_compiled_reference(sm):
+    """The form of the oracle bench.py times on all host threads (keypoint ranges over std::threads, private sums, fixed-order combine)
+    against the single-threaded reference: same residuals, state to 1e-9."""
+    ref, om = _pair(sm)
+    prm = O.r3live_params(max_num_residuals=BIG)
+    e0 = O.Eskf(p=sm["t_init"].copy(), q=sm["q_init"].copy(), cov=sm["prior_cov"].copy())
+    r = ref.update_iekf(sm["raw_xyz"], e0, sm["t_last"], prm)
+    for nt in (2, 5, 8):
+        o = om.update_iekf(sm["raw_xyz"], e0, sm["t_last"], prm, nthreads=nt)
+        assert o["success"] and o["num_residuals_used"] == r["num_residuals_used"]
+        _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
