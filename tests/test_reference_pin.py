@@ -559,3 +559,40 @@ def test_threaded_oracle_port_equals_the_compiled_reference(sm):
         o = om.update_iekf(sm["raw_xyz"], e0, sm["t_last"], prm, nthreads=nt)
         assert o["success"] and o["num_residuals_used"] == r["num_residuals_used"]
         _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-9, atol=1e-11)
+
+
+# ---- a seeded sweep over the parameter space (icpOptions the yaml files never set included) --------------------------------------------
+def test_random_parameter_sets_equal_the_oracle():
+    rng = np.random.default_rng(77)
+    pts = synth.sample_map_points(80.0, 50.0, seed=9)
+    sw = synth.make_sweep(1500, seed=3700, yaw=-0.7, position=(2.0, -3.0, 1.6))
+    maps = {}
+    checked = 0
+    for trial in range(36):
+        size = [0.5, 1.0, 2.0][trial % 3]
+        cap = [20, 8, 32][(trial // 3) % 3]
+        if (size, cap) not in maps:
+            ref = Rf.Reference(); om = O.OracleMap()
+            assert ref.add_points_to_map(pts, size, cap, 0.07 * size, 0) == om.add_points(pts, size, cap, 0.07 * size, 0)
+            maps[(size, cap)] = (ref, om)
+        ref, om = maps[(size, cap)]
+        kmax = int(rng.choice([5, 10, 20, 30]))
+        kw = dict(size_voxel_map=size, max_number_neighbors=kmax, min_number_neighbors=int(rng.integers(3, kmax + 1)),
+                  threshold_voxel_occupancy=int(rng.choice([1, 2, 5])), voxel_neighborhood=int(rng.choice([0, 1, 2])),
+                  power_planarity=float(rng.choice([0.5, 1.0, 2.0, 3.0])), max_dist_to_plane_icp=float(rng.choice([0.05, 0.3, 1.0])),
+                  weight_alpha=float(rng.uniform(-1, 1)), weight_neighborhood=float(rng.uniform(0.05, 1)),
+                  max_num_residuals=int(rng.choice([BIG, 600, 50, -1])), frame_id=int(rng.choice([1, 5, 19, 20, 100])),
+                  init_num_frames=int(rng.choice([0, 20])))
+        prm = O.r3live_params(**kw)
+        dq = synth.quat_from_rotvec(rng.normal(0, 0.01, 3))
+        q = synth.quat_mul(sw.q_true, dq); t = sw.t_true + rng.normal(0, 0.05, 3)
+        r = ref.build_plane_residuals(sw.raw_xyz, q, t, sw.t_last, prm)
+        o = om.build_plane_residuals(sw.raw_xyz, q, t, sw.t_last, prm, debug=True)
+        assert r["threw"] == bool(o.nan_planarity), kw
+        if r["threw"]:
+            continue
+        assert r["success"] == o.success and r["num_residuals_used"] == o.num_residuals, kw
+        assert np.array_equal(r["rows"], o.plane[o.status == 2][:, :15]), kw
+        assert r["loss_sum"] == o.loss_sum
+        checked += r["rows"].shape[0]
+    assert checked > 5000
