@@ -596,3 +596,25 @@ def test_random_parameter_sets_equal_the_oracle():
         assert r["loss_sum"] == o.loss_sum
         checked += r["rows"].shape[0]
     assert checked > 5000
+
+
+def test_random_update_parameter_sets_equal_the_oracle(sm):
+    ref, om = _pair(sm)
+    rng = np.random.default_rng(78)
+    n_ok = 0
+    for trial in range(16):
+        kw = dict(max_num_residuals=int(rng.choice([BIG, 600, 200])), num_iters_icp=int(rng.choice([1, 2, 5, 8])),
+                  threshold_translation_norm=float(rng.choice([0.0, 0.001, 0.01, 0.2])), threshold_orientation_norm=float(rng.choice([0.0, 0.01, 0.1, 2.0])),
+                  frame_id=int(rng.choice([1, 2, 5, 100])), init_num_frames=int(rng.choice([0, 20])), laser_point_cov=float(rng.choice([0.001, 0.01, 0.0001])),
+                  max_dist_to_plane_icp=float(rng.choice([0.1, 0.3])), power_planarity=float(rng.choice([1.0, 2.0])))
+        prm = O.r3live_params(**kw)
+        e0 = O.Eskf(p=sm["t_init"] + rng.normal(0, 0.03, 3), q=synth.quat_mul(sm["q_init"], synth.quat_from_rotvec(rng.normal(0, 0.004, 3))),
+                    v=rng.normal(0, 0.5, 3), ba=rng.normal(0, 0.02, 3), bg=rng.normal(0, 0.002, 3), g=np.array([0.0, 0.0, 9.81]) + rng.normal(0, 0.05, 3),
+                    cov=sm["prior_cov"] * float(rng.choice([0.1, 1.0, 10.0])))
+        r = ref.update_iekf(sm["raw_xyz"], e0, sm["t_last"], prm)
+        o = om.update_iekf(sm["raw_xyz"], e0, sm["t_last"], prm)
+        assert not r["threw"] and r["success"] == o["success"] and r["num_residuals_used"] == o["num_residuals_used"], kw
+        _assert_eskf_equal(r["eskf"], o["eskf"], rtol=1e-8, atol=1e-10)
+        assert np.allclose(r["frame_q"], o["frame_q"], atol=1e-10) and np.allclose(r["frame_t"], o["frame_t"], atol=1e-10), kw
+        n_ok += r["success"]
+    assert n_ok >= 12
